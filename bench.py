@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the foveated resampling path (grid -> grid_sample -> inverse fill) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic frames:
+    S1 saliency -> grid, S2 grid_sample(image, grid), S3 scatter + point selection + Delaunay + walk hints +
+    value table + fused inverse fill writing the [B,C,H,W] score tensor (the reference's `pred_sampled`).
+`value`  : whole-job frames/s with inputs resident in HBM (device-timed, max over ranks).
+`e2e`    : the same path through the public API with HOST (pinned) buffers: H2D of image/saliency/pred every
+           step, the path with the fused argmax, D2H of the int64 instance masks.
+`roofline`: the dominant kernel (inverse_fill): algorithmic bytes 4*C*H*W per frame / measured launch duration
+           against the measured HBM copy ceiling in MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the reference's own CPU formulation of the path (oracle/reference_port.py:
+           the same torch CPU ops + host Qhull the reference runs) timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "foveated-instance-segmentation_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: batch 64 of 1024x1024, 51-class head, saliency/task 80x80, gaussian_radius 45
+    "b64_1024": dict(B=64, H=1024, W=1024, C=51, g=80, R=45),
+    # configs[2] per-GPU shard: 64 frames of 2048x2048 (512 over 8 GPUs)
+    "b64_2048": dict(B=64, H=2048, W=2048, C=51, g=80, R=45),
+    # configs[4] per-GPU shard: 16 frames of 4096x4096
+    "b16_4096": dict(B=16, H=4096, W=4096, C=51, g=80, R=45),
+    "tiny": dict(B=4, H=256, W=256, C=51, g=80, R=45),
+}
+KERNELS_PER_STEP = 8  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay, locate_hints, box4_table, inverse_fill
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def make_inputs(cfg, seed, device=None, pinned=False):
+    from oracle.reference_port import synthetic_saliency, synthetic_pred  # input generators only
+    B, H, W, C, g = cfg["B"], cfg["H"], cfg["W"], cfg["C"], cfg["g"]
+    gen = torch.Generator().manual_seed(seed)
+    xs, gaze = synthetic_saliency(B, g, g, seed=seed)
+    pred = synthetic_pred(B, C, g, g, seed=seed)
+    # image ~ U[0,1): generated per frame to bound host memory, written straight into the destination buffer
+    if device is not None:
+        x = torch.empty(B, 3, H, W, device=device)
+        for b in range(B):
+            x[b].copy_(torch.rand(3, H, W, generator=gen))
+        return x, xs.to(device), pred.to(device)
+    x = torch.empty(B, 3, H, W, pin_memory=pinned)
+    for b in range(B):
+        x[b].copy_(torch.rand(3, H, W, generator=gen))
+    if pinned:
+        xs, pred = xs.pin_memory(), pred.pin_memory()
+    return x, xs, pred
+
+
+class Path:
+    """The product path as a user drives it (fovea.ops), with every output buffer allocated once."""
+
+    def __init__(self, cfg, device, triangulation):
+        from fovea import ops
+        from oracle.reference_port import gaussian_filter_weight  # constant construction only (models.py:510-515)
+        self.ops, self.cfg, self.dev, self.tri = ops, cfg, device, triangulation
+        R = cfg["R"]
+        self.g1x, self.g1y = (t.to(device) for t in ops.separable_factors(gaussian_filter_weight(R, R, R)))
+        B, C, H, W = cfg["B"], cfg["C"], cfg["H"], cfg["W"]
+        self.scores = torch.empty(B, C, H, W, device=device)
+        self.mask = torch.empty(B, H, W, device=device, dtype=torch.int64)
+        self.fill_ms = []
+
+    def step(self, x, xs, pred, want_scores=True, want_mask=False, time_fill=False):
+        ops, cfg = self.ops, self.cfg
+        g, R = cfg["g"], cfg["R"]
+        grid = ops.saliency_to_grid(xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
+        x_sampled = ops.grid_sample(x, grid)
+        plan = ops.build_inverse_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"], triangulation=self.tri)
+        table_ready = None
+        if time_fill:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            table = ops.box4_table(pred)
+            e0.record()
+            self._fill(plan, pred, table, want_scores, want_mask)
+            e1.record()
+            self.fill_ms.append((e0, e1))
+        else:
+            self._fill(plan, pred, ops.box4_table(pred), want_scores, want_mask)
+        return x_sampled
+
+    def _fill(self, plan, pred, table, want_scores, want_mask):
+        from fovea import _lib
+        from fovea.ops import _ptr, _stream
+        cfg = self.cfg
+        _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
+                  _ptr(plan.tris), _ptr(plan.nbrs), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), cfg["B"], cfg["C"],
+                  table.shape[2], cfg["g"], cfg["g"], cfg["H"], cfg["W"], plan.cap, plan.tcap, 1,
+                  _ptr(self.scores) if want_scores else None, _ptr(self.mask) if want_mask else None, _stream())
+
+
+def cpu_reference_time(cfg, frames, reps, seed=0):
+    """Times oracle.reference_port.reference_hot_path (the reference's CPU formulation) on `frames` frames."""
+    from oracle import reference_port as rp
+    sub = dict(cfg, B=frames)
+    x, xs, pred = make_inputs(sub, seed)
+    torch.set_num_threads(os.cpu_count() or 1)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rp.reference_hot_path(x, xs, pred, cfg["R"], cfg["R"], cfg["R"], (cfg["H"], cfg["W"]))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return frames / best, best
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    frames = 1
+    times = []
+    from oracle import reference_port as rp
+    x, xs, pred = make_inputs(dict(cfg, B=frames), 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rp.reference_hot_path(x, xs, pred, cfg["R"], cfg["R"], cfg["R"], (cfg["H"], cfg["W"]))
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = frames * len(times) / total
+    sample = f"{frames} frame(s) of {cfg['H']}x{cfg['W']}, C={cfg['C']} per step (of the {cfg['B']}-frame batch)"
+    line = {
+        "impl": "reference", "metric": "foveated-resample frames/s", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, **cfg, "stages": "grid+grid_sample+inverse_fill(tri)"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="b64_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--triangulation", default=os.environ.get("FOVEA_TRIANGULATION", "host"),
+                    choices=["host", "device"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, C, H, W = cfg["B"], cfg["C"], cfg["H"], cfg["W"]
+    x, xs, pred = make_inputs(cfg, seed=rank, device=dev)
+    path = Path(cfg, dev, args.triangulation)
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        path.step(x, xs, pred)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            path.step(x, xs, pred, time_fill=True)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    fill_ms = sum(a.elapsed_time(b) for a, b in path.fill_ms) / max(1, len(path.fill_ms))
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---------------- end to end from host buffers (`e2e`)
+    e2e = None
+    if not args.no_e2e:
+        hx, hxs, hpred = make_inputs(cfg, seed=rank + 100, pinned=True)
+        hmask = torch.empty(B, H, W, dtype=torch.int64, pin_memory=True)
+        dx, dxs, dpred = torch.empty_like(x), torch.empty_like(xs), torch.empty_like(pred)
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True)
+            dxs.copy_(hxs, non_blocking=True)
+            dpred.copy_(hpred, non_blocking=True)
+            path.step(dx, dxs, dpred, want_scores=True, want_mask=True)
+            hmask.copy_(path.mask, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k = max(2, min(args.steps, 5))
+        e0.record()
+        for _ in range(k):
+            e2e_step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * k / (float(t.item()) * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": hx.numel() * 4 + hxs.numel() * 4 + hpred.numel() * 4,
+               "d2h_bytes_per_step": hmask.numel() * 8, "steps": k,
+               "what": "pinned host image+saliency+pred -> H2D -> path (scores + fused argmax) -> D2H int64 masks"}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = 4.0 * C * H * W * B
+        achieved = alg_bytes / (fill_ms * 1e-3) / 1e9
+        line = {
+            "metric": "foveated-resample frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, **cfg, "frames_per_gpu": B, "triangulation": args.triangulation,
+                       "stages": "grid+grid_sample+inverse_fill(tri), scores mode",
+                       "l2": "output per step (4*C*H*W*B bytes) exceeds the 126 MB L2; no flush needed"},
+            "gpu_launches": KERNELS_PER_STEP * args.steps if args.triangulation == "device"
+            else (KERNELS_PER_STEP - 1) * args.steps,
+            "clocks": clocks.summary(),
+            "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": fill_ms},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline:
+            fps, secs = cpu_reference_time(cfg, frames=1, reps=2)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"1 frame of {H}x{W}, C={C} (best of 2, {secs:.2f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

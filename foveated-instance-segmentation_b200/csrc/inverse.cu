@@ -1,0 +1,493 @@
+// Stage 3: inverse resampling of the low-resolution prediction back to the full-resolution canvas.
+//
+// Reference: models/models.py:640-655 (grid_inv scatter), :935-938 (F.grid_sample(pred, grid_inv) + NaN mask),
+// :159-286 (fillMissingValues_tensor 'tri'), interp2d.py:37-91 (Interp2D), models_instance.py:940 (NaN -> 0),
+// models/models.py:1044 (argmax).  The reference materialises grid_inv [B,H,W,2], the sampled scores, a NaN
+// mask, a [3,H*W,C] gather and the final scores; here the full-resolution tensor is written exactly once.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "mesh.cuh"
+#include "taps.cuh"
+
+namespace fovea {
+
+// ------------------------------------------------------------------------------------------------ A7
+// u = int(((gx+1)/2)*(W-1)), v = int(((gy+1)/2)*(H-1))  -- models/models.py:644-645, fp32 op for op.
+__device__ __forceinline__ int target_coord(float g, int size) {
+  const float f = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), static_cast<float>(size - 1));
+  return __float2int_rz(f);
+}
+
+__global__ void grid_inv_scatter_kernel(const float2* __restrict__ grid, int32_t* __restrict__ winner, int B, int hw,
+                                        int H, int W) {
+  const int total = B * hw;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / hw, node = idx - b * hw;
+    const float2 g = grid[idx];
+    const int u = target_coord(g.x, W), v = target_coord(g.y, H);
+    if (u < 0 || u >= W || v < 0 || v >= H) continue;  // NaN / out-of-range grids index nothing
+    atomicMax(&winner[(static_cast<size_t>(b) * H + v) * W + u], node);
+  }
+}
+
+__global__ void grid_inv_canvas_kernel(const int32_t* __restrict__ winner, float2* __restrict__ out, long long total,
+                                       int h, int w) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = winner[idx];
+    float2 o;
+    if (n < 0) {
+      o.x = o.y = CUDART_NAN_F;
+    } else {
+      const int i = n / w, j = n - i * w;
+      // models/models.py:652-653: x_cor / w * 2 - 1
+      o.x = __fadd_rn(__fmul_rn(__fdiv_rn(static_cast<float>(j), static_cast<float>(w)), 2.f), -1.f);
+      o.y = __fadd_rn(__fmul_rn(__fdiv_rn(static_cast<float>(i), static_cast<float>(h)), 2.f), -1.f);
+    }
+    out[idx] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ A8
+// table[b][node][c] = grid_sample(pred, grid_inv)[node]: the bilinear sample of pred at the coordinate the
+// reference stores for node (i,j).  One warp handles 32 consecutive nodes of one image; channel values are
+// transposed through shared memory so that both the pred reads and the table writes are coalesced.
+constexpr int kTabNodes = 32;
+constexpr int kTabThreads = 256;
+
+__global__ void __launch_bounds__(kTabThreads)
+box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int C, int Cs, int h, int w) {
+  __shared__ float tile[kTabNodes][65];  // [node][channel chunk of 64] (+1: bank-conflict-free transpose)
+  const int hw = h * w;
+  const int b = blockIdx.y;
+  const int node0 = blockIdx.x * kTabNodes;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
+  const float* pb = pred + static_cast<size_t>(b) * C * hw;
+  float* tb = table + static_cast<size_t>(b) * (hw + 1) * Cs;
+
+  const int node = node0 + lane;
+  Taps t;
+  bool valid = node < hw;
+  if (valid) {
+    const int i = node / w, j = node - i * w;
+    const float gx = __fadd_rn(__fmul_rn(__fdiv_rn(static_cast<float>(j), static_cast<float>(w)), 2.f), -1.f);
+    const float gy = __fadd_rn(__fmul_rn(__fdiv_rn(static_cast<float>(i), static_cast<float>(h)), 2.f), -1.f);
+    t = make_taps(gx, gy, h, w);
+  }
+  for (int c0 = 0; c0 < Cs; c0 += 64) {
+    // gather: warp `warp` handles channels c0 + warp, c0 + warp + 8, ...
+    for (int cc = warp; cc < 64; cc += 8) {
+      const int c = c0 + cc;
+      float acc = 0.f;
+      if (valid && c < C) {
+        const float* s = pb + static_cast<size_t>(c) * hw + t.y0 * w + t.x0;
+        const float v_nw = t.ok_nw ? __ldg(s) : 0.f;
+        const float v_ne = t.ok_ne ? __ldg(s + 1) : 0.f;
+        const float v_sw = t.ok_sw ? __ldg(s + w) : 0.f;
+        const float v_se = t.ok_se ? __ldg(s + w + 1) : 0.f;
+        acc = v_nw * t.nw;
+        acc = fmaf(v_ne, t.ne, acc);
+        acc = fmaf(v_sw, t.sw, acc);
+        acc = fmaf(v_se, t.se, acc);
+      }
+      tile[lane][cc] = acc;
+    }
+    __syncthreads();
+    // scatter rows: 256 threads write 32 nodes x min(64, Cs-c0) channels, channel-contiguous
+    const int nch = min(64, Cs - c0);
+    for (int e = threadIdx.x; e < kTabNodes * nch; e += kTabThreads) {
+      const int n = e / nch, cc = e - n * nch;
+      if (node0 + n < hw) tb[static_cast<size_t>(node0 + n) * Cs + c0 + cc] = tile[n][cc];
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0)  // the NaN row: value of an image corner no node landed on
+    for (int c = threadIdx.x; c < Cs; c += kTabThreads) tb[static_cast<size_t>(hw) * Cs + c] = CUDART_NAN_F;
+}
+
+// ------------------------------------------------------------------------------------------------ A9 points
+struct SelectParams {
+  int h, w, H, W, cap;
+  int scaled;           // 1: dilation runs on the nearest-downscaled mask (max(C,H,W) > 512)
+  int hs, ws;           // downscaled size
+  float dn_y, dn_x;     // H/hs, W/ws  (nearest downscale source scale)
+  float up_y, up_x;     // hs/H, ws/W  (nearest upscale source scale)
+};
+
+__device__ __forceinline__ bool invalid_at(const int32_t* win, int H, int W, int y, int x) {
+  return y >= 0 && y < H && x >= 0 && x < W && win[static_cast<size_t>(y) * W + x] < 0;
+}
+
+// dilated(y,x) of getPixelsForInterp: does the 3x3 cross around (y,x) touch an invalid pixel?
+__device__ bool dilation_covers(const int32_t* win, const SelectParams& p, int y, int x) {
+  if (!p.scaled) {
+    return invalid_at(win, p.H, p.W, y - 1, x) || invalid_at(win, p.H, p.W, y + 1, x) ||
+           invalid_at(win, p.H, p.W, y, x - 1) || invalid_at(win, p.H, p.W, y, x + 1) ||
+           invalid_at(win, p.H, p.W, y, x);
+  }
+  // nearest upscale: dilated[y][x] = dilated_s[ys][xs]
+  const int ys = min(static_cast<int>(floorf(static_cast<float>(y) * p.up_y)), p.hs - 1);
+  const int xs = min(static_cast<int>(floorf(static_cast<float>(x) * p.up_x)), p.ws - 1);
+  const int dy[5] = {0, -1, 1, 0, 0}, dx[5] = {0, 0, 0, -1, 1};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int yy = ys + dy[k], xx = xs + dx[k];
+    if (yy < 0 || yy >= p.hs || xx < 0 || xx >= p.ws) continue;  // conv2d zero padding
+    // nearest downscale: scaled[yy][xx] = invalid[min(floor(yy*H/hs), H-1)][...]
+    const int sy = min(static_cast<int>(floorf(static_cast<float>(yy) * p.dn_y)), p.H - 1);
+    const int sx = min(static_cast<int>(floorf(static_cast<float>(xx) * p.dn_x)), p.W - 1);
+    if (win[static_cast<size_t>(sy) * p.W + sx] < 0) return true;
+  }
+  return false;
+}
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelMax = 8192;
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict__ winner, int32_t* __restrict__ pts,
+                     int32_t* __restrict__ src, int32_t* __restrict__ npts, SelectParams p) {
+  extern __shared__ unsigned long long keys[];  // [kSelMax]  (row<<16|col) << 32 | table row
+  __shared__ int count;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int hw = p.h * p.w;
+  const int32_t* win = winner + static_cast<size_t>(b) * p.H * p.W;
+  if (tid == 0) count = 0;
+  __syncthreads();
+
+  for (int node = tid; node < hw; node += kSelThreads) {
+    const float2 g = grid[static_cast<size_t>(b) * hw + node];
+    const int u = target_coord(g.x, p.W), v = target_coord(g.y, p.H);
+    if (u < 0 || u >= p.W || v < 0 || v >= p.H) continue;
+    if (win[static_cast<size_t>(v) * p.W + u] != node) continue;  // lost a collision
+    const bool corner = (v == 0 || v == p.H - 1) && (u == 0 || u == p.W - 1);
+    if (corner) continue;  // corners are appended below, exactly once
+    if (!dilation_covers(win, p, v, u)) continue;
+    const int slot = atomicAdd(&count, 1);
+    keys[slot] = (static_cast<unsigned long long>((v << 16) | u) << 32) | static_cast<unsigned>(node);
+  }
+  if (tid < 4) {  // models/models.py:202-209: the four corners are always interpolation points
+    const int v = (tid & 2) ? p.H - 1 : 0, u = (tid & 1) ? p.W - 1 : 0;
+    // (degenerate 1-pixel-wide canvases would duplicate corners; the host rejects H,W < 2)
+    const int n = win[static_cast<size_t>(v) * p.W + u];
+    const int slot = atomicAdd(&count, 1);
+    keys[slot] = (static_cast<unsigned long long>((v << 16) | u) << 32) | static_cast<unsigned>(n < 0 ? hw : n);
+  }
+  __syncthreads();
+  const int n = count;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + tid; i < n2; i += kSelThreads) keys[i] = ~0ull;
+  __syncthreads();
+  // bitonic sort, ascending by pixel key = row-major order of torch.where (models/models.py:265)
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += kSelThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], c = keys[l];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += kSelThreads) {
+    pts[static_cast<size_t>(b) * p.cap + i] = static_cast<int32_t>(keys[i] >> 32);
+    src[static_cast<size_t>(b) * p.cap + i] = static_cast<int32_t>(keys[i] & 0xFFFFFFFFull);
+  }
+  if (tid == 0) npts[b] = n;
+}
+
+// ------------------------------------------------------------------------------------------------ hints
+constexpr int kHintThreads = 256;
+
+__global__ void __launch_bounds__(kHintThreads)
+locate_hints_kernel(const int32_t* __restrict__ pts, const ushort4* __restrict__ tris, const ushort4* __restrict__ nbrs,
+                    const int32_t* __restrict__ ntri, int cap, int tcap, int H, int W, int32_t* __restrict__ hints) {
+  __shared__ int coarse[16 * 16];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  Mesh m{pts + static_cast<size_t>(b) * cap, tris + static_cast<size_t>(b) * tcap, nbrs + static_cast<size_t>(b) * tcap,
+         ntri[b]};
+  const int ch = ceil_div(H, FOVEA_HINT_CELL), cw = ceil_div(W, FOVEA_HINT_CELL);
+  int32_t* hb = hints + static_cast<size_t>(b) * ch * cw;
+  if (m.ntri <= 0) {
+    for (int i = tid; i < ch * cw; i += kHintThreads) hb[i] = 0;
+    return;
+  }
+  // level 0: 16x16 probes walked from triangle 0
+  {
+    const int py = tid / 16, px = tid % 16;
+    const int qr = min(H - 1, (2 * py + 1) * H / 32), qc = min(W - 1, (2 * px + 1) * W / 32);
+    const Located L = locate(m, qr, qc, 0);
+    coarse[tid] = L.tri < 0 ? 0 : L.tri;
+  }
+  __syncthreads();
+  // level 1: every hint cell walks from the nearest level-0 probe
+  for (int i = tid; i < ch * cw; i += kHintThreads) {
+    const int cy = i / cw, cx = i - cy * cw;
+    const int qr = min(H - 1, cy * FOVEA_HINT_CELL + FOVEA_HINT_CELL / 2);
+    const int qc = min(W - 1, cx * FOVEA_HINT_CELL + FOVEA_HINT_CELL / 2);
+    const int py = min(15, qr * 16 / H), px = min(15, qc * 16 / W);
+    const Located L = locate(m, qr, qc, coarse[py * 16 + px]);
+    hb[i] = L.tri < 0 ? 0 : L.tri;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ A8+A9+A10
+struct FillParams {
+  int C, Cs, h, w, H, W, cap, tcap, zero_residual;
+};
+
+struct PixelSrc {
+  int n0, n1, n2;      // rows of the value table
+  float w0, w1, w2;    // barycentric weights (1,0,0 for a pixel that received a node)
+};
+
+constexpr int kFillThreads = 256;
+
+// Each thread owns 4 consecutive pixels of one row: locate them, then stream all channels with 128-bit stores.
+template <bool kScores, bool kMask>
+__global__ void __launch_bounds__(kFillThreads)
+inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
+                    const ushort4* __restrict__ tris, const ushort4* __restrict__ nbrs, const int32_t* __restrict__ ntri,
+                    const int32_t* __restrict__ hints, const float* __restrict__ table, float* __restrict__ scores,
+                    long long* __restrict__ mask, FillParams p) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int x0 = (blockIdx.x * kFillThreads + threadIdx.x) * 4;
+  if (x0 >= p.W) return;
+  const int hw = p.h * p.w;
+  const size_t pix0 = (static_cast<size_t>(b) * p.H + y) * p.W + x0;
+  const int32_t* srcb = src + static_cast<size_t>(b) * p.cap;
+  Mesh m{pts + static_cast<size_t>(b) * p.cap, tris + static_cast<size_t>(b) * p.tcap,
+         nbrs + static_cast<size_t>(b) * p.tcap, ntri[b]};
+
+  const int4 win = *reinterpret_cast<const int4*>(winner + pix0);
+  const int wn[4] = {win.x, win.y, win.z, win.w};
+  PixelSrc ps[4];
+  const int cw = ceil_div(p.W, FOVEA_HINT_CELL);
+  int start = hints[(static_cast<size_t>(b) * ceil_div(p.H, FOVEA_HINT_CELL) + y / FOVEA_HINT_CELL) * cw +
+                    x0 / FOVEA_HINT_CELL];
+  bool uniform = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (wn[k] >= 0) {
+      ps[k] = PixelSrc{wn[k], wn[k], wn[k], 1.f, 0.f, 0.f};
+    } else {
+      const Located L = locate(m, y, x0 + k, start);
+      if (L.tri < 0) {
+        // outside the triangulation (cannot happen with the four corners present): NaN, like an unfilled corner
+        ps[k] = PixelSrc{hw, hw, hw, 1.f, 0.f, 0.f};
+      } else {
+        start = L.tri;
+        // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 from the transform, c2 = 1 - c0 - c1, in float64
+        const double c0 = static_cast<double>(L.a0) / static_cast<double>(L.area);
+        const double c1 = static_cast<double>(L.a1) / static_cast<double>(L.area);
+        const double c2 = 1.0 - c0 - c1;
+        ps[k] = PixelSrc{srcb[L.v.x], srcb[L.v.y], srcb[L.v.z], static_cast<float>(c0), static_cast<float>(c1),
+                         static_cast<float>(c2)};
+      }
+    }
+    if (k > 0)
+      uniform = uniform && ps[k].n0 == ps[0].n0 && ps[k].n1 == ps[0].n1 && ps[k].n2 == ps[0].n2;
+  }
+
+  const float* tb = table + static_cast<size_t>(b) * (hw + 1) * p.Cs;
+  const size_t plane = static_cast<size_t>(p.H) * p.W;
+  float* out = kScores ? scores + static_cast<size_t>(b) * p.C * plane + static_cast<size_t>(y) * p.W + x0 : nullptr;
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  int besti[4] = {0, 0, 0, 0};
+  bool bestnan[4] = {false, false, false, false};
+
+  for (int c = 0; c < p.Cs; c += 4) {
+    float v[4][4];  // [pixel][channel]
+    if (uniform) {
+      const float4 a = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[0].n0) * p.Cs + c);
+      const float4 bq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[0].n1) * p.Cs + c);
+      const float4 cq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[0].n2) * p.Cs + c);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)  // interp2d.py:85-89: mul, then sum over the 3 vertices in order
+          v[k][e] = __fadd_rn(__fadd_rn(__fmul_rn(av[e], ps[k].w0), __fmul_rn(bv[e], ps[k].w1)),
+                              __fmul_rn(cv[e], ps[k].w2));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[k].n0) * p.Cs + c);
+        const float4 bq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[k].n1) * p.Cs + c);
+        const float4 cq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[k].n2) * p.Cs + c);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          v[k][e] = __fadd_rn(__fadd_rn(__fmul_rn(av[e], ps[k].w0), __fmul_rn(bv[e], ps[k].w1)),
+                              __fmul_rn(cv[e], ps[k].w2));
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e >= p.C) break;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float val = v[k][e];
+        if (p.zero_residual && !(val == val)) val = 0.f;  // models_instance.py:940
+        o[k] = val;
+        if (kMask) {  // torch.argmax: first maximum wins; NaN counts as the maximum
+          const bool isn = !(val == val);
+          if (c + e == 0) {
+            best[k] = val; besti[k] = 0; bestnan[k] = isn;
+          } else if (!bestnan[k] && (isn || val > best[k])) {
+            best[k] = val; besti[k] = c + e; bestnan[k] = isn;
+          }
+        }
+      }
+      if (kScores) {
+        float4 st = make_float4(o[0], o[1], o[2], o[3]);
+        __stcs(reinterpret_cast<float4*>(out + static_cast<size_t>(c + e) * plane), st);
+      }
+    }
+  }
+  if (kMask) {
+    longlong2 m0 = make_longlong2(besti[0], besti[1]), m1 = make_longlong2(besti[2], besti[3]);
+    longlong2* mp = reinterpret_cast<longlong2*>(mask + pix0);
+    mp[0] = m0;
+    mp[1] = m1;
+  }
+}
+
+// torch.argmax(scores, dim=1) as a stand-alone streaming pass
+__global__ void __launch_bounds__(256)
+argmax_classes_kernel(const float* __restrict__ scores, long long* __restrict__ mask, int C, long long HW,
+                      long long total) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = idx / HW, pix = idx - b * HW;
+    const float* s = scores + b * C * HW + pix;
+    float best = __ldcs(s);
+    int bi = 0;
+    bool bn = !(best == best);
+    for (int c = 1; c < C; ++c) {
+      const float v = __ldcs(s + static_cast<long long>(c) * HW);
+      const bool isn = !(v == v);
+      if (!bn && (isn || v > best)) { best = v; bi = c; bn = isn; }
+    }
+    mask[idx] = bi;
+  }
+}
+
+}  // namespace fovea
+
+using namespace fovea;
+
+extern "C" int fovea_grid_inv_scatter(const float* grid, int B, int h, int w, int H, int W, int32_t* winner,
+                                      fovea_stream_t stream) {
+  FOVEA_REQUIRE(grid && winner && B > 0 && h > 0 && w > 0 && H > 1 && W > 1, "fovea_grid_inv_scatter: bad arguments");
+  FOVEA_REQUIRE(H < 65536 && W < 65536, "fovea_grid_inv_scatter: canvas side must be < 65536");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOVEA_CUDA(cudaMemsetAsync(winner, 0xFF, sizeof(int32_t) * static_cast<size_t>(B) * H * W, s));
+  const int total = B * h * w;
+  grid_inv_scatter_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(
+      reinterpret_cast<const float2*>(grid), winner, B, h * w, H, W);
+  return check_launch("fovea_grid_inv_scatter");
+}
+
+extern "C" int fovea_grid_inv_canvas(const int32_t* winner, int B, int h, int w, int H, int W, float* grid_inv,
+                                     fovea_stream_t stream) {
+  FOVEA_REQUIRE(winner && grid_inv && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "fovea_grid_inv_canvas: bad arguments");
+  const long long total = static_cast<long long>(B) * H * W;
+  const long long blocks = (total + 255) / 256;
+  grid_inv_canvas_kernel<<<static_cast<int>(blocks < kNumSMs * 32 ? blocks : kNumSMs * 32), 256, 0,
+                           static_cast<cudaStream_t>(stream)>>>(winner, reinterpret_cast<float2*>(grid_inv), total, h, w);
+  return check_launch("fovea_grid_inv_canvas");
+}
+
+extern "C" int fovea_box4_table(const float* pred, int B, int C, int h, int w, int Cs, float* table,
+                                fovea_stream_t stream) {
+  FOVEA_REQUIRE(pred && table && B > 0 && C > 0 && h > 0 && w > 0, "fovea_box4_table: bad arguments");
+  FOVEA_REQUIRE(Cs >= C && Cs % 4 == 0, "fovea_box4_table: Cs=%d must be a multiple of 4 and >= C=%d", Cs, C);
+  dim3 grid(ceil_div(h * w, kTabNodes), B);
+  box4_table_kernel<<<grid, kTabThreads, 0, static_cast<cudaStream_t>(stream)>>>(pred, table, C, Cs, h, w);
+  return check_launch("fovea_box4_table");
+}
+
+extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W,
+                                   int nchan, int cap, int32_t* pts, int32_t* src, int32_t* npts,
+                                   fovea_stream_t stream) {
+  FOVEA_REQUIRE(grid && winner && pts && src && npts, "fovea_select_points: null pointer");
+  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "fovea_select_points: bad sizes");
+  if (cap < h * w + 4 || cap > kSelMax) {
+    set_error("fovea_select_points: cap=%d must satisfy h*w+4=%d <= cap <= %d", cap, h * w + 4, kSelMax);
+    return FOVEA_ERR_CAPACITY;
+  }
+  SelectParams p;
+  p.h = h; p.w = w; p.H = H; p.W = W; p.cap = cap;
+  const int mx = nchan > H ? (nchan > W ? nchan : W) : (H > W ? H : W);
+  p.scaled = mx > 512;
+  p.hs = H; p.ws = W; p.dn_y = p.dn_x = p.up_y = p.up_x = 1.f;
+  if (p.scaled) {  // models/models.py:183-187, Python float (double) arithmetic then int()
+    const double dr = static_cast<double>(mx) / 512.0;
+    p.hs = static_cast<int>(static_cast<double>(H) / dr);
+    p.ws = static_cast<int>(static_cast<double>(W) / dr);
+    FOVEA_REQUIRE(p.hs > 0 && p.ws > 0, "fovea_select_points: downscaled mask is empty (%dx%d)", p.hs, p.ws);
+    p.dn_y = static_cast<float>(H) / static_cast<float>(p.hs);
+    p.dn_x = static_cast<float>(W) / static_cast<float>(p.ws);
+    p.up_y = static_cast<float>(p.hs) / static_cast<float>(H);
+    p.up_x = static_cast<float>(p.ws) / static_cast<float>(W);
+  }
+  const int smem = kSelMax * static_cast<int>(sizeof(unsigned long long));
+  FOVEA_CUDA(cudaFuncSetAttribute(select_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  select_points_kernel<<<B, kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(grid), winner, pts, src, npts, p);
+  return check_launch("fovea_select_points");
+}
+
+extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* tris, const uint16_t* nbrs,
+                                  const int32_t* ntri, int B, int cap, int tcap, int H, int W, int32_t* hints,
+                                  fovea_stream_t stream) {
+  (void)npts;
+  FOVEA_REQUIRE(pts && tris && nbrs && ntri && hints && B > 0 && H > 0 && W > 0, "fovea_locate_hints: bad arguments");
+  locate_hints_kernel<<<B, kHintThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      pts, reinterpret_cast<const ushort4*>(tris), reinterpret_cast<const ushort4*>(nbrs), ntri, cap, tcap, H, W, hints);
+  return check_launch("fovea_locate_hints");
+}
+
+extern "C" int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
+                                  const uint16_t* tris, const uint16_t* nbrs, const int32_t* ntri,
+                                  const int32_t* hints, const float* table, int B, int C, int Cs, int h, int w, int H,
+                                  int W, int cap, int tcap, int zero_residual, float* scores, int64_t* mask,
+                                  fovea_stream_t stream) {
+  (void)npts;
+  FOVEA_REQUIRE(winner && pts && src && tris && nbrs && ntri && hints && table, "fovea_inverse_fill: null pointer");
+  FOVEA_REQUIRE(scores || mask, "fovea_inverse_fill: neither scores nor mask requested");
+  FOVEA_REQUIRE(B > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && h > 0 && w > 0 && H > 1 && W > 1,
+                "fovea_inverse_fill: bad sizes");
+  FOVEA_REQUIRE(W % 4 == 0, "fovea_inverse_fill: W=%d must be a multiple of 4 (128-bit stores)", W);
+  FOVEA_REQUIRE(B <= 65535 && H <= 65535, "fovea_inverse_fill: B and H must be <= 65535");
+  FillParams p{C, Cs, h, w, H, W, cap, tcap, zero_residual};
+  dim3 grid(ceil_div(W, kFillThreads * 4), H, B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const ushort4* t4 = reinterpret_cast<const ushort4*>(tris);
+  const ushort4* n4 = reinterpret_cast<const ushort4*>(nbrs);
+  long long* mk = reinterpret_cast<long long*>(mask);
+  if (scores && mask)
+    inverse_fill_kernel<true, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, t4, n4, ntri, hints, table, scores, mk, p);
+  else if (scores)
+    inverse_fill_kernel<true, false><<<grid, kFillThreads, 0, s>>>(winner, pts, src, t4, n4, ntri, hints, table, scores, mk, p);
+  else
+    inverse_fill_kernel<false, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, t4, n4, ntri, hints, table, scores, mk, p);
+  return check_launch("fovea_inverse_fill");
+}
+
+extern "C" int fovea_argmax_classes(const float* scores, int B, int C, int64_t HW, int64_t* mask,
+                                    fovea_stream_t stream) {
+  FOVEA_REQUIRE(scores && mask && B > 0 && C > 0 && HW > 0, "fovea_argmax_classes: bad arguments");
+  const long long total = static_cast<long long>(B) * HW;
+  const long long blocks = (total + 255) / 256;
+  argmax_classes_kernel<<<static_cast<int>(blocks < kNumSMs * 32 ? blocks : kNumSMs * 32), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(scores, reinterpret_cast<long long*>(mask), C, HW, total);
+  return check_launch("fovea_argmax_classes");
+}

@@ -1,0 +1,79 @@
+// Triangle mesh access + exact point location shared by the stage-3 kernels.
+//
+// Points are packed (row<<16 | col); triangles are ushort4 (v0,v1,v2,_) indices into the per-image point list;
+// nbrs[t].{x,y,z} is the triangle across the edge OPPOSITE vertex 0,1,2 (SciPy's `neighbors` convention,
+// spatial/qhull.pyx:1367-1380), 0xFFFF = convex-hull edge.  Orientation may be either sign (host Qhull emits
+// both); all predicates are exact integer arithmetic, so a pixel on a shared edge is accepted by whichever
+// triangle the walk reaches first -- like the reference's eps-tolerant barycentric test, and harmless because the
+// interpolant is continuous across edges.
+#pragma once
+#include "common.cuh"
+
+namespace fovea {
+
+constexpr unsigned kNoTri = 0xFFFFu;
+
+struct Mesh {
+  const int32_t* pts;
+  const ushort4* tris;
+  const ushort4* nbrs;
+  int ntri;
+};
+
+__device__ __forceinline__ long long orient2d(int ar, int ac, int br, int bc, int qr, int qc) {
+  // z of (b-a) x (q-a) with x = col, y = row
+  return static_cast<long long>(bc - ac) * (qr - ar) - static_cast<long long>(br - ar) * (qc - ac);
+}
+
+struct Located {
+  int tri;            // -1: outside the triangulation
+  long long a0, a1;   // orientation-normalised sub-areas opposite vertex 0 and 1
+  long long area;     // |orient(v0,v1,v2)|
+  ushort4 v;
+};
+
+__device__ __forceinline__ bool test_triangle(const Mesh& m, int t, int qr, int qc, Located& out, int& next) {
+  const ushort4 v = m.tris[t];
+  const int p0 = m.pts[v.x], p1 = m.pts[v.y], p2 = m.pts[v.z];
+  const int r0 = p0 >> 16, c0 = p0 & 0xFFFF, r1 = p1 >> 16, c1 = p1 & 0xFFFF, r2 = p2 >> 16, c2 = p2 & 0xFFFF;
+  long long A = orient2d(r0, c0, r1, c1, r2, c2);
+  const long long s = A < 0 ? -1 : 1;
+  A *= s;
+  const long long e0 = s * orient2d(r1, c1, r2, c2, qr, qc);
+  const long long e1 = s * orient2d(r2, c2, r0, c0, qr, qc);
+  const long long e2 = A - e0 - e1;  // == s*orient(p0,p1,q)
+  next = -1;
+  if (A == 0) return false;
+  if (e0 < 0) { next = m.nbrs[t].x; return false; }
+  if (e1 < 0) { next = m.nbrs[t].y; return false; }
+  if (e2 < 0) { next = m.nbrs[t].z; return false; }
+  out.tri = t; out.a0 = e0; out.a1 = e1; out.area = A; out.v = v;
+  return true;
+}
+
+// Visibility walk from `start`; falls back to a scan of all triangles if the walk meets a degenerate
+// triangle or exceeds its step budget (cannot happen on a Delaunay mesh, may on a host mesh with flat facets).
+__device__ __noinline__ Located locate_bruteforce(const Mesh& m, int qr, int qc) {
+  Located L; L.tri = -1; L.a0 = L.a1 = 0; L.area = 1; L.v = make_ushort4(0, 0, 0, 0);
+  int next;
+  for (int t = 0; t < m.ntri; ++t)
+    if (test_triangle(m, t, qr, qc, L, next)) return L;
+  L.tri = -1;
+  return L;
+}
+
+__device__ __forceinline__ Located locate(const Mesh& m, int qr, int qc, int start) {
+  Located L; L.tri = -1; L.a0 = L.a1 = 0; L.area = 1; L.v = make_ushort4(0, 0, 0, 0);
+  int t = (start >= 0 && start < m.ntri) ? start : 0;
+  const int budget = m.ntri + 8;
+  for (int step = 0; step < budget; ++step) {
+    int next;
+    if (test_triangle(m, t, qr, qc, L, next)) return L;
+    if (next < 0) break;                                   // degenerate triangle
+    if (static_cast<unsigned>(next) == kNoTri) { L.tri = -1; return L; }  // left the hull
+    t = next;
+  }
+  return locate_bruteforce(m, qr, qc);
+}
+
+}  // namespace fovea

@@ -1,0 +1,81 @@
+"""ctypes binding of libfovea_b200.so (the C ABI declared in include/fovea_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a call fails, a
+`FoveaError` is raised.  PyTorch is used only for device memory and streams -- no torch type crosses the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfovea_b200.so")
+
+FOVEA_OK = 0
+PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
+PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
+HINT_CELL = 32
+ABI_VERSION = 1
+
+
+class FoveaError(RuntimeError):
+    pass
+
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); mirrors include/fovea_b200.h one to one
+PROTOTYPES = {
+    "fovea_abi_version": (_i, []),
+    "fovea_last_error": (C.c_char_p, []),
+    "fovea_grid_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p]),
+    "fovea_grid_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "fovea_grid_resize": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_grid_resize_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_grid_sample_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_grid_sample_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_grid_inv_scatter": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_grid_inv_canvas": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_box4_table": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_select_points": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fovea_delaunay_workspace_bytes": (_i64, [_i, _i]),
+    "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "fovea_locate_hints": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_inverse_fill": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_argmax_classes": (_i, [_p, _i, _i, _i64, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise FoveaError (never fall back) if it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FoveaError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` or `make -C "
+            f"foveated-instance-segmentation_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise FoveaError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fovea_abi_version() != ABI_VERSION:
+        raise FoveaError(f"ABI version mismatch: library {lib.fovea_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != FOVEA_OK:
+        msg = lib.fovea_last_error().decode("utf-8", "replace")
+        raise FoveaError(f"{name} failed (rc={rc}): {msg}")

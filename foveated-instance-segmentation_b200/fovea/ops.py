@@ -1,0 +1,318 @@
+"""Torch-facing operators of the foveated resampling path, each a thin call into libfovea_b200.so.
+
+Every function takes/returns CUDA tensors, checks dtype/contiguity/device in Python (the C ABI sees only raw
+pointers and sizes) and launches on torch's current stream.  Nothing here computes on the CPU except the optional
+host triangulation of `build_inverse_plan(..., triangulation="host")`, which is what the reference itself does
+(interp2d.py:53-58 runs Qhull on the host).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FoveaError, PAD_MODES
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise FoveaError(f"{name}: expected a CUDA tensor (this path has no CPU fallback), got "
+                         f"{type(t).__name__}{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.dtype != dtype:
+        raise FoveaError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise FoveaError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ stage 1
+
+def separable_factors(filter_weight: torch.Tensor, rtol: float = 1e-5):
+    """Split the dense Gaussian `filter.weight[0,0]` ([2Rx+1, 2Ry+1], models/models.py:510-515) into its two 1-D
+    factors g1x (rows) and g1y (cols).  Raises if the weight is not rank-1 (e.g. it was trained away from the
+    Gaussian): the sm_100a kernel is a separable filter and will not silently approximate."""
+    w = filter_weight.detach().reshape(filter_weight.shape[-2], filter_weight.shape[-1]).double().cpu()
+    Kx, Ky = w.shape
+    Rx, Ry = Kx // 2, Ky // 2
+    centre = w[Rx, Ry]
+    if centre == 0:
+        raise FoveaError("filter.weight centre is zero; cannot factor")
+    g1y = w[Rx, :].clone()
+    g1x = w[:, Ry] / centre
+    err = (torch.outer(g1x, g1y) - w).abs().max() / w.abs().max()
+    if err > rtol:
+        raise FoveaError(f"filter.weight is not rank-1 (relative residual {err:.2e}); the separable kernel "
+                         f"requires the Gaussian built from cfg.MODEL.gaussian_radius")
+    return g1x.float(), g1y.float()
+
+
+class _GridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, g1x, g1y, gh, gw, Rx, Ry, pad_mode, out_h, out_w):
+        B = xs.shape[0]
+        xs_c = _req(xs, torch.float32, "xs").view(B, xs.shape[-2], xs.shape[-1])
+        grid = torch.empty(B, out_h, out_w, 2, device=xs.device, dtype=torch.float32)
+        sums = torch.empty(B, 3, gh, gw, device=xs.device, dtype=torch.float32)
+        _lib.call("fovea_grid_fwd", _ptr(xs_c), B, gh, gw, Rx, Ry, pad_mode, _ptr(g1x), _ptr(g1y), out_h, out_w,
+                  _ptr(grid), _ptr(sums), _stream())
+        ctx.save_for_backward(sums, g1x, g1y)
+        ctx.geom = (gh, gw, Rx, Ry, pad_mode, out_h, out_w, tuple(xs.shape))
+        return grid
+
+    @staticmethod
+    def backward(ctx, grad_grid):
+        sums, g1x, g1y = ctx.saved_tensors
+        gh, gw, Rx, Ry, pad_mode, out_h, out_w, shape = ctx.geom
+        B = shape[0]
+        gg = _req(grad_grid, torch.float32, "grad_grid")
+        grad_xs = torch.empty(shape, device=gg.device, dtype=torch.float32)
+        _lib.call("fovea_grid_bwd", _ptr(gg), _ptr(sums), B, gh, gw, Rx, Ry, pad_mode, _ptr(g1x), _ptr(g1y), out_h,
+                  out_w, _ptr(grad_xs), _stream())
+        return (grad_xs,) + (None,) * 9
+
+
+def saliency_to_grid(xs, g1x, g1y, gh, gw, Rx, Ry, pad_mode, out_size):
+    """Stage 1 (models/models.py:594-637 [+ :819-825 when pad_mode != 'none']).
+
+    xs: [B,1,gh,gw] normalised saliency (fused padding) or the padded xs_hm [B,1,gh+2Rx,gw+2Ry] (pad_mode='none').
+    Returns grid [B,out_h,out_w,2]; differentiable w.r.t. xs.
+    """
+    mode = PAD_MODES[pad_mode] if isinstance(pad_mode, str) else int(pad_mode)
+    eh, ew = (gh + 2 * Rx, gw + 2 * Ry) if mode == _lib.PAD_NONE else (gh, gw)
+    if xs.dim() != 4 or xs.shape[1] != 1 or tuple(xs.shape[-2:]) != (eh, ew):
+        raise FoveaError(f"saliency_to_grid: expected xs of shape [B,1,{eh},{ew}], got {tuple(xs.shape)}")
+    g1x = _req(g1x, torch.float32, "g1x")
+    g1y = _req(g1y, torch.float32, "g1y")
+    if g1x.numel() != 2 * Rx + 1 or g1y.numel() != 2 * Ry + 1:
+        raise FoveaError("saliency_to_grid: filter factor lengths do not match Rx/Ry")
+    return _GridFn.apply(xs, g1x, g1y, gh, gw, Rx, Ry, mode, int(out_size[0]), int(out_size[1]))
+
+
+class _GridResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grid, oh, ow):
+        g = _req(grid, torch.float32, "grid", 4)
+        B, ih, iw, _ = g.shape
+        out = torch.empty(B, oh, ow, 2, device=g.device, dtype=torch.float32)
+        _lib.call("fovea_grid_resize", _ptr(g), B, ih, iw, oh, ow, _ptr(out), _stream())
+        ctx.geom = (B, ih, iw, oh, ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, ih, iw, oh, ow = ctx.geom
+        go = _req(grad_out, torch.float32, "grad_out")
+        gi = torch.empty(B, ih, iw, 2, device=go.device, dtype=torch.float32)
+        _lib.call("fovea_grid_resize_bwd", _ptr(go), B, ih, iw, oh, ow, _ptr(gi), _stream())
+        return gi, None, None
+
+
+def grid_resize(grid, out_size):
+    """nn.Upsample(size, 'bilinear') of an NHWC grid (models/models.py:627-631); identity sizes alias."""
+    oh, ow = int(out_size[0]), int(out_size[1])
+    if grid.shape[1] == oh and grid.shape[2] == ow:
+        return grid
+    return _GridResizeFn.apply(grid, oh, ow)
+
+
+# ------------------------------------------------------------------------------------------------ stage 2
+
+class _GridSampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, grid):
+        x = _req(inp, torch.float32, "input", 4)
+        g = _req(grid, torch.float32, "grid", 4)
+        B, Cc, H, W = x.shape
+        if g.shape[0] != B or g.shape[3] != 2:
+            raise FoveaError(f"grid_sample: grid {tuple(g.shape)} does not match input {tuple(x.shape)}")
+        h, w = g.shape[1], g.shape[2]
+        out = torch.empty(B, Cc, h, w, device=x.device, dtype=torch.float32)
+        _lib.call("fovea_grid_sample_fwd", _ptr(x), _ptr(g), B, Cc, H, W, h, w, _ptr(out), _stream())
+        ctx.save_for_backward(x, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, g = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        h, w = g.shape[1], g.shape[2]
+        go = _req(grad_out, torch.float32, "grad_out")
+        need_in, need_grid = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gi = torch.zeros_like(x) if need_in else None
+        gg = torch.empty_like(g) if need_grid else None
+        if need_in or need_grid:
+            _lib.call("fovea_grid_sample_bwd", _ptr(go), _ptr(x), _ptr(g), B, Cc, H, W, h, w, _ptr(gi), _ptr(gg),
+                      _stream())
+        return gi, gg
+
+
+def grid_sample(inp, grid):
+    """F.grid_sample(inp, grid) with the reference's defaults (models/models.py:865, 880, 909, 937)."""
+    return _GridSampleFn.apply(inp, grid)
+
+
+# ------------------------------------------------------------------------------------------------ stage 3
+
+def grid_inv_scatter(grid, segSize):
+    """models/models.py:640-651 -> winner int32 [B,H,W] (row-major low-res index, -1 unfilled)."""
+    g = _req(grid.detach(), torch.float32, "grid", 4)
+    B, h, w, _ = g.shape
+    H, W = int(segSize[0]), int(segSize[1])
+    winner = torch.empty(B, H, W, device=g.device, dtype=torch.int32)
+    _lib.call("fovea_grid_inv_scatter", _ptr(g), B, h, w, H, W, _ptr(winner), _stream())
+    return winner
+
+
+def grid_inv_canvas(winner, h, w):
+    """models/models.py:652-655 -> grid_inv float [B,H,W,2], NaN where unfilled."""
+    win = _req(winner, torch.int32, "winner", 3)
+    B, H, W = win.shape
+    out = torch.empty(B, H, W, 2, device=win.device, dtype=torch.float32)
+    _lib.call("fovea_grid_inv_canvas", _ptr(win), B, h, w, H, W, _ptr(out), _stream())
+    return out
+
+
+@dataclass
+class InversePlan:
+    """Everything stage 3 needs that depends only on the sampling grid (not on the scores being warped)."""
+    winner: torch.Tensor   # [B,H,W] int32
+    pts: torch.Tensor      # [B,cap] int32 (row<<16|col), row-major sorted
+    src: torch.Tensor      # [B,cap] int32 row of the value table
+    npts: torch.Tensor     # [B] int32
+    tris: torch.Tensor     # [B,tcap,4] uint16
+    nbrs: torch.Tensor     # [B,tcap,4] uint16
+    ntri: torch.Tensor     # [B] int32
+    hints: torch.Tensor    # [B,ceil(H/32),ceil(W/32)] int32
+    h: int
+    w: int
+    H: int
+    W: int
+    cap: int
+    tcap: int
+    triangulation: str
+
+
+def _host_delaunay_one(pts_packed: np.ndarray):
+    """Stock SciPy Qhull on one image's points, exactly as interp2d.py:55 (default options + Qt)."""
+    from scipy.spatial import Delaunay
+    rc = np.stack([pts_packed >> 16, pts_packed & 0xFFFF], 1).astype(np.float64)
+    tri = Delaunay(rc)
+    return tri.simplices.astype(np.int64), tri.neighbors.astype(np.int64)
+
+
+def _triangulate_host(pts, npts, cap, tcap, pool=None):
+    B = pts.shape[0]
+    pts_h = pts.cpu().numpy()
+    npts_h = npts.cpu().numpy()
+    tris = np.zeros((B, tcap, 4), dtype=np.uint16)
+    nbrs = np.full((B, tcap, 4), 0xFFFF, dtype=np.uint16)
+    ntri = np.zeros(B, dtype=np.int32)
+    jobs = [pts_h[b, : npts_h[b]] for b in range(B)]
+    if pool is None and B > 1:
+        with ThreadPoolExecutor(max_workers=min(B, 32)) as ex:
+            res = list(ex.map(_host_delaunay_one, jobs))
+    elif pool is not None:
+        res = list(pool.map(_host_delaunay_one, jobs))
+    else:
+        res = [_host_delaunay_one(jobs[0])]
+    for b, (simp, nb) in enumerate(res):
+        T = simp.shape[0]
+        if T > tcap:
+            raise FoveaError(f"host triangulation produced {T} triangles > tcap={tcap}")
+        tris[b, :T, :3] = simp
+        nb = np.where(nb < 0, 0xFFFF, nb)
+        nbrs[b, :T, :3] = nb
+        ntri[b] = T
+    dev = pts.device
+    return (torch.from_numpy(tris).to(dev), torch.from_numpy(nbrs).to(dev), torch.from_numpy(ntri).to(dev))
+
+
+def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) -> InversePlan:
+    """A7 scatter + A9 point selection + triangulation + walk hints for a batch of sampling grids.
+
+    triangulation='host'  : stock SciPy Qhull on the host, exactly what the reference does (parity mode);
+    triangulation='device': the sm_100a Delaunay kernel (fast mode; differs from Qhull only in how co-circular
+                            point sets are split).
+    """
+    g = _req(grid.detach(), torch.float32, "grid", 4)
+    B, h, w, _ = g.shape
+    H, W = int(segSize[0]), int(segSize[1])
+    dev = g.device
+    winner = grid_inv_scatter(g, (H, W))
+    cap = h * w + 4
+    tcap = 2 * cap
+    pts = torch.empty(B, cap, device=dev, dtype=torch.int32)
+    src = torch.empty(B, cap, device=dev, dtype=torch.int32)
+    npts = torch.empty(B, device=dev, dtype=torch.int32)
+    _lib.call("fovea_select_points", _ptr(g), _ptr(winner), B, h, w, H, W, int(nchan), cap, _ptr(pts), _ptr(src),
+              _ptr(npts), _stream())
+    if triangulation == "host":
+        tris, nbrs, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
+    elif triangulation == "device":
+        tris = torch.empty(B, tcap, 4, device=dev, dtype=torch.uint16)
+        nbrs = torch.empty(B, tcap, 4, device=dev, dtype=torch.uint16)
+        ntri = torch.empty(B, device=dev, dtype=torch.int32)
+        ws_bytes = _lib.load().fovea_delaunay_workspace_bytes(B, cap)
+        ws = torch.empty(max(int(ws_bytes), 16), device=dev, dtype=torch.uint8)
+        _lib.call("fovea_delaunay", _ptr(pts), _ptr(npts), B, cap, tcap, _ptr(tris), _ptr(nbrs), _ptr(ntri), _ptr(ws),
+                  _stream())
+    else:
+        raise FoveaError(f"unknown triangulation mode {triangulation!r}")
+    ch, cw = -(-H // _lib.HINT_CELL), -(-W // _lib.HINT_CELL)
+    hints = torch.empty(B, ch, cw, device=dev, dtype=torch.int32)
+    _lib.call("fovea_locate_hints", _ptr(pts), _ptr(npts), _ptr(tris), _ptr(nbrs), _ptr(ntri), B, cap, tcap, H, W,
+              _ptr(hints), _stream())
+    return InversePlan(winner, pts, src, npts, tris, nbrs, ntri, hints, h, w, H, W, cap, tcap, triangulation)
+
+
+def box4_table(pred, Cs=None):
+    """A8 at the nodes: [B, h*w+1, Cs] value table (last row NaN), models/models.py:935-937."""
+    p = _req(pred.detach(), torch.float32, "pred", 4)
+    B, Cc, h, w = p.shape
+    Cs = Cs or (Cc + 3) // 4 * 4
+    table = torch.empty(B, h * w + 1, Cs, device=p.device, dtype=torch.float32)
+    _lib.call("fovea_box4_table", _ptr(p), B, Cc, h, w, Cs, _ptr(table), _stream())
+    return table
+
+
+def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zero_residual=True, out=None,
+                 mask_out=None):
+    """A8 + A9 (+A10): full-resolution scores [B,C,H,W] and/or argmax mask [B,H,W] int64 from pred [B,C,h,w]."""
+    p = _req(pred.detach(), torch.float32, "pred", 4)
+    B, Cc, h, w = p.shape
+    if (h, w) != (plan.h, plan.w) or B != plan.winner.shape[0]:
+        raise FoveaError(f"inverse_fill: pred {tuple(p.shape)} does not match the plan ({B}x{plan.h}x{plan.w})")
+    table = box4_table(p)
+    Cs = table.shape[2]
+    scores = None
+    if want_scores:
+        scores = out if out is not None else torch.empty(B, Cc, plan.H, plan.W, device=p.device, dtype=torch.float32)
+        _req(scores, torch.float32, "scores out", 4)
+    mask = None
+    if want_mask:
+        mask = mask_out if mask_out is not None else torch.empty(B, plan.H, plan.W, device=p.device, dtype=torch.int64)
+    _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
+              _ptr(plan.tris), _ptr(plan.nbrs), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), B, Cc, Cs, h, w,
+              plan.H, plan.W, plan.cap, plan.tcap, 1 if zero_residual else 0, _ptr(scores), _ptr(mask), _stream())
+    return scores, mask
+
+
+def argmax_classes(scores):
+    """torch.argmax(scores, dim=1) (models/models.py:1044) as one streaming pass."""
+    s = _req(scores, torch.float32, "scores", 4)
+    B, Cc, H, W = s.shape
+    mask = torch.empty(B, H, W, device=s.device, dtype=torch.int64)
+    _lib.call("fovea_argmax_classes", _ptr(s), B, Cc, H * W, _ptr(mask), _stream())
+    return mask

@@ -1,0 +1,171 @@
+/*
+ * fovea_b200.h -- C ABI of libfovea_b200.so: the foveated resampling hot path of FovealSeg
+ * (SAI-Lab-NYU/Foveated-Instance-Segmentation) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI of its own: its "operator interface" for this path is the Python surface of
+ * models/models.py (DeformSegmentationModule.create_grid, the F.grid_sample call sites,
+ * fillMissingValues_tensor) and interp2d.py (Interp2D).  Each entry point below names the reference
+ * lines it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes stubs a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - all float tensors are fp32, contiguous, NCHW unless the comment gives another layout;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
+ *   - the caller owns every buffer; the library keeps no global state except the last-error string;
+ *   - return value: 0 = FOVEA_OK, negative = FOVEA_ERR_*; no C++ exception crosses the boundary;
+ *   - there is NO CPU fallback: every entry point launches CUDA kernels or fails.
+ */
+#ifndef FOVEA_B200_H_
+#define FOVEA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOVEA_ABI_VERSION 1
+
+enum fovea_status {
+  FOVEA_OK = 0,
+  FOVEA_ERR_ARG = -1,      /* bad shape / null pointer / unsupported size */
+  FOVEA_ERR_CUDA = -2,     /* a CUDA runtime call or launch failed; see fovea_last_error() */
+  FOVEA_ERR_CAPACITY = -3  /* a per-image capacity (points, triangles, shared memory) is exceeded */
+};
+
+/* how the saliency map handed to fovea_grid_* relates to the padded map xs_hm of the reference
+ * (models/models.py:819-825, cfg.TRAIN.def_saliency_pad_mode) */
+enum fovea_pad_mode {
+  FOVEA_PAD_NONE = 0,        /* input IS xs_hm [B,gh+2Rx,gw+2Ry], as create_grid() receives it */
+  FOVEA_PAD_REPLICATION = 1, /* input is xs [B,gh,gw]; nn.ReplicationPad2d fused into the filter taps */
+  FOVEA_PAD_REFLECT = 2,     /* F.pad(mode='reflect') fused */
+  FOVEA_PAD_ZERO = 3         /* F.pad(mode='constant') fused */
+};
+
+typedef void* fovea_stream_t; /* cudaStream_t */
+
+int fovea_abi_version(void);
+/* thread-local, NUL-terminated description of the last failure in this thread ("" if none) */
+const char* fovea_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 -- saliency -> sampling grid.      Replaces models/models.py:594-637 (create_grid, forward
+ * part: three dense (2Rx+1)x(2Ry+1) convs + div + clamp + nn.Upsample + NCHW->NHWC) and, for
+ * pad_mode != NONE, the padding at models/models.py:819-825.
+ *
+ * The dense Gaussian `filter.weight` (models/models.py:510-515) is exactly rank-1; the caller passes its
+ * two 1-D factors g1x[2Rx+1] (rows) and g1y[2Ry+1] (cols), filter[a][b] == g1x[a]*g1y[b].
+ *
+ *   xs        [B, src_h, src_w]   src = (gh,gw) for fused padding, (gh+2Rx, gw+2Ry) for FOVEA_PAD_NONE
+ *   grid      [B, out_h, out_w, 2]  (x->width, y->height) in [-1,1]; bilinear(align_corners=False)
+ *                                   resize of the raw gh x gw grid, identity when out == (gh,gw)
+ *   sums      [B, 3, gh, gw]       den, num_x, num_y  -- saved for fovea_grid_bwd (may be NULL)
+ * ------------------------------------------------------------------------------------------------ */
+int fovea_grid_fwd(const float* xs, int B, int gh, int gw, int Rx, int Ry, int pad_mode,
+                   const float* g1x, const float* g1y, int out_h, int out_w,
+                   float* grid, float* sums, fovea_stream_t stream);
+
+/* Backward of fovea_grid_fwd w.r.t. xs.  Replaces the autograd chain conv2d_backward(input) ->
+ * div/clamp/Upsample backward -> replication_pad2d_backward of models/models.py:594-637, 821.
+ * d(filter.weight) is NOT produced: no optimizer consumes it (train_deform_semantic.py:273-288).
+ *   grad_grid [B,out_h,out_w,2]   sums [B,3,gh,gw] from the forward   grad_xs [B,src_h,src_w] (overwritten) */
+int fovea_grid_bwd(const float* grad_grid, const float* sums, int B, int gh, int gw, int Rx, int Ry,
+                   int pad_mode, const float* g1x, const float* g1y, int out_h, int out_w,
+                   float* grad_xs, fovea_stream_t stream);
+
+/* Bilinear (align_corners=False) resize of an NHWC 2-channel grid: the second nn.Upsample that derives
+ * grid_y from grid (models/models.py:627-631).  in [B,ih,iw,2] -> out [B,oh,ow,2]. */
+int fovea_grid_resize(const float* in, int B, int ih, int iw, int oh, int ow, float* out,
+                      fovea_stream_t stream);
+/* adjoint of fovea_grid_resize: grad_out [B,oh,ow,2] -> grad_in [B,ih,iw,2] (overwritten) */
+int fovea_grid_resize_bwd(const float* grad_out, int B, int ih, int iw, int oh, int ow, float* grad_in,
+                          fovea_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2 -- F.grid_sample(input, grid) with the reference's defaults (mode='bilinear',
+ * padding_mode='zeros', align_corners=False).   Replaces models/models.py:865, 880, 909 (and :937
+ * when the fused stage-3 kernel is not used).
+ *   in [B,C,H,W]   grid [B,h,w,2]   out [B,C,h,w]
+ * ------------------------------------------------------------------------------------------------ */
+int fovea_grid_sample_fwd(const float* in, const float* grid, int B, int C, int H, int W, int h, int w,
+                          float* out, fovea_stream_t stream);
+
+/* Backward (aten grid_sampler_2d_backward).  grad_in may be NULL (input does not require grad: the image
+ * and label); when given it must be ZERO-FILLED by the caller and receives a warp-aggregated scatter-add.
+ * grad_grid [B,h,w,2] may be NULL. */
+int fovea_grid_sample_bwd(const float* grad_out, const float* in, const float* grid, int B, int C, int H,
+                          int W, int h, int w, float* grad_in, float* grad_grid, fovea_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3 -- inverse resampling back to full resolution.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* A7: the scatter half of create_grid's inverse part, models/models.py:640-651.  winner[b,v,u] = row-major
+ * low-res index i*w+j of the node whose truncated target is pixel (v,u), -1 where no node lands.
+ * Duplicate targets: the LARGEST index wins (the reference leaves the winner undefined).
+ *   grid [B,h,w,2] -> winner [B,H,W] int32 (fully overwritten) */
+int fovea_grid_inv_scatter(const float* grid, int B, int h, int w, int H, int W, int32_t* winner,
+                           fovea_stream_t stream);
+
+/* A7: the float canvas create_grid returns, models/models.py:640-655: grid_inv[b,v,u] =
+ * (j/w*2-1, i/h*2-1) of the winner, NaN where unfilled.  winner [B,H,W] -> grid_inv [B,H,W,2] */
+int fovea_grid_inv_canvas(const int32_t* winner, int B, int h, int w, int H, int W, float* grid_inv,
+                          fovea_stream_t stream);
+
+/* A8 at the low-res nodes: table[b, i*w+j, c] = F.grid_sample(pred, grid_inv) evaluated at node (i,j)
+ * (= the zero-padded 2x2 box mean of pred, with aten's fp32 arithmetic), models/models.py:935-937.
+ * Row h*w of every image is NaN (value of an unfilled image corner, models/models.py:202-209, 268).
+ *   pred [B,C,h,w] -> table [B, h*w+1, Cs] fp32, Cs = channel stride >= C, multiple of 4 (tail zero) */
+int fovea_box4_table(const float* pred, int B, int C, int h, int w, int Cs, float* table,
+                     fovea_stream_t stream);
+
+/* A9 point selection: getPixelsForInterp of fillMissingValues_tensor, models/models.py:169-211, applied to
+ * the NaN pattern `winner < 0`: a filled pixel is an interpolation point iff the 3x3-cross dilation of the
+ * invalid mask (at <=512 px directly, else on the nearest-downscaled copy, :183-193) covers it; the four
+ * image corners are always points.  Points are emitted in row-major order (torch.where order, :265).
+ *   nchan     C of the tensor the reference would dilate (enters max(C,H,W)/512, models.py:183)
+ *   grid [B,h,w,2] the sampling grid the winners were scattered from
+ *   pts  [B,cap] int32  (row<<16 | col)      src [B,cap] int32 row into `table` (h*w = NaN corner)
+ *   npts [B]     int32                       h*w+4 <= cap <= 8192 */
+int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
+                        int cap, int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream);
+
+/* Delaunay triangulation of each image's points ON THE DEVICE (one CTA per image, exact int64
+ * in-circle predicates).  Replaces the host Qhull call interp2d.py:55 (spatial/qhull.pyx:1679).
+ * The caller may instead fill tris/nbrs/ntri from a host triangulation (parity mode: stock SciPy Qhull).
+ *   tris [B,tcap,4] uint16 (v0,v1,v2,0) indices into pts, counter-clockwise in (col,row) axes
+ *   nbrs [B,tcap,4] uint16  nbrs[t][k] = triangle opposite vertex k, 0xFFFF = hull edge
+ *   ntri [B] int32          tcap >= 2*cap
+ *   workspace: fovea_delaunay_workspace_bytes(B, cap) bytes of device memory */
+int64_t fovea_delaunay_workspace_bytes(int B, int cap);
+int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, uint16_t* tris,
+                   uint16_t* nbrs, int32_t* ntri, void* workspace, fovea_stream_t stream);
+
+/* Walk-start hints for fovea_inverse_fill: hints[b, cy, cx] = a triangle containing (or near) the centre
+ * of the FOVEA_HINT_CELL x FOVEA_HINT_CELL pixel cell.  hints [B, ceil(H/cell), ceil(W/cell)] int32 */
+#define FOVEA_HINT_CELL 32
+int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* tris, const uint16_t* nbrs,
+                       const int32_t* ntri, int B, int cap, int tcap, int H, int W, int32_t* hints,
+                       fovea_stream_t stream);
+
+/* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
+ * fillMissingValues_tensor(..., 'tri') = Interp2D point location + barycentric gather
+ * (models/models.py:939-940, interp2d.py:58-91), residual NaN -> 0 (models_instance.py:940) and
+ * torch.argmax over classes (models/models.py:1044), in one pass over the full-resolution canvas.
+ *   scores [B,C,H,W] fp32   (NULL = do not materialise)
+ *   mask   [B,H,W]  int64   (NULL = do not compute)
+ *   zero_residual: 1 = NaN -> 0 before writing / argmax */
+int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
+                       const uint16_t* tris, const uint16_t* nbrs, const int32_t* ntri, const int32_t* hints,
+                       const float* table, int B, int C, int Cs, int h, int w, int H, int W, int cap,
+                       int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
+
+/* torch.argmax(scores, dim=1) as a stand-alone pass (models/models.py:1044): first maximum wins, NaN is
+ * treated as the maximum (torch semantics).  scores [B,C,H,W] -> mask [B,H,W] int64 */
+int fovea_argmax_classes(const float* scores, int B, int C, int64_t HW, int64_t* mask, fovea_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOVEA_B200_H_ */

@@ -1,0 +1,255 @@
+"""GPU parity tests: the sm_100a kernels (called through the C ABI) against the CPU oracle and the committed
+golden vectors produced by the unmodified reference.  Run with `pytest -m gpu` on the B200 box.
+
+Tolerances (north_star): sampling grids and resampled tensors within 1e-5 relative error in fp32 -- written below
+as |a-b| <= 1e-5 * max(1, |b|) for grid coordinates (range [-1,1]) and |a-b| <= 1e-5 * max|b| for resampled
+tensors GIVEN THE SAME GRID; argmax masks bit-exact except where the oracle's top-2 scores tie to within 1e-5.
+Integer outputs (scatter winners, selected points, their order) are compared bit-exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+
+GRID_CASES = ["grid_80_R45", "grid_80_R45_seg520", "grid_40x80_R12_reflect", "grid_40x80_R12_zero", "grid_32_R10_eval"]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (run on the B200 box with -m gpu)")
+    from fovea import ops as _ops
+    _ops._lib.load()
+    return _ops
+
+
+def _load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz")))
+
+
+def _geom(g):
+    gh, gw = g["xs"].shape[-2:]
+    return gh, gw, int(g["Rx"]), int(g["Ry"]), str(g["pad_mode"])
+
+
+def _close_grid(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    assert err.max() <= 1e-5, f"grid rel err {err.max():.3e}"
+
+
+def _close_rel(a, b, tol=1e-5):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN patterns differ"
+    scale = np.nanmax(np.abs(b)) if np.isfinite(b).any() else 1.0
+    err = np.nanmax(np.abs(a - b)) if np.isfinite(b).any() else 0.0
+    assert err <= tol * scale, f"max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ stage 1
+
+@pytest.mark.parametrize("name", GRID_CASES)
+def test_grid_matches_reference_golden(ops, golden_dir, name):
+    g = _load(golden_dir, name)
+    gh, gw, Rx, Ry, pad = _geom(g)
+    g1x, g1y = ops.separable_factors(torch.from_numpy(g["filt"]))
+    g1x, g1y = g1x.cuda(), g1y.cuda()
+    xs = torch.from_numpy(g["xs"]).cuda()
+    task, task_eval, rate = tuple(int(v) for v in g["task"]), tuple(int(v) for v in g["task_eval"]), int(g["rate"])
+    # fused padding (saliency map in, padded map never materialised)
+    grid = ops.saliency_to_grid(xs, g1x, g1y, gh, gw, Rx, Ry, pad, task)
+    _close_grid(grid.cpu().numpy(), g["grid"])
+    # the reference-shaped call: create_grid(xs_hm) on the padded map
+    xs_hm = rp.pad_saliency(torch.from_numpy(g["xs"]), Rx, Ry, pad).cuda()
+    grid2 = ops.saliency_to_grid(xs_hm, g1x, g1y, gh, gw, Rx, Ry, "none", task)
+    _close_grid(grid2.cpu().numpy(), g["grid"])
+    # label grid (second Upsample, models/models.py:627-631)
+    grid_y = ops.grid_resize(grid, tuple(t // rate for t in task))
+    _close_grid(grid_y.cpu().numpy(), g["grid_y"])
+    # inference-size grid
+    infer = task_eval if len(task_eval) else task
+    grid3 = ops.saliency_to_grid(xs, g1x, g1y, gh, gw, Rx, Ry, pad, infer)
+    _close_grid(grid3.cpu().numpy(), g["grid_infer"])
+
+
+@pytest.mark.parametrize("name", ["grid_80_R45", "grid_40x80_R12_reflect", "grid_40x80_R12_zero", "grid_32_R10_eval"])
+@pytest.mark.parametrize("padded_input", [False, True])
+def test_grid_backward_matches_autograd_oracle(ops, golden_dir, name, padded_input):
+    g = _load(golden_dir, name)
+    gh, gw, Rx, Ry, pad = _geom(g)
+    filt, P = torch.from_numpy(g["filt"]), torch.from_numpy(g["P_basis"])
+    task = tuple(int(v) for v in g["task"])
+    xs_cpu = torch.from_numpy(g["xs"]).clone().requires_grad_(True)
+    xs_hm = rp.pad_saliency(xs_cpu, Rx, Ry, pad)
+    grid_ref, _ = rp.create_grid(xs_hm, filt, P, gh, gw, task)
+    gen = torch.Generator().manual_seed(11)
+    up = torch.randn(grid_ref.shape, generator=gen)
+    (grid_ref * up).sum().backward()
+    g1x, g1y = (t.cuda() for t in ops.separable_factors(filt))
+    if padded_input:
+        xin = rp.pad_saliency(torch.from_numpy(g["xs"]), Rx, Ry, pad).cuda().requires_grad_(True)
+        grid = ops.saliency_to_grid(xin, g1x, g1y, gh, gw, Rx, Ry, "none", task)
+        (grid * up.cuda()).sum().backward()
+        # fold the padded gradient exactly as autograd's pad backward does
+        xs_leaf = torch.from_numpy(g["xs"]).clone().requires_grad_(True)
+        rp.pad_saliency(xs_leaf, Rx, Ry, pad).backward(xin.grad.cpu())
+        got = xs_leaf.grad
+    else:
+        xin = torch.from_numpy(g["xs"]).cuda().requires_grad_(True)
+        grid = ops.saliency_to_grid(xin, g1x, g1y, gh, gw, Rx, Ry, pad, task)
+        (grid * up.cuda()).sum().backward()
+        got = xin.grad.cpu()
+    _close_rel(got.numpy(), xs_cpu.grad.numpy(), tol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ stage 2
+
+@pytest.mark.parametrize("name", ["inverse_80_to_128", "inverse_80_to_520"])
+def test_grid_sample_matches_reference_golden(ops, golden_dir, name):
+    g = _load(golden_dir, name)
+    grid = torch.from_numpy(g["grid"])
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.rand(grid.shape[0], 3, int(g["x_hw"][0]), int(g["x_hw"][1]), generator=gen)
+    out = ops.grid_sample(x.cuda(), grid.cuda()).cpu().numpy()
+    # same fp32 arithmetic as aten's kernel: agreement is at the last-bit level, far inside 1e-5
+    np.testing.assert_allclose(out, g["x_sampled"], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 1024, 1024), (1, 1, 300, 500), (2, 51, 80, 80)])
+def test_grid_sample_forward_backward_vs_oracle(ops, shape):
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(B, C, H, W, generator=gen)
+    xs, _ = rp.synthetic_saliency(B, 80, 80, seed=9)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    grid = grid.detach()
+    grid[0, 0, :4, 0] = torch.tensor([-1.0, 1.0, -1.2, 1.3])  # borders + out-of-range taps (zeros padding)
+    x_ref = x.clone().requires_grad_(True)
+    g_ref = grid.clone().requires_grad_(True)
+    out_ref = rp.grid_sample(x_ref, g_ref)
+    up = torch.randn(out_ref.shape, generator=gen)
+    (out_ref * up).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    gg = grid.cuda().requires_grad_(True)
+    out = ops.grid_sample(xg, gg)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), out_ref.detach().numpy(), rtol=0, atol=2e-7 * max(1, C // 8))
+    (out * up.cuda()).sum().backward()
+    _close_rel(gg.grad.cpu().numpy(), g_ref.grad.numpy(), tol=1e-5)
+    _close_rel(xg.grad.cpu().numpy(), x_ref.grad.numpy(), tol=1e-5)
+    # input without grad (the image / label case): only grad_grid is produced
+    gg2 = grid.cuda().requires_grad_(True)
+    (ops.grid_sample(x.cuda(), gg2) * up.cuda()).sum().backward()
+    _close_rel(gg2.grad.cpu().numpy(), g_ref.grad.numpy(), tol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ stage 3
+
+def _oracle_points(ps_nan_one):
+    mask, invalid = rp.pixels_for_interp(ps_nan_one)
+    rr, cc = torch.where(mask[0])
+    return torch.stack([rr, cc], 1).numpy()
+
+
+@pytest.mark.parametrize("name,grid_name,C", [("inverse_80_to_128", "grid_80_R45", 5),
+                                              ("inverse_80_to_520", "grid_80_R45_seg520", 2)])
+def test_inverse_pieces_match_oracle(ops, golden_dir, name, grid_name, C):
+    g, gg = _load(golden_dir, name), _load(golden_dir, grid_name)
+    grid = torch.from_numpy(g["grid"])
+    pred = torch.from_numpy(g["pred"])
+    seg = tuple(int(s) for s in gg["segSize"])
+    B, h, w, _ = grid.shape
+    # A7: winners and the float canvas, bit-exact under the deterministic tie rule
+    win = ops.grid_inv_scatter(grid.cuda(), seg)
+    assert np.array_equal(win.cpu().numpy(), rp.grid_inverse_winner(grid, seg).numpy())
+    canvas = ops.grid_inv_canvas(win, h, w).cpu().numpy()
+    assert np.array_equal(canvas, rp.grid_inverse(grid, seg, tie="max").numpy(), equal_nan=True)
+    # ... and equal to the reference's own canvas wherever the reference's winner is defined (no collision)
+    ref_canvas = gg["grid_inv"]
+    assert np.array_equal(np.isnan(canvas), np.isnan(ref_canvas))
+    same = np.isclose(canvas, ref_canvas, equal_nan=True).all(-1)
+    assert same.mean() > 0.99
+    # A8 at the nodes == F.grid_sample(pred, grid_inv) at the winners' pixels
+    ps_nan = rp.inverse_sample(pred, rp.grid_inverse(grid, seg, tie="max"))
+    table = ops.box4_table(pred.cuda()).cpu()
+    assert torch.isnan(table[:, h * w, :]).all()
+    wn = win.cpu().long()
+    for b in range(B):
+        ys, xs_ = torch.where(wn[b] >= 0)
+        got = table[b, wn[b, ys, xs_], :C]
+        want = ps_nan[b, :, ys, xs_].T
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=1e-6)
+    # A9 point selection: same set, same (row-major) order as torch.where on the reference's mask
+    plan = ops.build_inverse_plan(grid.cuda(), seg, nchan=C, triangulation="host")
+    npts = plan.npts.cpu().numpy()
+    pts = plan.pts.cpu().numpy()
+    for b in range(B):
+        want = _oracle_points(ps_nan[b])
+        got = np.stack([pts[b, : npts[b]] >> 16, pts[b, : npts[b]] & 0xFFFF], 1)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name,grid_name,C", [("inverse_80_to_128", "grid_80_R45", 5),
+                                              ("inverse_80_to_520", "grid_80_R45_seg520", 2)])
+@pytest.mark.parametrize("zero_residual", [False, True])
+def test_inverse_fill_matches_oracle_and_golden(ops, golden_dir, name, grid_name, C, zero_residual):
+    g, gg = _load(golden_dir, name), _load(golden_dir, grid_name)
+    grid, pred = torch.from_numpy(g["grid"]), torch.from_numpy(g["pred"])
+    seg = tuple(int(s) for s in gg["segSize"])
+    want = rp.inverse_path(pred, grid, seg, zero_residual=zero_residual, tie="max")
+    plan = ops.build_inverse_plan(grid.cuda(), seg, nchan=C, triangulation="host")
+    scores, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=True, want_mask=True, zero_residual=zero_residual)
+    _close_rel(scores.cpu().numpy(), want.numpy(), tol=1e-5)
+    _check_masks(mask.cpu(), want)
+    # stand-alone argmax pass == fused argmax == torch.argmax of our own scores
+    assert torch.equal(ops.argmax_classes(scores), mask)
+    assert torch.equal(torch.argmax(scores, dim=1), mask)
+    # mask-only mode writes the same mask without materialising scores
+    _, mask2 = ops.inverse_fill(plan, pred.cuda(), want_scores=False, want_mask=True, zero_residual=zero_residual)
+    assert torch.equal(mask2, mask)
+    # against the unmodified reference's own output: identical except around its undefined collision winners
+    ref = g["pred_sampled"].copy()
+    if zero_residual:
+        ref[np.isnan(ref)] = 0
+    ok = np.isclose(scores.cpu().numpy(), ref, rtol=1e-5, atol=1e-5, equal_nan=True)
+    assert ok.mean() > 0.9, f"only {ok.mean():.3f} of pixels agree with the reference golden"
+
+
+def _check_masks(mask, want_scores, tie=1e-5):
+    want_mask = rp.instance_mask(want_scores)
+    diff = mask != want_mask
+    if diff.any():
+        top2 = torch.topk(torch.nan_to_num(want_scores, nan=float("inf")), 2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1]).abs()
+        assert (gap[diff] <= tie).all(), f"{int(diff.sum())} mask pixels differ away from ties"
+
+
+def test_inverse_fill_full_resolution_1024(ops):
+    """BASELINE geometry (80x80 grid -> 1024^2, C=51) against the oracle on one image + size-independent checks."""
+    B, C, H, W = 2, 51, 1024, 1024
+    xs, _ = rp.synthetic_saliency(B, seed=21)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    pred = rp.synthetic_pred(B, C, seed=21)
+    plan = ops.build_inverse_plan(grid.cuda(), (H, W), nchan=C, triangulation="host")
+    scores, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=True, want_mask=True)
+    want = rp.inverse_path(pred[:1], grid[:1], (H, W))
+    _close_rel(scores[:1].cpu().numpy(), want.numpy(), tol=1e-5)
+    _check_masks(mask[:1].cpu(), want)
+    # pixels that received a node carry exactly that node's table row
+    table = ops.box4_table(pred.cuda())
+    win = plan.winner.long()
+    b, ys, xs_ = torch.where(win >= 0)
+    assert torch.equal(scores[b, :, ys, xs_], table[b, win[b, ys, xs_], :C])
+    # linearity in pred (interpolation weights do not depend on the values)
+    pred2 = rp.synthetic_pred(B, C, seed=22)
+    s2, _ = ops.inverse_fill(plan, pred2.cuda())
+    s12, _ = ops.inverse_fill(plan, (0.5 * pred + 2.0 * pred2).cuda())
+    lin = 0.5 * scores + 2.0 * s2
+    assert (s12 - lin).abs().max() <= 1e-5 * lin.abs().max()
+    assert torch.equal(torch.argmax(scores, dim=1), mask)
