@@ -32,6 +32,18 @@ struct Located {
   ushort4 v;
 };
 
+// Tie rule for a query that lies EXACTLY on an edge (or vertex): the pixel belongs to the triangle that contains
+// the symbolically perturbed point q + (d_row = eps^2, d_col = -eps) -- a top-left fill rule, so every pixel inside
+// the hull has exactly one owner and the result does not depend on where the walk started.  (The reference's
+// find_simplex accepts whichever eps-tolerant triangle its sequential warm-started walk meets first,
+// spatial/qhull.pyx:1367-1467; this rule reproduces that choice for ~82% of on-edge pixels.  The choice only
+// shows where one of the two triangles has a NaN vertex, because the interpolant is continuous across edges.)
+__device__ __forceinline__ bool edge_owned(long long e, long long s, int ar, int ac, int br, int bc) {
+  if (e != 0) return e > 0;
+  const int dr = br - ar;
+  return dr != 0 ? (s * dr > 0) : (s * (bc - ac) > 0);
+}
+
 __device__ __forceinline__ bool test_triangle(const Mesh& m, int t, int qr, int qc, Located& out, int& next) {
   const ushort4 v = m.tris[t];
   const int p0 = m.pts[v.x], p1 = m.pts[v.y], p2 = m.pts[v.z];
@@ -44,9 +56,14 @@ __device__ __forceinline__ bool test_triangle(const Mesh& m, int t, int qr, int 
   const long long e2 = A - e0 - e1;  // == s*orient(p0,p1,q)
   next = -1;
   if (A == 0) return false;
-  if (e0 < 0) { next = m.nbrs[t].x; return false; }
-  if (e1 < 0) { next = m.nbrs[t].y; return false; }
-  if (e2 < 0) { next = m.nbrs[t].z; return false; }
+  const bool strict = e0 > 0 && e1 > 0 && e2 > 0;  // the common case: no neighbour lookups at all
+  if (!strict) {
+    const ushort4 nb = m.nbrs[t];
+    // an edge on the convex hull owns its pixels (there is no neighbour to hand them to)
+    if (!(edge_owned(e0, s, r1, c1, r2, c2) || (e0 == 0 && nb.x == kNoTri))) { next = nb.x; return false; }
+    if (!(edge_owned(e1, s, r2, c2, r0, c0) || (e1 == 0 && nb.y == kNoTri))) { next = nb.y; return false; }
+    if (!(edge_owned(e2, s, r0, c0, r1, c1) || (e2 == 0 && nb.z == kNoTri))) { next = nb.z; return false; }
+  }
   out.tri = t; out.a0 = e0; out.a1 = e1; out.area = A; out.v = v;
   return true;
 }
