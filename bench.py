@@ -147,7 +147,7 @@ class Path:
         from fovea.ops import _ptr, _stream
         cfg = self.cfg
         _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
-                  _ptr(plan.tris), _ptr(plan.nbrs), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), cfg["B"], cfg["C"],
+                  _ptr(plan.mesh), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), cfg["B"], cfg["C"],
                   table.shape[2], cfg["g"], cfg["g"], cfg["H"], cfg["W"], plan.cap, plan.tcap, 1,
                   _ptr(self.scores) if want_scores else None, _ptr(self.mask) if want_mask else None, _stream())
 

@@ -1,16 +1,474 @@
-// Device Delaunay triangulation (placeholder until the kernel lands; the host-Qhull parity mode does not use it).
+// Device Delaunay triangulation: one CTA (1024 threads) per image, the whole mesh in shared memory.
+//
+// Replaces the host Qhull call of the reference (interp2d.py:55, spatial/qhull.pyx:1679) for the <= ~6.4k integer
+// pixel sites of one image.  Input points arrive sorted row-major and unique (fovea_select_points).
+//
+//   1. rows      : group points by pixel row (block scan).
+//   2. strips    : the band between two consecutive occupied rows is triangulated by the merge ("zipper") of the
+//                  two sorted rows -- closed form per row edge (two binary searches), so all strip triangles and
+//                  their adjacency are produced in parallel with no hashing.
+//   3. pockets   : the two regions between the left/right chain of row end points and the convex hull are
+//                  monotone mountains; they are closed by PARALLEL ear clipping (independent sets of convex chain
+//                  vertices per round), which also yields the hull edges.
+//   4. Lawson    : parallel edge flips with exact int64 in-circle tests until every interior edge is locally
+//                  Delaunay.  Each round every dirty triangle proposes one illegal edge; proposals claim their two
+//                  triangles and the four outer neighbours with a random-priority atomicMin, winners flip.
+//                  Random priorities matter: with index priorities the skinny strips serialise (~10^4 rounds on a
+//                  1024^2 frame, ~150 with random ones; measured in the NumPy prototype of this algorithm).
+//
+// Exactness: coordinates < 8192 keep the 4th-order in-circle determinant inside int64 (checked on the host).
+// Co-circular point sets (ubiquitous on a pixel lattice) have no unique Delaunay triangulation; any locally
+// Delaunay result is accepted (in-circle == 0 is legal), exactly as Qhull's 'Qt' picks an arbitrary one.
 #include "common.cuh"
+
+namespace fovea {
+
+constexpr int kDtThreads = 1024;
+constexpr unsigned kNoneCode = 0xFFFFu;     // hull edge
+constexpr unsigned kPendingCode = 0xFFFEu;  // chain edge of an empty strip (both pockets touch it)
+constexpr unsigned kFixLeft = 0xFFFDu;      // strip triangle whose left neighbour slot is filled in pass 2
+
+struct DtArrays {
+  unsigned short *v0, *v1, *v2;  // vertex ids, counter-clockwise in (x=col, y=row)
+  unsigned short *n0, *n1, *n2;  // neighbour codes: (triangle << 2) | slot-in-neighbour, opposite v0/v1/v2
+  unsigned* lock;                // [tcap] flip claims (aliased by the construction scratch below)
+  unsigned* dirty;               // [ceil(tcap/32)] bitmask
+  unsigned short* rowStart;      // [n+1]
+  // construction scratch, aliased onto `lock`
+  unsigned short *stripBase, *cprev, *cnext, *cown;
+};
+
+__device__ __forceinline__ int pt_row(int p) { return p >> 16; }
+__device__ __forceinline__ int pt_col(int p) { return p & 0xFFFF; }
+
+__device__ __forceinline__ long long orient_pts(int a, int b, int c) {
+  return static_cast<long long>(pt_col(b) - pt_col(a)) * (pt_row(c) - pt_row(a)) -
+         static_cast<long long>(pt_row(b) - pt_row(a)) * (pt_col(c) - pt_col(a));
+}
+
+// > 0  <=>  d strictly inside the circumcircle of the counter-clockwise triangle (a,b,c)
+__device__ __forceinline__ long long incircle_pts(int a, int b, int c, int d) {
+  const long long ax = pt_col(a) - pt_col(d), ay = pt_row(a) - pt_row(d);
+  const long long bx = pt_col(b) - pt_col(d), by = pt_row(b) - pt_row(d);
+  const long long cx = pt_col(c) - pt_col(d), cy = pt_row(c) - pt_row(d);
+  return (ax * ax + ay * ay) * (bx * cy - by * cx) - (bx * bx + by * by) * (ax * cy - ay * cx) +
+         (cx * cx + cy * cy) * (ax * by - ay * bx);
+}
+
+__device__ __forceinline__ unsigned hash32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+// exclusive block scan of one int per thread; returns the exclusive prefix, `total` = block sum
+__device__ int block_scan_excl(int v, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_sums[lane] = wi - w;  // exclusive warp offsets
+    if (lane == 31) warp_sums[32] = wi;
+  }
+  __syncthreads();
+  const int res = warp_sums[warp] + incl - v;
+  total = warp_sums[32];
+  __syncthreads();
+  return res;
+}
+
+// number of x in [0,cnt) with col(pts[first+x]) < key  (strict)  /  <= key (non-strict)
+__device__ __forceinline__ int count_less(const int32_t* pts, int first, int cnt, int key, bool or_equal) {
+  int lo = 0, hi = cnt;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = pt_col(pts[first + mid]);
+    if (or_equal ? (c <= key) : (c < key)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ unsigned short& nb_slot(const DtArrays& A, int t, int k) {
+  return k == 0 ? A.n0[t] : (k == 1 ? A.n1[t] : A.n2[t]);
+}
+__device__ __forceinline__ unsigned short vert(const DtArrays& A, int t, int k) {
+  return k == 0 ? A.v0[t] : (k == 1 ? A.v1[t] : A.v2[t]);
+}
+__device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsigned me) {
+  if (code < kPendingCode) nb_slot(A, code >> 2, code & 3) = static_cast<unsigned short>(me);
+}
+
+__global__ void __launch_bounds__(kDtThreads, 1)
+delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
+                uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
+                int max_rounds, int32_t* __restrict__ dbg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int warp_sums[33];
+  __shared__ int s_ntri;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int32_t* pts = pts_g + static_cast<size_t>(b) * cap;
+  const int n = npts[b];
+
+  DtArrays A;
+  {
+    unsigned char* p = smem_raw;
+    A.v0 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
+    A.v1 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
+    A.v2 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
+    A.n0 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
+    A.n1 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
+    A.n2 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
+    A.lock = reinterpret_cast<unsigned*>(p); p += 4 * tcap;
+    A.dirty = reinterpret_cast<unsigned*>(p); p += 4 * ((tcap + 31) / 32);
+    A.rowStart = reinterpret_cast<unsigned short*>(p);
+    unsigned short* s = reinterpret_cast<unsigned short*>(A.lock);  // 2*tcap shorts of scratch
+    A.stripBase = s;
+    A.cprev = s + cap;
+    A.cnext = s + 2 * cap;
+    A.cown = s + 3 * cap;
+  }
+  uint16_t* mesh = mesh_out + static_cast<size_t>(b) * tcap * 8;
+  if (dbg && tid == 0) { dbg[b * 8 + 0] = 1; dbg[b * 8 + 1] = n; }
+
+  // ------------------------------------------------------------------ 1. rows
+  const int items = (n + kDtThreads - 1) / kDtThreads;
+  const int base = tid * items;
+  int cnt = 0;
+  for (int i = 0; i < items; ++i) {
+    const int p = base + i;
+    if (p < n && (p == 0 || pt_row(pts[p]) != pt_row(pts[p - 1]))) ++cnt;
+  }
+  int R;
+  int off = block_scan_excl(cnt, warp_sums, R);
+  for (int i = 0; i < items; ++i) {
+    const int p = base + i;
+    if (p < n && (p == 0 || pt_row(pts[p]) != pt_row(pts[p - 1]))) A.rowStart[off++] = static_cast<unsigned short>(p);
+  }
+  if (tid == 0) A.rowStart[R] = static_cast<unsigned short>(n);
+  __syncthreads();
+  if (n < 3 || R < 2) {  // nothing to triangulate (all points collinear in one row)
+    if (tid == 0) { ntri_out[b] = 0; if (rounds_out) rounds_out[b] = 0; }
+    return;
+  }
+
+  // ------------------------------------------------------------------ 2. strips
+  const int nstrips = R - 1;
+  const int sitems = (nstrips + kDtThreads - 1) / kDtThreads;
+  const int sbase = tid * sitems;
+  cnt = 0;
+  for (int i = 0; i < sitems; ++i) {
+    const int r = sbase + i;
+    if (r < nstrips) cnt += static_cast<int>(A.rowStart[r + 2]) - static_cast<int>(A.rowStart[r]) - 2;
+  }
+  int nstrip_tris;
+  off = block_scan_excl(cnt, warp_sums, nstrip_tris);
+  for (int i = 0; i < sitems; ++i) {
+    const int r = sbase + i;
+    if (r < nstrips) {
+      A.stripBase[r] = static_cast<unsigned short>(off);
+      const int c = static_cast<int>(A.rowStart[r + 2]) - static_cast<int>(A.rowStart[r]) - 2;
+      off += c;
+      // chain-edge owners default to "empty strip"; overwritten below when the strip has triangles
+      A.cown[r] = static_cast<unsigned short>(c == 0 ? kPendingCode : kNoneCode);   // left chain owners
+      A.cnext[r] = static_cast<unsigned short>(c == 0 ? kPendingCode : kNoneCode);  // right chain owners (temp)
+    }
+  }
+  __syncthreads();
+
+  for (int p = tid; p + 1 < n; p += kDtThreads) {
+    // row of p: largest r with rowStart[r] <= p
+    int lo = 0, hi = R - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (A.rowStart[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    const int r = lo;
+    const int rs = A.rowStart[r], re = A.rowStart[r + 1];
+    if (p + 1 >= re) continue;  // p is the last point of its row: no row edge (p, p+1)
+    const int a = p - rs;
+    const int key = pt_col(pts[p + 1]);
+    int idD = -1, idU = -1, j = 0, iu = 0;
+    if (r + 1 < R) {  // (p,p+1) is a top edge of strip r: "down" triangle (p, p+1, bottom_j)
+      const int bs = A.rowStart[r + 1], nb = A.rowStart[r + 2] - bs;
+      j = count_less(pts, bs + 1, nb - 1, key, false);
+      idD = A.stripBase[r] + a + j;
+    }
+    if (r > 0) {  // (p,p+1) is a bottom edge of strip r-1: "up" triangle (top_i, p+1, p)
+      const int ts = A.rowStart[r - 1], nt = rs - ts;
+      iu = count_less(pts, ts + 1, nt - 1, key, true);
+      idU = A.stripBase[r - 1] + a + iu;
+    }
+    if (idD >= 0) {
+      const int bs = A.rowStart[r + 1];
+      const int scount = static_cast<int>(A.rowStart[r + 2]) - rs - 2;
+      const int pos = idD - A.stripBase[r];
+      A.v0[idD] = static_cast<unsigned short>(p);
+      A.v1[idD] = static_cast<unsigned short>(p + 1);
+      A.v2[idD] = static_cast<unsigned short>(bs + j);
+      A.n2[idD] = static_cast<unsigned short>(idU >= 0 ? ((idU << 2) | 0) : kNoneCode);
+      if (pos == scount - 1) { A.n0[idD] = kNoneCode; A.cnext[r] = static_cast<unsigned short>((idD << 2) | 0); }
+      else A.n0[idD] = static_cast<unsigned short>(((idD + 1) << 2) | 1);
+      if (pos == 0) { A.n1[idD] = kNoneCode; A.cown[r] = static_cast<unsigned short>((idD << 2) | 1); }
+      else A.n1[idD] = kFixLeft;
+    }
+    if (idU >= 0) {
+      const int ts = A.rowStart[r - 1];
+      const int scount = re - ts - 2;
+      const int pos = idU - A.stripBase[r - 1];
+      A.v0[idU] = static_cast<unsigned short>(ts + iu);
+      A.v1[idU] = static_cast<unsigned short>(p + 1);
+      A.v2[idU] = static_cast<unsigned short>(p);
+      A.n0[idU] = static_cast<unsigned short>(idD >= 0 ? ((idD << 2) | 2) : kNoneCode);
+      if (pos == scount - 1) { A.n2[idU] = kNoneCode; A.cnext[r - 1] = static_cast<unsigned short>((idU << 2) | 2); }
+      else A.n2[idU] = static_cast<unsigned short>(((idU + 1) << 2) | 1);
+      if (pos == 0) { A.n1[idU] = kNoneCode; A.cown[r - 1] = static_cast<unsigned short>((idU << 2) | 1); }
+      else A.n1[idU] = kFixLeft;
+    }
+  }
+  if (tid == 0) { s_ntri = nstrip_tris; if (dbg) { dbg[b * 8 + 0] = 2; dbg[b * 8 + 2] = R; dbg[b * 8 + 3] = nstrip_tris; } }
+  __syncthreads();
+  // pass 2: left neighbour's slot depends on that neighbour's kind (down: right diagonal opposite v0, up: opposite v2)
+  for (int t = tid; t < nstrip_tris; t += kDtThreads) {
+    if (A.n1[t] == kFixLeft) {
+      const bool prev_down = A.v1[t - 1] == A.v0[t - 1] + 1;
+      A.n1[t] = static_cast<unsigned short>(((t - 1) << 2) | (prev_down ? 0 : 2));
+    }
+  }
+  __syncthreads();
+  // right-chain owners were parked in cnext; move them into the (now dead) stripBase array
+  unsigned short* rown = A.stripBase;
+  for (int r = tid; r < nstrips; r += kDtThreads) {
+    rown[r] = A.cnext[r];
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ 3. pockets (left, then right)
+  // cprev[m]: bits 0..12 = previous alive chain vertex (kCNone = chain start), bit 13 DEAD, bit 14 SELECTED, bit 15 EAR
+  constexpr unsigned kCIdx = 0x1FFFu, kCNone = 0x1FFFu, kCDead = 0x2000u, kCSel = 0x4000u, kCEar = 0x8000u;
+  for (int side = 0; side < 2; ++side) {
+    auto cpt = [&](int m) { return side == 0 ? static_cast<int>(A.rowStart[m]) : static_cast<int>(A.rowStart[m + 1]) - 1; };
+    auto cpri = [&](int m, int round) {
+      return (hash32(static_cast<unsigned>(m) * 2654435761u + static_cast<unsigned>(round) * 40503u + side) << 13) |
+             static_cast<unsigned>(m);
+    };
+    for (int m = tid; m < R; m += kDtThreads) {
+      A.cprev[m] = static_cast<unsigned short>(m == 0 ? kCNone : m - 1);
+      A.cnext[m] = static_cast<unsigned short>(m == R - 1 ? kCNone : m + 1);
+      if (side == 1 && m < nstrips) A.cown[m] = rown[m];
+    }
+    __syncthreads();
+    for (int round = 0; round < 4 * R + 64; ++round) {
+      if (dbg && tid == 0) dbg[b * 8 + 4 + side] = round;
+      // phase 1: which alive interior chain vertices are ears (strictly convex towards the pocket)?
+      for (int m = tid; m < R; m += kDtThreads) {
+        const unsigned cp = A.cprev[m];
+        if (cp & kCDead) continue;
+        const unsigned pv = cp & kCIdx, nx = A.cnext[m];
+        bool ear = false;
+        if (pv != kCNone && nx != kCNone) {
+          const long long o = orient_pts(pts[cpt(pv)], pts[cpt(m)], pts[cpt(nx)]);
+          ear = side == 0 ? (o > 0) : (o < 0);
+        }
+        A.cprev[m] = static_cast<unsigned short>(pv | (ear ? kCEar : 0u));
+      }
+      __syncthreads();
+      // phase 2a: independent set -- an ear is selected iff it beats both neighbouring ears (random priority)
+      bool selected_any = false;
+      for (int m = tid; m < R; m += kDtThreads) {
+        const unsigned cp = A.cprev[m];
+        if ((cp & kCDead) || !(cp & kCEar)) continue;
+        const unsigned pv = cp & kCIdx, nx = A.cnext[m];
+        const unsigned pri = cpri(m, round);
+        const unsigned cpp = A.cprev[pv], cpn = A.cprev[nx];
+        if ((cpp & kCEar) && cpri(pv, round) < pri) continue;
+        if ((cpn & kCEar) && cpri(nx, round) < pri) continue;
+        selected_any = true;
+        A.cprev[m] = static_cast<unsigned short>(cp | kCSel);
+      }
+      if (!__syncthreads_or(selected_any)) break;
+      // phase 2b: clip the selected ears (their neighbours are not selected, so the list surgery is race-free)
+      for (int m = tid; m < R; m += kDtThreads) {
+        const unsigned cp = A.cprev[m];
+        if ((cp & kCDead) || !(cp & kCSel)) continue;
+        const int pv = cp & kCIdx, nx = A.cnext[m];
+        const int E = atomicAdd(&s_ntri, 1);
+        const int P = cpt(pv), M = cpt(m), N = cpt(nx);
+        // left : (P,M,N) is ccw: edge(P,M) opposite v2, edge(M,N) opposite v0, edge(N,P) opposite v1
+        // right: (P,N,M) is ccw: edge(P,M) opposite v1, edge(M,N) opposite v0, edge(P,N) opposite v2
+        const int s_pm = side == 0 ? 2 : 1, s_mn = 0, s_pn = side == 0 ? 1 : 2;
+        A.v0[E] = static_cast<unsigned short>(P);
+        A.v1[E] = static_cast<unsigned short>(side == 0 ? M : N);
+        A.v2[E] = static_cast<unsigned short>(side == 0 ? N : M);
+        unsigned own_pm = A.cown[pv], own_mn = A.cown[m];
+        if (own_pm == kPendingCode) {  // edge of an empty strip: the right pocket owns its far side (if anyone)
+          if (side == 0) rown[pv] = static_cast<unsigned short>((E << 2) | s_pm);
+          own_pm = kNoneCode;
+        }
+        if (own_mn == kPendingCode) {
+          if (side == 0) rown[m] = static_cast<unsigned short>((E << 2) | s_mn);
+          own_mn = kNoneCode;
+        }
+        nb_slot(A, E, s_pm) = static_cast<unsigned short>(own_pm);
+        nb_slot(A, E, s_mn) = static_cast<unsigned short>(own_mn);
+        nb_slot(A, E, s_pn) = static_cast<unsigned short>(kNoneCode);
+        link_back(A, own_pm, (E << 2) | s_pm);
+        link_back(A, own_mn, (E << 2) | s_mn);
+        A.cown[pv] = static_cast<unsigned short>((E << 2) | s_pn);
+        A.cnext[pv] = static_cast<unsigned short>(nx);
+        A.cprev[nx] = static_cast<unsigned short>((A.cprev[nx] & ~kCIdx) | static_cast<unsigned>(pv));
+        A.cprev[m] = static_cast<unsigned short>(kCDead);
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+  const int T = s_ntri;
+  if (dbg && tid == 0) { dbg[b * 8 + 0] = 3; dbg[b * 8 + 6] = T; }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ 4. Lawson flips
+  for (int t = tid; t < tcap; t += kDtThreads) A.lock[t] = 0xFFFFFFFFu;
+  for (int w = tid; w < (tcap + 31) / 32; w += kDtThreads) {
+    const int lo = w * 32;
+    A.dirty[w] = lo + 32 <= T ? 0xFFFFFFFFu : (lo >= T ? 0u : ((1u << (T - lo)) - 1u));
+  }
+  __syncthreads();
+  int round = 0;
+  for (; round < max_rounds; ++round) {
+    if (dbg && tid == 0) dbg[b * 8 + 7] = round;
+    unsigned cand = 0;  // 2 bits per owned triangle: 0 = none, else edge slot + 1
+    bool any = false;
+    int it = 0;
+    for (int t = tid; t < T; t += kDtThreads, ++it) {
+      if (!((A.dirty[t >> 5] >> (t & 31)) & 1u)) continue;
+      int found = -1;
+      unsigned ucode = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (found >= 0) break;
+        const unsigned code = nb_slot(A, t, k);
+        if (code >= kPendingCode) continue;
+        const int u = code >> 2, ku = code & 3;
+        const int a = pts[vert(A, t, k)], bq = pts[vert(A, t, (k + 1) % 3)], c = pts[vert(A, t, (k + 2) % 3)];
+        const int d = pts[vert(A, u, ku)];
+        if (incircle_pts(a, bq, c, d) > 0) { found = k; ucode = code; }
+      }
+      if (found < 0) {
+        atomicAnd(&A.dirty[t >> 5], ~(1u << (t & 31)));
+        continue;
+      }
+      any = true;
+      cand |= static_cast<unsigned>(found + 1) << (2 * it);
+      const unsigned pri = (hash32(t * 2654435761u + round * 0x9E3779B9u) << 14) | static_cast<unsigned>(t);
+      const int u = ucode >> 2, ku = ucode & 3;
+      atomicMin(&A.lock[t], pri);
+      atomicMin(&A.lock[u], pri);
+      const unsigned o1 = nb_slot(A, t, (found + 1) % 3), o2 = nb_slot(A, t, (found + 2) % 3);
+      const unsigned o3 = nb_slot(A, u, (ku + 1) % 3), o4 = nb_slot(A, u, (ku + 2) % 3);
+      if (o1 < kPendingCode) atomicMin(&A.lock[o1 >> 2], pri);
+      if (o2 < kPendingCode) atomicMin(&A.lock[o2 >> 2], pri);
+      if (o3 < kPendingCode) atomicMin(&A.lock[o3 >> 2], pri);
+      if (o4 < kPendingCode) atomicMin(&A.lock[o4 >> 2], pri);
+    }
+    if (!__syncthreads_or(any)) break;
+    it = 0;
+    for (int t = tid; t < T; t += kDtThreads, ++it) {
+      const int sel = (cand >> (2 * it)) & 3;
+      if (!sel) continue;
+      const int k = sel - 1;
+      const unsigned pri = (hash32(t * 2654435761u + round * 0x9E3779B9u) << 14) | static_cast<unsigned>(t);
+      const unsigned ucode = nb_slot(A, t, k);
+      const int u = ucode >> 2, ku = ucode & 3;
+      const unsigned n_ca = nb_slot(A, t, (k + 1) % 3), n_ab = nb_slot(A, t, (k + 2) % 3);
+      const unsigned n_bd = nb_slot(A, u, (ku + 1) % 3), n_dc = nb_slot(A, u, (ku + 2) % 3);
+      bool win = A.lock[t] == pri && A.lock[u] == pri;
+      if (n_ca < kPendingCode) win = win && A.lock[n_ca >> 2] == pri;
+      if (n_ab < kPendingCode) win = win && A.lock[n_ab >> 2] == pri;
+      if (n_bd < kPendingCode) win = win && A.lock[n_bd >> 2] == pri;
+      if (n_dc < kPendingCode) win = win && A.lock[n_dc >> 2] == pri;
+      if (!win) continue;
+      const unsigned short a = vert(A, t, k), bq = vert(A, t, (k + 1) % 3), c = vert(A, t, (k + 2) % 3);
+      const unsigned short d = vert(A, u, ku);
+      // t <- (a,b,d), u <- (a,d,c); the new diagonal (a,d) is opposite v1 in t and opposite v2 in u
+      A.v0[t] = a; A.v1[t] = bq; A.v2[t] = d;
+      A.n0[t] = static_cast<unsigned short>(n_bd); A.n1[t] = static_cast<unsigned short>((u << 2) | 2);
+      A.n2[t] = static_cast<unsigned short>(n_ab);
+      A.v0[u] = a; A.v1[u] = d; A.v2[u] = c;
+      A.n0[u] = static_cast<unsigned short>(n_dc); A.n1[u] = static_cast<unsigned short>(n_ca);
+      A.n2[u] = static_cast<unsigned short>((t << 2) | 1);
+      link_back(A, n_bd, (t << 2) | 0);
+      link_back(A, n_ab, (t << 2) | 2);
+      link_back(A, n_dc, (u << 2) | 0);
+      link_back(A, n_ca, (u << 2) | 1);
+      atomicOr(&A.dirty[t >> 5], 1u << (t & 31));
+      atomicOr(&A.dirty[u >> 5], 1u << (u & 31));
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += kDtThreads) A.lock[t] = 0xFFFFFFFFu;
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ output: 16-byte records (v0,v1,v2,0,n0,n1,n2,0)
+  for (int t = tid; t < T; t += kDtThreads) {
+    const unsigned c0 = A.n0[t], c1 = A.n1[t], c2 = A.n2[t];
+    uint4 rec;
+    rec.x = static_cast<unsigned>(A.v0[t]) | (static_cast<unsigned>(A.v1[t]) << 16);
+    rec.y = static_cast<unsigned>(A.v2[t]);
+    rec.z = (c0 >= kPendingCode ? 0xFFFFu : (c0 >> 2)) | ((c1 >= kPendingCode ? 0xFFFFu : (c1 >> 2)) << 16);
+    rec.w = (c2 >= kPendingCode ? 0xFFFFu : (c2 >> 2));
+    reinterpret_cast<uint4*>(mesh)[t] = rec;
+  }
+  if (tid == 0) {
+    ntri_out[b] = T;
+    if (rounds_out) rounds_out[b] = round;
+  }
+}
+
+static size_t dt_smem_bytes(int cap, int tcap) {
+  return static_cast<size_t>(12) * tcap + 4 * static_cast<size_t>(tcap) + 4 * static_cast<size_t>((tcap + 31) / 32) +
+         2 * static_cast<size_t>(cap + 2);
+}
+
+}  // namespace fovea
 
 using namespace fovea;
 
 extern "C" int64_t fovea_delaunay_workspace_bytes(int B, int cap) {
-  (void)B; (void)cap;
-  return 16;
+  (void)cap;
+  return static_cast<int64_t>(B) * 4 * 9;  // flip-round count per image + 8 debug words per image
 }
 
-extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, uint16_t* tris,
-                              uint16_t* nbrs, int32_t* ntri, void* workspace, fovea_stream_t stream) {
-  (void)pts; (void)npts; (void)B; (void)cap; (void)tcap; (void)tris; (void)nbrs; (void)ntri; (void)workspace; (void)stream;
-  set_error("fovea_delaunay: device triangulation is not built into this library");
-  return FOVEA_ERR_ARG;
+extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
+                              uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream) {
+  FOVEA_REQUIRE(pts && npts && mesh && ntri, "fovea_delaunay: null pointer");
+  FOVEA_REQUIRE(B > 0 && cap >= 4 && tcap >= 2 * cap, "fovea_delaunay: need tcap >= 2*cap (cap=%d tcap=%d)", cap, tcap);
+  FOVEA_REQUIRE(max_coord > 0 && max_coord <= 8192,
+                "fovea_delaunay: coordinates must be < 8192 for the exact int64 in-circle test (got %d)", max_coord);
+  if (tcap > 16383 || cap > 8190) {
+    set_error("fovea_delaunay: tcap=%d exceeds the 16-bit mesh encoding (max 16383 triangles)", tcap);
+    return FOVEA_ERR_CAPACITY;
+  }
+  const size_t smem = dt_smem_bytes(cap, tcap);
+  if (smem > 227 * 1024) {
+    set_error("fovea_delaunay: %zu B of shared memory needed for cap=%d (> 227 KB); use the host triangulation", smem, cap);
+    return FOVEA_ERR_CAPACITY;
+  }
+  FOVEA_CUDA(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  delaunay_kernel<<<B, kDtThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      pts, npts, cap, tcap, mesh, ntri, static_cast<int32_t*>(workspace), 20000,
+      workspace ? static_cast<int32_t*>(workspace) + B : nullptr);
+  return check_launch("fovea_delaunay");
 }

@@ -64,7 +64,7 @@ box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int
   const int node0 = blockIdx.x * kTabNodes;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
   const float* pb = pred + static_cast<size_t>(b) * C * hw;
-  float* tb = table + static_cast<size_t>(b) * (hw + 1) * Cs;
+  float* tb = table + static_cast<size_t>(b) * (hw + 2) * Cs;
 
   const int node = node0 + lane;
   Taps t;
@@ -102,8 +102,11 @@ box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0)  // the NaN row: value of an image corner no node landed on
-    for (int c = threadIdx.x; c < Cs; c += kTabThreads) tb[static_cast<size_t>(hw) * Cs + c] = CUDART_NAN_F;
+  if (blockIdx.x == 0)  // row hw: NaN (an image corner no node landed on); row hw+1: zeros (NaN after NaN -> 0)
+    for (int c = threadIdx.x; c < Cs; c += kTabThreads) {
+      tb[static_cast<size_t>(hw) * Cs + c] = CUDART_NAN_F;
+      tb[static_cast<size_t>(hw + 1) * Cs + c] = 0.f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ A9 points
@@ -202,30 +205,35 @@ select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ hints
-constexpr int kHintThreads = 256;
+// One CTA per image stages the mesh records in shared memory (<= 205 KB) so that the long first-level walks run
+// at shared-memory latency; level 0 = 16x16 probes walked from triangle 0, level 1 = every 32x32-pixel cell
+// walked from the nearest probe.
+constexpr int kHintThreads = 512;
 
-__global__ void __launch_bounds__(kHintThreads)
-locate_hints_kernel(const int32_t* __restrict__ pts, const ushort4* __restrict__ tris, const ushort4* __restrict__ nbrs,
-                    const int32_t* __restrict__ ntri, int cap, int tcap, int H, int W, int32_t* __restrict__ hints) {
+__global__ void __launch_bounds__(kHintThreads, 1)
+locate_hints_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const int32_t* __restrict__ ntri,
+                    int cap, int tcap, int H, int W, int32_t* __restrict__ hints) {
+  extern __shared__ __align__(16) uint4 srec[];
   __shared__ int coarse[16 * 16];
   const int b = blockIdx.x, tid = threadIdx.x;
-  Mesh m{pts + static_cast<size_t>(b) * cap, tris + static_cast<size_t>(b) * tcap, nbrs + static_cast<size_t>(b) * tcap,
-         ntri[b]};
+  const int T = ntri[b];
   const int ch = ceil_div(H, FOVEA_HINT_CELL), cw = ceil_div(W, FOVEA_HINT_CELL);
   int32_t* hb = hints + static_cast<size_t>(b) * ch * cw;
-  if (m.ntri <= 0) {
+  if (T <= 0) {
     for (int i = tid; i < ch * cw; i += kHintThreads) hb[i] = 0;
     return;
   }
-  // level 0: 16x16 probes walked from triangle 0
-  {
+  const uint4* mb = mesh + static_cast<size_t>(b) * tcap;
+  for (int t = tid; t < T; t += kHintThreads) srec[t] = mb[t];
+  __syncthreads();
+  Mesh m{pts + static_cast<size_t>(b) * cap, srec, T};
+  if (tid < 256) {
     const int py = tid / 16, px = tid % 16;
     const int qr = min(H - 1, (2 * py + 1) * H / 32), qc = min(W - 1, (2 * px + 1) * W / 32);
     const Located L = locate(m, qr, qc, 0);
     coarse[tid] = L.tri < 0 ? 0 : L.tri;
   }
   __syncthreads();
-  // level 1: every hint cell walks from the nearest level-0 probe
   for (int i = tid; i < ch * cw; i += kHintThreads) {
     const int cy = i / cw, cx = i - cy * cw;
     const int qr = min(H - 1, cy * FOVEA_HINT_CELL + FOVEA_HINT_CELL / 2);
@@ -241,121 +249,118 @@ struct FillParams {
   int C, Cs, h, w, H, W, cap, tcap, zero_residual;
 };
 
-struct PixelSrc {
-  int n0, n1, n2;      // rows of the value table
-  float w0, w1, w2;    // barycentric weights (1,0,0 for a pixel that received a node)
-};
-
 constexpr int kFillThreads = 256;
 
-// Each thread owns 4 consecutive pixels of one row: locate them, then stream all channels with 128-bit stores.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Each thread owns 4 consecutive pixels of one row: locate them once, then stream all channels with 128-bit
+// stores.  Addressing is "uniform base + 32-bit per-thread offset" everywhere in the channel loop: the table base
+// advances with the channel group, the per-pixel row offsets (n*Cs) and the pixel offset (y*W+x0) never change.
 template <bool kScores, bool kMask>
 __global__ void __launch_bounds__(kFillThreads)
 inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
-                    const ushort4* __restrict__ tris, const ushort4* __restrict__ nbrs, const int32_t* __restrict__ ntri,
-                    const int32_t* __restrict__ hints, const float* __restrict__ table, float* __restrict__ scores,
-                    long long* __restrict__ mask, FillParams p) {
+                    const uint4* __restrict__ mesh, const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints,
+                    const float* __restrict__ table, float* __restrict__ scores, long long* __restrict__ mask,
+                    FillParams p) {
   const int b = blockIdx.z, y = blockIdx.y;
   const int x0 = (blockIdx.x * kFillThreads + threadIdx.x) * 4;
   if (x0 >= p.W) return;
   const int hw = p.h * p.w;
-  const size_t pix0 = (static_cast<size_t>(b) * p.H + y) * p.W + x0;
+  const unsigned pixoff = static_cast<unsigned>(y) * p.W + x0;  // H*W < 2^32 is checked on the host
+  const size_t plane = static_cast<size_t>(p.H) * p.W;
   const int32_t* srcb = src + static_cast<size_t>(b) * p.cap;
-  Mesh m{pts + static_cast<size_t>(b) * p.cap, tris + static_cast<size_t>(b) * p.tcap,
-         nbrs + static_cast<size_t>(b) * p.tcap, ntri[b]};
+  Mesh m{pts + static_cast<size_t>(b) * p.cap, mesh + static_cast<size_t>(b) * p.tcap, ntri[b]};
 
-  const int4 win = *reinterpret_cast<const int4*>(winner + pix0);
+  const int4 win = *reinterpret_cast<const int4*>(winner + static_cast<size_t>(b) * plane + pixoff);
   const int wn[4] = {win.x, win.y, win.z, win.w};
-  PixelSrc ps[4];
+  unsigned o0[4], o1[4], o2[4];  // element offsets of the three table rows of each pixel
+  float w0[4], w1[4], w2[4];     // barycentric weights ((1,0,0) for a pixel that received a node)
+  unsigned nanmask = 0;          // pixels whose value is NaN in every channel
   const int cw = ceil_div(p.W, FOVEA_HINT_CELL);
   int start = hints[(static_cast<size_t>(b) * ceil_div(p.H, FOVEA_HINT_CELL) + y / FOVEA_HINT_CELL) * cw +
                     x0 / FOVEA_HINT_CELL];
-  bool uniform = true;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    int n0 = hw, n1 = hw, n2 = hw;
+    float a0 = 1.f, a1 = 0.f, a2 = 0.f;
     if (wn[k] >= 0) {
-      ps[k] = PixelSrc{wn[k], wn[k], wn[k], 1.f, 0.f, 0.f};
+      n0 = n1 = n2 = wn[k];
     } else {
       const Located L = locate(m, y, x0 + k, start);
-      if (L.tri < 0) {
-        // outside the triangulation (cannot happen with the four corners present): NaN, like an unfilled corner
-        ps[k] = PixelSrc{hw, hw, hw, 1.f, 0.f, 0.f};
-      } else {
+      if (L.tri >= 0) {  // (outside the triangulation cannot happen with the four corners present: NaN row)
         start = L.tri;
         // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 from the transform, c2 = 1 - c0 - c1, in float64
         const double c0 = static_cast<double>(L.a0) / static_cast<double>(L.area);
         const double c1 = static_cast<double>(L.a1) / static_cast<double>(L.area);
-        const double c2 = 1.0 - c0 - c1;
-        ps[k] = PixelSrc{srcb[L.v.x], srcb[L.v.y], srcb[L.v.z], static_cast<float>(c0), static_cast<float>(c1),
-                         static_cast<float>(c2)};
+        a0 = static_cast<float>(c0);
+        a1 = static_cast<float>(c1);
+        a2 = static_cast<float>(1.0 - c0 - c1);
+        n0 = srcb[L.v01 & 0xFFFFu];
+        n1 = srcb[L.v01 >> 16];
+        n2 = srcb[L.v2];
       }
     }
-    if (k > 0)
-      uniform = uniform && ps[k].n0 == ps[0].n0 && ps[k].n1 == ps[0].n1 && ps[k].n2 == ps[0].n2;
+    if (n0 == hw || n1 == hw || n2 == hw) {  // a NaN vertex poisons every channel (NaN*w, even for w == 0)
+      nanmask |= 1u << k;
+      n0 = n1 = n2 = p.zero_residual ? hw + 1 : hw;  // models_instance.py:940: residual NaN -> 0
+      a0 = 1.f; a1 = 0.f; a2 = 0.f;
+    }
+    o0[k] = static_cast<unsigned>(n0) * p.Cs;
+    o1[k] = static_cast<unsigned>(n1) * p.Cs;
+    o2[k] = static_cast<unsigned>(n2) * p.Cs;
+    w0[k] = a0; w1[k] = a1; w2[k] = a2;
   }
-
-  const float* tb = table + static_cast<size_t>(b) * (hw + 1) * p.Cs;
-  const size_t plane = static_cast<size_t>(p.H) * p.W;
-  float* out = kScores ? scores + static_cast<size_t>(b) * p.C * plane + static_cast<size_t>(y) * p.W + x0 : nullptr;
+  // Byte offsets of the table rows; the channel loop adds them to one 64-bit base that advances by 16 B per group.
+  unsigned ob0[4], ob1[4], ob2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { ob0[k] = o0[k] * 4u; ob1[k] = o1[k] * 4u; ob2[k] = o2[k] * 4u; }
+  unsigned long long tbase = reinterpret_cast<unsigned long long>(table + static_cast<size_t>(b) * (hw + 2) * p.Cs);
+  unsigned long long obase = reinterpret_cast<unsigned long long>(
+      kScores ? scores + static_cast<size_t>(b) * p.C * plane + pixoff : nullptr);
+  const unsigned long long ostep = static_cast<unsigned long long>(plane) * 4ull;
+  // keep the hoisted bases in registers (ptxas otherwise rematerialises the 64-bit products inside the loop)
+  asm volatile("" : "+l"(tbase), "+l"(obase));
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int besti[4] = {0, 0, 0, 0};
-  bool bestnan[4] = {false, false, false, false};
 
-  for (int c = 0; c < p.Cs; c += 4) {
+  for (int c = 0; c < p.Cs; c += 4, tbase += 16ull) {
     float v[4][4];  // [pixel][channel]
-    if (uniform) {
-      const float4 a = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[0].n0) * p.Cs + c);
-      const float4 bq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[0].n1) * p.Cs + c);
-      const float4 cq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[0].n2) * p.Cs + c);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int e = 0; e < 4; ++e)  // interp2d.py:85-89: mul, then sum over the 3 vertices in order
-          v[k][e] = __fadd_rn(__fadd_rn(__fmul_rn(av[e], ps[k].w0), __fmul_rn(bv[e], ps[k].w1)),
-                              __fmul_rn(cv[e], ps[k].w2));
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[k].n0) * p.Cs + c);
-        const float4 bq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[k].n1) * p.Cs + c);
-        const float4 cq = *reinterpret_cast<const float4*>(tb + static_cast<size_t>(ps[k].n2) * p.Cs + c);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          v[k][e] = __fadd_rn(__fadd_rn(__fmul_rn(av[e], ps[k].w0), __fmul_rn(bv[e], ps[k].w1)),
-                              __fmul_rn(cv[e], ps[k].w2));
-      }
+    for (int k = 0; k < 4; ++k) {
+      // unconditional loads: neighbouring pixels usually share a triangle, so these are L1 broadcast hits
+      const float4 ra = __ldg(reinterpret_cast<const float4*>(tbase + ob0[k]));
+      const float4 rb = __ldg(reinterpret_cast<const float4*>(tbase + ob1[k]));
+      const float4 rc = __ldg(reinterpret_cast<const float4*>(tbase + ob2[k]));
+      // interp2d.py:85-89: mul, then sum over the three vertices in order (separate roundings, no FMA)
+      v[k][0] = __fadd_rn(__fadd_rn(__fmul_rn(ra.x, w0[k]), __fmul_rn(rb.x, w1[k])), __fmul_rn(rc.x, w2[k]));
+      v[k][1] = __fadd_rn(__fadd_rn(__fmul_rn(ra.y, w0[k]), __fmul_rn(rb.y, w1[k])), __fmul_rn(rc.y, w2[k]));
+      v[k][2] = __fadd_rn(__fadd_rn(__fmul_rn(ra.z, w0[k]), __fmul_rn(rb.z, w1[k])), __fmul_rn(rc.z, w2[k]));
+      v[k][3] = __fadd_rn(__fadd_rn(__fmul_rn(ra.w, w0[k]), __fmul_rn(rb.w, w1[k])), __fmul_rn(rc.w, w2[k]));
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (c + e >= p.C) break;
-      float o[4];
+      if (c + e < p.C) {
+        if (kScores) {
+          __stcs(reinterpret_cast<float4*>(obase), make_float4(v[0][e], v[1][e], v[2][e], v[3][e]));
+          obase += ostep;
+        }
+        if (kMask) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float val = v[k][e];
-        if (p.zero_residual && !(val == val)) val = 0.f;  // models_instance.py:940
-        o[k] = val;
-        if (kMask) {  // torch.argmax: first maximum wins; NaN counts as the maximum
-          const bool isn = !(val == val);
-          if (c + e == 0) {
-            best[k] = val; besti[k] = 0; bestnan[k] = isn;
-          } else if (!bestnan[k] && (isn || val > best[k])) {
-            best[k] = val; besti[k] = c + e; bestnan[k] = isn;
+          for (int k = 0; k < 4; ++k) {  // torch.argmax: the first maximum wins
+            if (c + e == 0 || v[k][e] > best[k]) { best[k] = v[k][e]; besti[k] = c + e; }
           }
         }
-      }
-      if (kScores) {
-        float4 st = make_float4(o[0], o[1], o[2], o[3]);
-        __stcs(reinterpret_cast<float4*>(out + static_cast<size_t>(c + e) * plane), st);
       }
     }
   }
   if (kMask) {
-    longlong2 m0 = make_longlong2(besti[0], besti[1]), m1 = make_longlong2(besti[2], besti[3]);
-    longlong2* mp = reinterpret_cast<longlong2*>(mask + pix0);
-    mp[0] = m0;
-    mp[1] = m1;
+    // a pixel that is NaN in every channel: torch.argmax returns the first NaN -> class 0
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((nanmask >> k) & 1u) besti[k] = 0;
+    longlong2* mp = reinterpret_cast<longlong2*>(mask + static_cast<size_t>(b) * plane + pixoff);
+    mp[0] = make_longlong2(besti[0], besti[1]);
+    mp[1] = make_longlong2(besti[2], besti[3]);
   }
 }
 
@@ -445,40 +450,45 @@ extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int
   return check_launch("fovea_select_points");
 }
 
-extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* tris, const uint16_t* nbrs,
-                                  const int32_t* ntri, int B, int cap, int tcap, int H, int W, int32_t* hints,
-                                  fovea_stream_t stream) {
+extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* mesh, const int32_t* ntri,
+                                  int B, int cap, int tcap, int H, int W, int32_t* hints, fovea_stream_t stream) {
   (void)npts;
-  FOVEA_REQUIRE(pts && tris && nbrs && ntri && hints && B > 0 && H > 0 && W > 0, "fovea_locate_hints: bad arguments");
-  locate_hints_kernel<<<B, kHintThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      pts, reinterpret_cast<const ushort4*>(tris), reinterpret_cast<const ushort4*>(nbrs), ntri, cap, tcap, H, W, hints);
+  FOVEA_REQUIRE(pts && mesh && ntri && hints && B > 0 && H > 0 && W > 0, "fovea_locate_hints: bad arguments");
+  const size_t smem = static_cast<size_t>(tcap) * sizeof(uint4);
+  if (smem > 220 * 1024) {
+    set_error("fovea_locate_hints: tcap=%d needs %zu B of shared memory (> 220 KB)", tcap, smem);
+    return FOVEA_ERR_CAPACITY;
+  }
+  FOVEA_CUDA(cudaFuncSetAttribute(locate_hints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  locate_hints_kernel<<<B, kHintThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      pts, reinterpret_cast<const uint4*>(mesh), ntri, cap, tcap, H, W, hints);
   return check_launch("fovea_locate_hints");
 }
 
 extern "C" int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
-                                  const uint16_t* tris, const uint16_t* nbrs, const int32_t* ntri,
-                                  const int32_t* hints, const float* table, int B, int C, int Cs, int h, int w, int H,
-                                  int W, int cap, int tcap, int zero_residual, float* scores, int64_t* mask,
-                                  fovea_stream_t stream) {
+                                  const uint16_t* mesh, const int32_t* ntri, const int32_t* hints, const float* table,
+                                  int B, int C, int Cs, int h, int w, int H, int W, int cap, int tcap,
+                                  int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream) {
   (void)npts;
-  FOVEA_REQUIRE(winner && pts && src && tris && nbrs && ntri && hints && table, "fovea_inverse_fill: null pointer");
+  FOVEA_REQUIRE(winner && pts && src && mesh && ntri && hints && table, "fovea_inverse_fill: null pointer");
   FOVEA_REQUIRE(scores || mask, "fovea_inverse_fill: neither scores nor mask requested");
   FOVEA_REQUIRE(B > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && h > 0 && w > 0 && H > 1 && W > 1,
                 "fovea_inverse_fill: bad sizes");
   FOVEA_REQUIRE(W % 4 == 0, "fovea_inverse_fill: W=%d must be a multiple of 4 (128-bit stores)", W);
   FOVEA_REQUIRE(B <= 65535 && H <= 65535, "fovea_inverse_fill: B and H must be <= 65535");
+  FOVEA_REQUIRE(static_cast<long long>(H) * W < (1ll << 32) && static_cast<long long>(h) * w * Cs < (1ll << 31),
+                "fovea_inverse_fill: canvas or value table too large for 32-bit offsets");
   FillParams p{C, Cs, h, w, H, W, cap, tcap, zero_residual};
   dim3 grid(ceil_div(W, kFillThreads * 4), H, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const ushort4* t4 = reinterpret_cast<const ushort4*>(tris);
-  const ushort4* n4 = reinterpret_cast<const ushort4*>(nbrs);
+  const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
   long long* mk = reinterpret_cast<long long*>(mask);
   if (scores && mask)
-    inverse_fill_kernel<true, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, t4, n4, ntri, hints, table, scores, mk, p);
+    inverse_fill_kernel<true, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
   else if (scores)
-    inverse_fill_kernel<true, false><<<grid, kFillThreads, 0, s>>>(winner, pts, src, t4, n4, ntri, hints, table, scores, mk, p);
+    inverse_fill_kernel<true, false><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
   else
-    inverse_fill_kernel<false, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, t4, n4, ntri, hints, table, scores, mk, p);
+    inverse_fill_kernel<false, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
   return check_launch("fovea_inverse_fill");
 }
 

@@ -1,11 +1,9 @@
 // Triangle mesh access + exact point location shared by the stage-3 kernels.
 //
-// Points are packed (row<<16 | col); triangles are ushort4 (v0,v1,v2,_) indices into the per-image point list;
-// nbrs[t].{x,y,z} is the triangle across the edge OPPOSITE vertex 0,1,2 (SciPy's `neighbors` convention,
+// Points are packed (row<<16 | col); a triangle is one 16-byte record of uint16 (v0,v1,v2,0,n0,n1,n2,0): v* index
+// the per-image point list, n_k is the triangle across the edge OPPOSITE vertex k (SciPy's `neighbors` convention,
 // spatial/qhull.pyx:1367-1380), 0xFFFF = convex-hull edge.  Orientation may be either sign (host Qhull emits
-// both); all predicates are exact integer arithmetic, so a pixel on a shared edge is accepted by whichever
-// triangle the walk reaches first -- like the reference's eps-tolerant barycentric test, and harmless because the
-// interpolant is continuous across edges.
+// both); all predicates are exact integer arithmetic.
 #pragma once
 #include "common.cuh"
 
@@ -15,8 +13,7 @@ constexpr unsigned kNoTri = 0xFFFFu;
 
 struct Mesh {
   const int32_t* pts;
-  const ushort4* tris;
-  const ushort4* nbrs;
+  const uint4* rec;  // global or shared memory
   int ntri;
 };
 
@@ -29,7 +26,7 @@ struct Located {
   int tri;            // -1: outside the triangulation
   long long a0, a1;   // orientation-normalised sub-areas opposite vertex 0 and 1
   long long area;     // |orient(v0,v1,v2)|
-  ushort4 v;
+  unsigned v01, v2;    // packed vertex ids (v0 | v1<<16, v2)
 };
 
 // Tie rule for a query that lies EXACTLY on an edge (or vertex): the pixel belongs to the triangle that contains
@@ -45,8 +42,8 @@ __device__ __forceinline__ bool edge_owned(long long e, long long s, int ar, int
 }
 
 __device__ __forceinline__ bool test_triangle(const Mesh& m, int t, int qr, int qc, Located& out, int& next) {
-  const ushort4 v = m.tris[t];
-  const int p0 = m.pts[v.x], p1 = m.pts[v.y], p2 = m.pts[v.z];
+  const uint4 rec = m.rec[t];
+  const int p0 = m.pts[rec.x & 0xFFFFu], p1 = m.pts[rec.x >> 16], p2 = m.pts[rec.y & 0xFFFFu];
   const int r0 = p0 >> 16, c0 = p0 & 0xFFFF, r1 = p1 >> 16, c1 = p1 & 0xFFFF, r2 = p2 >> 16, c2 = p2 & 0xFFFF;
   long long A = orient2d(r0, c0, r1, c1, r2, c2);
   const long long s = A < 0 ? -1 : 1;
@@ -56,22 +53,22 @@ __device__ __forceinline__ bool test_triangle(const Mesh& m, int t, int qr, int 
   const long long e2 = A - e0 - e1;  // == s*orient(p0,p1,q)
   next = -1;
   if (A == 0) return false;
-  const bool strict = e0 > 0 && e1 > 0 && e2 > 0;  // the common case: no neighbour lookups at all
+  const bool strict = e0 > 0 && e1 > 0 && e2 > 0;  // the common case
   if (!strict) {
-    const ushort4 nb = m.nbrs[t];
+    const unsigned n0 = rec.z & 0xFFFFu, n1 = rec.z >> 16, n2 = rec.w & 0xFFFFu;
     // an edge on the convex hull owns its pixels (there is no neighbour to hand them to)
-    if (!(edge_owned(e0, s, r1, c1, r2, c2) || (e0 == 0 && nb.x == kNoTri))) { next = nb.x; return false; }
-    if (!(edge_owned(e1, s, r2, c2, r0, c0) || (e1 == 0 && nb.y == kNoTri))) { next = nb.y; return false; }
-    if (!(edge_owned(e2, s, r0, c0, r1, c1) || (e2 == 0 && nb.z == kNoTri))) { next = nb.z; return false; }
+    if (!(edge_owned(e0, s, r1, c1, r2, c2) || (e0 == 0 && n0 == kNoTri))) { next = n0; return false; }
+    if (!(edge_owned(e1, s, r2, c2, r0, c0) || (e1 == 0 && n1 == kNoTri))) { next = n1; return false; }
+    if (!(edge_owned(e2, s, r0, c0, r1, c1) || (e2 == 0 && n2 == kNoTri))) { next = n2; return false; }
   }
-  out.tri = t; out.a0 = e0; out.a1 = e1; out.area = A; out.v = v;
+  out.tri = t; out.a0 = e0; out.a1 = e1; out.area = A; out.v01 = rec.x; out.v2 = rec.y & 0xFFFFu;
   return true;
 }
 
 // Visibility walk from `start`; falls back to a scan of all triangles if the walk meets a degenerate
 // triangle or exceeds its step budget (cannot happen on a Delaunay mesh, may on a host mesh with flat facets).
 __device__ __noinline__ Located locate_bruteforce(const Mesh& m, int qr, int qc) {
-  Located L; L.tri = -1; L.a0 = L.a1 = 0; L.area = 1; L.v = make_ushort4(0, 0, 0, 0);
+  Located L; L.tri = -1; L.a0 = L.a1 = 0; L.area = 1; L.v01 = 0; L.v2 = 0;
   int next;
   for (int t = 0; t < m.ntri; ++t)
     if (test_triangle(m, t, qr, qc, L, next)) return L;
@@ -80,7 +77,7 @@ __device__ __noinline__ Located locate_bruteforce(const Mesh& m, int qr, int qc)
 }
 
 __device__ __forceinline__ Located locate(const Mesh& m, int qr, int qc, int start) {
-  Located L; L.tri = -1; L.a0 = L.a1 = 0; L.area = 1; L.v = make_ushort4(0, 0, 0, 0);
+  Located L; L.tri = -1; L.a0 = L.a1 = 0; L.area = 1; L.v01 = 0; L.v2 = 0;
   int t = (start >= 0 && start < m.ntri) ? start : 0;
   const int budget = m.ntri + 8;
   for (int step = 0; step < budget; ++step) {

@@ -41,9 +41,9 @@ PROTOTYPES = {
     "fovea_box4_table": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_select_points": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_delaunay_workspace_bytes": (_i64, [_i, _i]),
-    "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "fovea_locate_hints": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
-    "fovea_inverse_fill": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_inverse_fill": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_argmax_classes": (_i, [_p, _i, _i, _i64, _p, _p]),
 }
 

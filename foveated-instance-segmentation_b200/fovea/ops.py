@@ -191,8 +191,7 @@ class InversePlan:
     pts: torch.Tensor      # [B,cap] int32 (row<<16|col), row-major sorted
     src: torch.Tensor      # [B,cap] int32 row of the value table
     npts: torch.Tensor     # [B] int32
-    tris: torch.Tensor     # [B,tcap,4] uint16
-    nbrs: torch.Tensor     # [B,tcap,4] uint16
+    mesh: torch.Tensor     # [B,tcap,8] uint16: (v0,v1,v2,0,n0,n1,n2,0) per triangle
     ntri: torch.Tensor     # [B] int32
     hints: torch.Tensor    # [B,ceil(H/32),ceil(W/32)] int32
     h: int
@@ -216,8 +215,7 @@ def _triangulate_host(pts, npts, cap, tcap, pool=None):
     B = pts.shape[0]
     pts_h = pts.cpu().numpy()
     npts_h = npts.cpu().numpy()
-    tris = np.zeros((B, tcap, 4), dtype=np.uint16)
-    nbrs = np.full((B, tcap, 4), 0xFFFF, dtype=np.uint16)
+    mesh = np.zeros((B, tcap, 8), dtype=np.uint16)
     ntri = np.zeros(B, dtype=np.int32)
     jobs = [pts_h[b, : npts_h[b]] for b in range(B)]
     if pool is None and B > 1:
@@ -231,12 +229,11 @@ def _triangulate_host(pts, npts, cap, tcap, pool=None):
         T = simp.shape[0]
         if T > tcap:
             raise FoveaError(f"host triangulation produced {T} triangles > tcap={tcap}")
-        tris[b, :T, :3] = simp
-        nb = np.where(nb < 0, 0xFFFF, nb)
-        nbrs[b, :T, :3] = nb
+        mesh[b, :T, 0:3] = simp
+        mesh[b, :T, 4:7] = np.where(nb < 0, 0xFFFF, nb)
         ntri[b] = T
     dev = pts.device
-    return (torch.from_numpy(tris).to(dev), torch.from_numpy(nbrs).to(dev), torch.from_numpy(ntri).to(dev))
+    return torch.from_numpy(mesh).to(dev), torch.from_numpy(ntri).to(dev)
 
 
 def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) -> InversePlan:
@@ -259,30 +256,38 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
     _lib.call("fovea_select_points", _ptr(g), _ptr(winner), B, h, w, H, W, int(nchan), cap, _ptr(pts), _ptr(src),
               _ptr(npts), _stream())
     if triangulation == "host":
-        tris, nbrs, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
+        mesh, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
     elif triangulation == "device":
-        tris = torch.empty(B, tcap, 4, device=dev, dtype=torch.uint16)
-        nbrs = torch.empty(B, tcap, 4, device=dev, dtype=torch.uint16)
-        ntri = torch.empty(B, device=dev, dtype=torch.int32)
-        ws_bytes = _lib.load().fovea_delaunay_workspace_bytes(B, cap)
-        ws = torch.empty(max(int(ws_bytes), 16), device=dev, dtype=torch.uint8)
-        _lib.call("fovea_delaunay", _ptr(pts), _ptr(npts), B, cap, tcap, _ptr(tris), _ptr(nbrs), _ptr(ntri), _ptr(ws),
-                  _stream())
+        mesh, ntri, _ = delaunay_device(pts, npts, cap, tcap, max(H, W))
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
     ch, cw = -(-H // _lib.HINT_CELL), -(-W // _lib.HINT_CELL)
     hints = torch.empty(B, ch, cw, device=dev, dtype=torch.int32)
-    _lib.call("fovea_locate_hints", _ptr(pts), _ptr(npts), _ptr(tris), _ptr(nbrs), _ptr(ntri), B, cap, tcap, H, W,
-              _ptr(hints), _stream())
-    return InversePlan(winner, pts, src, npts, tris, nbrs, ntri, hints, h, w, H, W, cap, tcap, triangulation)
+    _lib.call("fovea_locate_hints", _ptr(pts), _ptr(npts), _ptr(mesh), _ptr(ntri), B, cap, tcap, H, W, _ptr(hints),
+              _stream())
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, h, w, H, W, cap, tcap, triangulation)
+
+
+def delaunay_device(pts, npts, cap, tcap, max_coord):
+    """interp2d.py:55 on the device: Delaunay-triangulate every image's sorted, unique packed points.
+    Returns (mesh [B,tcap,8] uint16, ntri [B] int32, flip_rounds [B] int32)."""
+    pts = _req(pts, torch.int32, "pts", 2)
+    npts = _req(npts, torch.int32, "npts", 1)
+    B, dev = pts.shape[0], pts.device
+    mesh = torch.empty(B, tcap, 8, device=dev, dtype=torch.uint16)
+    ntri = torch.empty(B, device=dev, dtype=torch.int32)
+    ws = torch.zeros(9 * B, device=dev, dtype=torch.int32)  # [B] flip rounds + [B,8] stage counters
+    _lib.call("fovea_delaunay", _ptr(pts), _ptr(npts), B, cap, tcap, int(max_coord), _ptr(mesh), _ptr(ntri),
+              _ptr(ws), _stream())
+    return mesh, ntri, ws
 
 
 def box4_table(pred, Cs=None):
-    """A8 at the nodes: [B, h*w+1, Cs] value table (last row NaN), models/models.py:935-937."""
+    """A8 at the nodes: [B, h*w+2, Cs] value table (row h*w NaN, row h*w+1 zeros), models/models.py:935-937."""
     p = _req(pred.detach(), torch.float32, "pred", 4)
     B, Cc, h, w = p.shape
     Cs = Cs or (Cc + 3) // 4 * 4
-    table = torch.empty(B, h * w + 1, Cs, device=p.device, dtype=torch.float32)
+    table = torch.empty(B, h * w + 2, Cs, device=p.device, dtype=torch.float32)
     _lib.call("fovea_box4_table", _ptr(p), B, Cc, h, w, Cs, _ptr(table), _stream())
     return table
 
@@ -304,7 +309,7 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
     if want_mask:
         mask = mask_out if mask_out is not None else torch.empty(B, plan.H, plan.W, device=p.device, dtype=torch.int64)
     _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
-              _ptr(plan.tris), _ptr(plan.nbrs), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), B, Cc, Cs, h, w,
+              _ptr(plan.mesh), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), B, Cc, Cs, h, w,
               plan.H, plan.W, plan.cap, plan.tcap, 1 if zero_residual else 0, _ptr(scores), _ptr(mask), _stream())
     return scores, mask
 

@@ -115,8 +115,9 @@ int fovea_grid_inv_canvas(const int32_t* winner, int B, int h, int w, int H, int
 
 /* A8 at the low-res nodes: table[b, i*w+j, c] = F.grid_sample(pred, grid_inv) evaluated at node (i,j)
  * (= the zero-padded 2x2 box mean of pred, with aten's fp32 arithmetic), models/models.py:935-937.
- * Row h*w of every image is NaN (value of an unfilled image corner, models/models.py:202-209, 268).
- *   pred [B,C,h,w] -> table [B, h*w+1, Cs] fp32, Cs = channel stride >= C, multiple of 4 (tail zero) */
+ * Row h*w of every image is NaN (value of an unfilled image corner, models/models.py:202-209, 268); row h*w+1
+ * is all zeros (what a NaN pixel becomes under the residual NaN -> 0 rule, models_instance.py:940).
+ *   pred [B,C,h,w] -> table [B, h*w+2, Cs] fp32, Cs = channel stride >= C, multiple of 4 (tail zero) */
 int fovea_box4_table(const float* pred, int B, int C, int h, int w, int Cs, float* table,
                      fovea_stream_t stream);
 
@@ -131,35 +132,41 @@ int fovea_box4_table(const float* pred, int B, int C, int h, int w, int Cs, floa
 int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
                         int cap, int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream);
 
-/* Delaunay triangulation of each image's points ON THE DEVICE (one CTA per image, exact int64
- * in-circle predicates).  Replaces the host Qhull call interp2d.py:55 (spatial/qhull.pyx:1679).
- * The caller may instead fill tris/nbrs/ntri from a host triangulation (parity mode: stock SciPy Qhull).
- *   tris [B,tcap,4] uint16 (v0,v1,v2,0) indices into pts, counter-clockwise in (col,row) axes
- *   nbrs [B,tcap,4] uint16  nbrs[t][k] = triangle opposite vertex k, 0xFFFF = hull edge
- *   ntri [B] int32          tcap >= 2*cap
- *   workspace: fovea_delaunay_workspace_bytes(B, cap) bytes of device memory */
+/* Triangle mesh layout shared by the entry points below:
+ *   mesh [B,tcap,8] uint16, one 16-byte record per triangle: (v0, v1, v2, 0, n0, n1, n2, 0)
+ *     v* = indices into the image's point list (either orientation); n_k = triangle across the edge opposite
+ *     vertex k (SciPy's `neighbors` convention, spatial/qhull.pyx), 0xFFFF = convex-hull edge.
+ *   ntri [B] int32 = triangles per image;  tcap >= 2*cap. */
+
+/* Delaunay triangulation of each image's points ON THE DEVICE (one CTA per image, mesh in shared memory, exact
+ * int64 in-circle predicates).  Replaces the host Qhull call interp2d.py:55 (spatial/qhull.pyx:1679).  The caller
+ * may instead fill mesh/ntri from a host triangulation (parity mode: stock SciPy Qhull, what the reference does).
+ *   pts must be sorted ascending (row-major) and unique, as fovea_select_points emits them;
+ *   max_coord = max(H, W) <= 8192;  cap <= 8190 and small enough for 227 KB of shared memory (~6.6k points),
+ *   else FOVEA_ERR_CAPACITY (use the host triangulation);
+ *   workspace: fovea_delaunay_workspace_bytes(B, cap) bytes; receives the flip-round count per image (int32). */
 int64_t fovea_delaunay_workspace_bytes(int B, int cap);
-int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, uint16_t* tris,
-                   uint16_t* nbrs, int32_t* ntri, void* workspace, fovea_stream_t stream);
+int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
+                   uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream);
 
 /* Walk-start hints for fovea_inverse_fill: hints[b, cy, cx] = a triangle containing (or near) the centre
  * of the FOVEA_HINT_CELL x FOVEA_HINT_CELL pixel cell.  hints [B, ceil(H/cell), ceil(W/cell)] int32 */
 #define FOVEA_HINT_CELL 32
-int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* tris, const uint16_t* nbrs,
-                       const int32_t* ntri, int B, int cap, int tcap, int H, int W, int32_t* hints,
-                       fovea_stream_t stream);
+int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* mesh, const int32_t* ntri, int B,
+                       int cap, int tcap, int H, int W, int32_t* hints, fovea_stream_t stream);
 
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
  * fillMissingValues_tensor(..., 'tri') = Interp2D point location + barycentric gather
  * (models/models.py:939-940, interp2d.py:58-91), residual NaN -> 0 (models_instance.py:940) and
  * torch.argmax over classes (models/models.py:1044), in one pass over the full-resolution canvas.
+ *   table  [B, h*w+2, Cs] from fovea_box4_table
  *   scores [B,C,H,W] fp32   (NULL = do not materialise)
  *   mask   [B,H,W]  int64   (NULL = do not compute)
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
 int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
-                       const uint16_t* tris, const uint16_t* nbrs, const int32_t* ntri, const int32_t* hints,
-                       const float* table, int B, int C, int Cs, int h, int w, int H, int W, int cap,
-                       int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
+                       const uint16_t* mesh, const int32_t* ntri, const int32_t* hints, const float* table, int B,
+                       int C, int Cs, int h, int w, int H, int W, int cap, int tcap, int zero_residual,
+                       float* scores, int64_t* mask, fovea_stream_t stream);
 
 /* torch.argmax(scores, dim=1) as a stand-alone pass (models/models.py:1044): first maximum wins, NaN is
  * treated as the maximum (torch semantics).  scores [B,C,H,W] -> mask [B,H,W] int64 */

@@ -1,0 +1,169 @@
+"""The device Delaunay kernel: exact validity checks (integer arithmetic on the CPU) + agreement with host Qhull.
+
+A Delaunay triangulation of lattice points is not unique (co-circular quadruples), so the mesh is not compared
+triangle by triangle with Qhull's; instead every property that DEFINES a Delaunay triangulation is verified exactly:
+positive orientation, symmetric adjacency over matching edges, hull coverage (area), triangle count, and the empty
+circumcircle condition on every interior edge.  The interpolated scores are then compared with the host-Qhull path.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (run on the B200 box with -m gpu)")
+    from fovea import ops as _ops
+    _ops._lib.load()
+    return _ops
+
+
+def _orient(a, b, c):
+    return (b[..., 1] - a[..., 1]) * (c[..., 0] - a[..., 0]) - (b[..., 0] - a[..., 0]) * (c[..., 1] - a[..., 1])
+
+
+def _incircle(a, b, c, d):
+    ax, ay = a[..., 1] - d[..., 1], a[..., 0] - d[..., 0]
+    bx, by = b[..., 1] - d[..., 1], b[..., 0] - d[..., 0]
+    cx, cy = c[..., 1] - d[..., 1], c[..., 0] - d[..., 0]
+    return ((ax * ax + ay * ay) * (bx * cy - by * cx) - (bx * bx + by * by) * (ax * cy - ay * cx)
+            + (cx * cx + cy * cy) * (ax * by - ay * bx))
+
+
+def check_mesh(pts_rc, mesh, T):
+    """pts_rc [N,2] int64 (row,col); mesh [tcap,8] uint16; raises AssertionError on any violated property."""
+    from scipy.spatial import ConvexHull, Delaunay
+    m = mesh[:T].astype(np.int64)
+    V, NB = m[:, 0:3], m[:, 4:7]
+    N = len(pts_rc)
+    assert V.min() >= 0 and V.max() < N
+    P = pts_rc.astype(np.int64)
+    area2 = _orient(P[V[:, 0]], P[V[:, 1]], P[V[:, 2]])
+    assert (area2 > 0).all(), "non-positive triangle"
+    # coverage: triangles tile the convex hull exactly
+    hull = ConvexHull(P[:, ::-1].astype(np.float64))
+    assert area2.sum() == int(round(2 * hull.volume)), (area2.sum(), 2 * hull.volume)
+    # every point is a vertex, triangle count matches any full triangulation of the set
+    assert len(np.unique(V)) == N
+    assert T == len(Delaunay(P.astype(np.float64)).simplices)
+    # adjacency: symmetric, and the shared edge has the same two vertices on both sides
+    for k in range(3):
+        u = NB[:, k]
+        interior = u != 0xFFFF
+        t = np.flatnonzero(interior)
+        u = u[interior]
+        if len(t) == 0:
+            continue
+        assert (u < T).all()
+        back = (NB[u] == t[:, None])
+        assert back.sum(1).min() == 1, "asymmetric adjacency"
+        ku = back.argmax(1)
+        e_t = np.sort(np.stack([V[t, (k + 1) % 3], V[t, (k + 2) % 3]], 1), 1)
+        e_u = np.sort(np.stack([V[u, (ku + 1) % 3], V[u, (ku + 2) % 3]], 1), 1)
+        assert (e_t == e_u).all(), "neighbour does not share the edge"
+        # empty circumcircle (locally Delaunay on every interior edge => globally Delaunay)
+        inc = _incircle(P[V[t, 0]], P[V[t, 1]], P[V[t, 2]], P[V[u, ku]])
+        assert (inc <= 0).all(), f"{(inc > 0).sum()} illegal edges"
+    return True
+
+
+def _run_device(ops, pts_list, max_coord):
+    """pts_list: list of [n_i,2] int arrays (row,col), each sorted row-major & unique."""
+    B = len(pts_list)
+    cap = max(max(len(p) for p in pts_list), 4)
+    tcap = 2 * cap
+    packed = torch.zeros(B, cap, dtype=torch.int32)
+    npts = torch.zeros(B, dtype=torch.int32)
+    for b, p in enumerate(pts_list):
+        packed[b, : len(p)] = torch.from_numpy((p[:, 0].astype(np.int64) << 16 | p[:, 1].astype(np.int64)).astype(np.int32))
+        npts[b] = len(p)
+    mesh, ntri, rounds = ops.delaunay_device(packed.cuda(), npts.cuda(), cap, tcap, max_coord)
+    torch.cuda.synchronize()
+    return mesh.cpu().numpy(), ntri.cpu().numpy(), rounds.cpu().numpy()
+
+
+def _sorted_unique(rc):
+    key = rc[:, 0].astype(np.int64) * 65536 + rc[:, 1]
+    key = np.unique(key)
+    return np.stack([key // 65536, key % 65536], 1)
+
+
+def _plan_points(ops, H, W, seed, B=2):
+    xs, _ = rp.synthetic_saliency(B, seed=seed)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    return grid
+
+
+@pytest.mark.parametrize("H,W,seed", [(128, 128, 1), (256, 320, 2), (1024, 1024, 3), (2048, 2048, 4), (4096, 4096, 5)])
+def test_device_delaunay_on_foveated_point_sets(ops, H, W, seed):
+    grid = _plan_points(ops, H, W, seed)
+    plan = ops.build_inverse_plan(grid.cuda(), (H, W), nchan=51, triangulation="device")
+    torch.cuda.synchronize()
+    npts, pts = plan.npts.cpu().numpy(), plan.pts.cpu().numpy()
+    mesh, ntri = plan.mesh.cpu().numpy(), plan.ntri.cpu().numpy()
+    for b in range(grid.shape[0]):
+        rc = np.stack([pts[b, : npts[b]] >> 16, pts[b, : npts[b]] & 0xFFFF], 1)
+        check_mesh(rc, mesh[b], int(ntri[b]))
+
+
+def test_device_delaunay_on_adversarial_point_sets(ops):
+    rng = np.random.default_rng(0)
+    sets = []
+    # random scatter without corners (arbitrary hull)
+    sets.append(_sorted_unique(rng.integers(0, 200, size=(1500, 2))))
+    # dense block: every lattice point of a 40x50 rectangle (maximally co-circular, all rows full)
+    rr, cc = np.meshgrid(np.arange(40), np.arange(50), indexing="ij")
+    sets.append(_sorted_unique(np.stack([rr.ravel(), cc.ravel()], 1)))
+    # single-point rows forming a zig-zag + a few wide rows (empty strips between single-point rows)
+    zz = np.stack([np.arange(0, 300, 3), 100 + 80 * ((np.arange(100) % 2) * 2 - 1) * (np.arange(100) % 7) // 7], 1)
+    sets.append(_sorted_unique(np.concatenate([zz, [[0, 0], [0, 250], [299, 0], [299, 250]]])))
+    # two rows only; one row + apex; collinear diagonal plus one off-line point
+    sets.append(_sorted_unique(np.array([[0, 0], [0, 5], [0, 9], [7, 2], [7, 3], [7, 30]])))
+    sets.append(_sorted_unique(np.array([[0, 0], [0, 10], [0, 20], [5, 7]])))
+    sets.append(_sorted_unique(np.concatenate([np.stack([np.arange(50), np.arange(50)], 1), [[10, 40]]])))
+    # clustered: a tight Gaussian blob (fovea) + the four corners of a 4096 canvas
+    blob = np.clip(rng.normal(2000, 15, size=(4000, 2)).astype(np.int64), 0, 4095)
+    sets.append(_sorted_unique(np.concatenate([blob, [[0, 0], [0, 4095], [4095, 0], [4095, 4095]]])))
+    mesh, ntri, rounds = _run_device(ops, sets, 4096)
+    for b, p in enumerate(sets):
+        check_mesh(p, mesh[b], int(ntri[b]))
+
+
+def test_device_delaunay_degenerate_inputs(ops):
+    """All points in one row (or fewer than 3 points): no triangles, no crash."""
+    sets = [np.array([[3, 1], [3, 4], [3, 9]]), np.array([[0, 0], [5, 5]]), np.array([[1, 1]])]
+    mesh, ntri, rounds = _run_device(ops, sets, 16)
+    assert (ntri == 0).all()
+
+
+@pytest.mark.parametrize("H,W", [(256, 256), (1024, 1024)])
+def test_device_triangulation_scores_agree_with_host_qhull(ops, H, W):
+    """Same points, two valid Delaunay triangulations: the interpolants differ only inside co-circular cells."""
+    B, C = 2, 8
+    grid = _plan_points(ops, H, W, seed=31, B=B)
+    pred = rp.synthetic_pred(B, C, seed=31).cuda()
+    plan_h = ops.build_inverse_plan(grid.cuda(), (H, W), nchan=C, triangulation="host")
+    plan_d = ops.build_inverse_plan(grid.cuda(), (H, W), nchan=C, triangulation="device")
+    assert torch.equal(plan_h.npts, plan_d.npts) and torch.equal(plan_h.ntri.cpu(), plan_d.ntri.cpu())
+    for b in range(B):
+        nb_ = int(plan_h.npts[b])
+        assert torch.equal(plan_h.pts[b, :nb_], plan_d.pts[b, :nb_])
+    sh, mh = ops.inverse_fill(plan_h, pred, want_scores=True, want_mask=True)
+    sd, md = ops.inverse_fill(plan_d, pred, want_scores=True, want_mask=True)
+    close = ((sh - sd).abs() <= 1e-5 * sh.abs().max()).all(1)
+    frac = close.float().mean().item()
+    magree = (mh == md).float().mean().item()
+    print(f"{H}x{W}: score pixels equal {frac:.4f}, mask agreement {magree:.4f}")
+    assert frac > 0.5 and magree > 0.8
+    # both are exact on the sites themselves
+    win = plan_d.winner.long()
+    b, ys, xs_ = torch.where(win >= 0)
+    assert torch.equal(sd[b, :, ys, xs_], sh[b, :, ys, xs_])

@@ -202,7 +202,7 @@ def test_inverse_pieces_match_oracle(ops, golden_dir, name, grid_name, C):
     # A8 at the nodes == F.grid_sample(pred, grid_inv) at the winners' pixels
     ps_nan = rp.inverse_sample(pred, rp.grid_inverse(grid, seg, tie="max"))
     table = ops.box4_table(pred.cuda()).cpu()
-    assert torch.isnan(table[:, h * w, :]).all()
+    assert torch.isnan(table[:, h * w, :]).all() and (table[:, h * w + 1, :] == 0).all()
     wn = win.cpu().long()
     for b in range(B):
         ys, xs_ = torch.where(wn[b] >= 0)
