@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="b64_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--triangulation", default=os.environ.get("FOVEA_TRIANGULATION", "host"),
+    ap.add_argument("--triangulation", default=os.environ.get("FOVEA_TRIANGULATION", "device"),
                     choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -33,7 +33,8 @@ struct DtArrays {
   unsigned short *n0, *n1, *n2;  // neighbour codes: (triangle << 2) | slot-in-neighbour, opposite v0/v1/v2
   unsigned* lock;                // [tcap] flip claims (aliased by the construction scratch below)
   unsigned* dirty;               // [ceil(tcap/32)] bitmask
-  unsigned short* rowStart;      // [n+1]
+  int* spts;                     // [cap] packed points (every predicate of the flip phase reads them)
+  unsigned short* rowStart;      // [n+1]  (global workspace: only the construction phases read it)
   // construction scratch, aliased onto `lock`
   unsigned short *stripBase, *cprev, *cnext, *cown;
 };
@@ -46,18 +47,36 @@ __device__ __forceinline__ long long orient_pts(int a, int b, int c) {
          static_cast<long long>(pt_row(b) - pt_row(a)) * (pt_col(c) - pt_col(a));
 }
 
-// > 0  <=>  d strictly inside the circumcircle of the counter-clockwise triangle (a,b,c)
+// > 0  <=>  d strictly inside the circumcircle of the counter-clockwise triangle (a,b,c).
+// Coordinates < 8192 (checked on the host): differences < 2^13, so squares/cross products fit int32 (< 2^27) and only
+// the three final products need 64 bits (< 2^55).
 __device__ __forceinline__ long long incircle_pts(int a, int b, int c, int d) {
-  const long long ax = pt_col(a) - pt_col(d), ay = pt_row(a) - pt_row(d);
-  const long long bx = pt_col(b) - pt_col(d), by = pt_row(b) - pt_row(d);
-  const long long cx = pt_col(c) - pt_col(d), cy = pt_row(c) - pt_row(d);
-  return (ax * ax + ay * ay) * (bx * cy - by * cx) - (bx * bx + by * by) * (ax * cy - ay * cx) +
-         (cx * cx + cy * cy) * (ax * by - ay * bx);
+  const int ax = pt_col(a) - pt_col(d), ay = pt_row(a) - pt_row(d);
+  const int bx = pt_col(b) - pt_col(d), by = pt_row(b) - pt_row(d);
+  const int cx = pt_col(c) - pt_col(d), cy = pt_row(c) - pt_row(d);
+  return static_cast<long long>(ax * ax + ay * ay) * (bx * cy - by * cx) -
+         static_cast<long long>(bx * bx + by * by) * (ax * cy - ay * cx) +
+         static_cast<long long>(cx * cx + cy * cy) * (ax * by - ay * bx);
 }
 
 __device__ __forceinline__ unsigned hash32(unsigned x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
+}
+
+// position of the n-th (0-based) set bit of w; branch-free binary search on popcounts (w must have > n set bits)
+__device__ __forceinline__ int nth_set_bit(unsigned w, int n) {
+  int pos = 0;
+  int c = __popc(w & 0xFFFFu);
+  if (n >= c) { n -= c; w >>= 16; pos += 16; }
+  c = __popc(w & 0xFFu);
+  if (n >= c) { n -= c; w >>= 8; pos += 8; }
+  c = __popc(w & 0xFu);
+  if (n >= c) { n -= c; w >>= 4; pos += 4; }
+  c = __popc(w & 0x3u);
+  if (n >= c) { n -= c; w >>= 2; pos += 2; }
+  if (n >= static_cast<int>(w & 1u)) pos += 1;
+  return pos;
 }
 
 // exclusive block scan of one int per thread; returns the exclusive prefix, `total` = block sum
@@ -90,7 +109,7 @@ __device__ int block_scan_excl(int v, int* warp_sums, int& total) {
 }
 
 // number of x in [0,cnt) with col(pts[first+x]) < key  (strict)  /  <= key (non-strict)
-__device__ __forceinline__ int count_less(const int32_t* pts, int first, int cnt, int key, bool or_equal) {
+__device__ __forceinline__ int count_less(const int* pts, int first, int cnt, int key, bool or_equal) {
   int lo = 0, hi = cnt;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -99,6 +118,17 @@ __device__ __forceinline__ int count_less(const int32_t* pts, int first, int cnt
   }
   return lo;
 }
+
+#ifdef DT_DEBUG
+__device__ int* g_dt_dbg = nullptr;
+__device__ __forceinline__ int ck(int idx, int lim, int line) {
+  if (idx < 0 || idx >= lim) { if (g_dt_dbg) { g_dt_dbg[0] = -line; g_dt_dbg[1] = idx; g_dt_dbg[2] = lim; } return 0; }
+  return idx;
+}
+#define CK(i, lim) ck((i), (lim), __LINE__)
+#else
+#define CK(i, lim) (i)
+#endif
 
 __device__ __forceinline__ unsigned short& nb_slot(const DtArrays& A, int t, int k) {
   return k == 0 ? A.n0[t] : (k == 1 ? A.n1[t] : A.n2[t]);
@@ -113,13 +143,14 @@ __device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsi
 __global__ void __launch_bounds__(kDtThreads, 1)
 delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
                 uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
-                int max_rounds, int32_t* __restrict__ dbg) {
+                int max_rounds, int32_t* __restrict__ dbg, unsigned short* __restrict__ row_ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int warp_sums[33];
   __shared__ int s_ntri;
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
-  const int32_t* pts = pts_g + static_cast<size_t>(b) * cap;
+  const long long clk0 = clock64();
+  const int32_t* pts_in = pts_g + static_cast<size_t>(b) * cap;
   const int n = npts[b];
 
   DtArrays A;
@@ -133,7 +164,8 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     A.n2 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
     A.lock = reinterpret_cast<unsigned*>(p); p += 4 * tcap;
     A.dirty = reinterpret_cast<unsigned*>(p); p += 4 * ((tcap + 31) / 32);
-    A.rowStart = reinterpret_cast<unsigned short*>(p);
+    A.spts = reinterpret_cast<int*>(p);
+    A.rowStart = row_ws + static_cast<size_t>(b) * (cap + 2);
     unsigned short* s = reinterpret_cast<unsigned short*>(A.lock);  // 2*tcap shorts of scratch
     A.stripBase = s;
     A.cprev = s + cap;
@@ -141,6 +173,9 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     A.cown = s + 3 * cap;
   }
   uint16_t* mesh = mesh_out + static_cast<size_t>(b) * tcap * 8;
+  for (int i = tid; i < n; i += kDtThreads) A.spts[i] = pts_in[i];
+  const int* pts = A.spts;
+  __syncthreads();
   if (dbg && tid == 0) { dbg[b * 8 + 0] = 1; dbg[b * 8 + 1] = n; }
 
   // ------------------------------------------------------------------ 1. rows
@@ -164,6 +199,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     return;
   }
 
+  if (dbg && tid == 0) dbg[b * 8 + 1] = (int)((clock64() - clk0) >> 4);
   // ------------------------------------------------------------------ 2. strips
   const int nstrips = R - 1;
   const int sitems = (nstrips + kDtThreads - 1) / kDtThreads;
@@ -255,6 +291,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   }
   __syncthreads();
 
+  if (dbg && tid == 0) dbg[b * 8 + 2] = (int)((clock64() - clk0) >> 4);
   // ------------------------------------------------------------------ 3. pockets (left, then right)
   // cprev[m]: bits 0..12 = previous alive chain vertex (kCNone = chain start), bit 13 DEAD, bit 14 SELECTED, bit 15 EAR
   constexpr unsigned kCIdx = 0x1FFFu, kCNone = 0x1FFFu, kCDead = 0x2000u, kCSel = 0x4000u, kCEar = 0x8000u;
@@ -339,69 +376,140 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   if (dbg && tid == 0) { dbg[b * 8 + 0] = 3; dbg[b * 8 + 6] = T; }
   __syncthreads();
 
+  if (dbg && tid == 0) dbg[b * 8 + 3] = (int)((clock64() - clk0) >> 4);
   // ------------------------------------------------------------------ 4. Lawson flips
+  // Flat accessors: the three vertex (neighbour) arrays are consecutive, so slot k of triangle t is one load.
+  unsigned short* const VV = A.v0;
+  unsigned short* const NN = A.n0;
+#define DT_V(t, k) VV[(k) * tcap + (t)]
+#define DT_N(t, k) NN[(k) * tcap + (t)]
+  const int nwords = (tcap + 31) / 32;
   for (int t = tid; t < tcap; t += kDtThreads) A.lock[t] = 0xFFFFFFFFu;
-  for (int w = tid; w < (tcap + 31) / 32; w += kDtThreads) {
+  for (int w = tid; w < nwords; w += kDtThreads) {
     const int lo = w * 32;
     A.dirty[w] = lo + 32 <= T ? 0xFFFFFFFFu : (lo >= T ? 0u : ((1u << (T - lo)) - 1u));
   }
   __syncthreads();
+  // Every warp owns a contiguous range of dirty words and processes ITS set bits densely (rank -> lane), so a round
+  // costs ceil(dirty/32) full-warp test iterations instead of one mostly-idle iteration per 32 triangles.
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wpw = (nwords + 31) / 32;  // dirty words per warp (<= 16 for tcap <= 16383)
+  const int wbase = warp * wpw;
   int round = 0;
   for (; round < max_rounds; ++round) {
-    if (dbg && tid == 0) dbg[b * 8 + 7] = round;
-    unsigned cand = 0;  // 2 bits per owned triangle: 0 = none, else edge slot + 1
-    bool any = false;
+    // Claims carry a 6-bit round tag that DEcreases every round, so this round's atomicMin always beats the stale
+    // claims of earlier rounds and the lock array only needs a reset when the tag wraps (every 64 rounds).
+    if ((round & 63) == 0 && round > 0) {
+      for (int t = tid; t < T; t += kDtThreads) A.lock[t] = 0xFFFFFFFFu;
+      __syncthreads();
+    }
+    const unsigned tag = static_cast<unsigned>(63 - (round & 63)) << 26;
+    // P0: snapshot my warp's dirty words and clear them; triangles that stay illegal re-set their bit below
+    // While a warp's range is densely dirty (the first rounds after the strip construction) only a random quarter
+    // of its dirty triangles competes per round: six-triangle claims make ~12 candidates contend for every win, so
+    // thinning costs few wins per round but removes 3/4 of the tests and claims.  Unselected bits stay dirty.
+    unsigned myword = 0;
+    bool deferred = false;
+    if (lane < wpw && wbase + lane < nwords) {
+      const unsigned w = A.dirty[wbase + lane];
+      const bool dense = __popc(w) > 8;
+      const unsigned h = hash32((wbase + lane) * 0x9E3779B9u + round * 0x85EBCA6Bu);
+      myword = dense ? (w & h & hash32(h)) : w;
+      if (dense && myword == 0u) myword = w & (0u - w);  // keep at least one (lowest) bit so progress is guaranteed
+      A.dirty[wbase + lane] = w & ~myword;
+      deferred = (w & ~myword) != 0u;  // unselected dirty triangles: the loop must not terminate this round
+    }
+    // inclusive prefix of the per-word popcounts across the warp (lane j <-> word j)
+    const int mycnt = __popc(myword);
+    int incl = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int excl = incl - mycnt;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned cand = 0;  // 2 bits per iteration: 0 = none, else illegal edge slot + 1
+    bool any = deferred;
     int it = 0;
-    for (int t = tid; t < T; t += kDtThreads, ++it) {
-      if (!((A.dirty[t >> 5] >> (t & 31)) & 1u)) continue;
+    for (int base = 0; base < total; base += 32, ++it) {
+      // triangle of rank base+lane among this warp's dirty bits
+      const int rank = base + lane;
+      // word holding the rank-th dirty bit: smallest lane j with incl_j > rank (binary search by shuffles)
+      int jsel = 0;
+#pragma unroll
+      for (int sstep = 16; sstep > 0; sstep >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, incl, jsel + sstep - 1);
+        if (v <= rank) jsel += sstep;
+      }
+      jsel = min(jsel, 31);
+      const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
+      const int ex = __shfl_sync(0xffffffffu, excl, jsel);
+      const int t = rank < total ? (wbase + jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      if (t < 0) continue;
+      const int pa = pts[DT_V(t, 0)], pb = pts[DT_V(t, 1)], pc = pts[DT_V(t, 2)];
       int found = -1;
       unsigned ucode = 0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (found >= 0) break;
-        const unsigned code = nb_slot(A, t, k);
+        const unsigned code = DT_N(t, k);
         if (code >= kPendingCode) continue;
-        const int u = code >> 2, ku = code & 3;
-        const int a = pts[vert(A, t, k)], bq = pts[vert(A, t, (k + 1) % 3)], c = pts[vert(A, t, (k + 2) % 3)];
-        const int d = pts[vert(A, u, ku)];
-        if (incircle_pts(a, bq, c, d) > 0) { found = k; ucode = code; }
+        const int d = pts[DT_V(code >> 2, code & 3)];
+        if (incircle_pts(pa, pb, pc, d) > 0) { found = k; ucode = code; }
       }
-      if (found < 0) {
-        atomicAnd(&A.dirty[t >> 5], ~(1u << (t & 31)));
-        continue;
-      }
+      if (found < 0) continue;
       any = true;
       cand |= static_cast<unsigned>(found + 1) << (2 * it);
-      const unsigned pri = (hash32(t * 2654435761u + round * 0x9E3779B9u) << 14) | static_cast<unsigned>(t);
+      atomicOr(&A.dirty[t >> 5], 1u << (t & 31));  // stays dirty until it wins
+      const unsigned pri = tag | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0xFFFu) << 14) | static_cast<unsigned>(t);
       const int u = ucode >> 2, ku = ucode & 3;
       atomicMin(&A.lock[t], pri);
       atomicMin(&A.lock[u], pri);
-      const unsigned o1 = nb_slot(A, t, (found + 1) % 3), o2 = nb_slot(A, t, (found + 2) % 3);
-      const unsigned o3 = nb_slot(A, u, (ku + 1) % 3), o4 = nb_slot(A, u, (ku + 2) % 3);
+      const unsigned o1 = DT_N(t, (found + 1) % 3), o2 = DT_N(t, (found + 2) % 3);
+      const unsigned o3 = DT_N(u, (ku + 1) % 3), o4 = DT_N(u, (ku + 2) % 3);
       if (o1 < kPendingCode) atomicMin(&A.lock[o1 >> 2], pri);
       if (o2 < kPendingCode) atomicMin(&A.lock[o2 >> 2], pri);
       if (o3 < kPendingCode) atomicMin(&A.lock[o3 >> 2], pri);
       if (o4 < kPendingCode) atomicMin(&A.lock[o4 >> 2], pri);
     }
     if (!__syncthreads_or(any)) break;
+    // P2: winners flip
     it = 0;
-    for (int t = tid; t < T; t += kDtThreads, ++it) {
+    for (int base = 0; base < total; base += 32, ++it) {
       const int sel = (cand >> (2 * it)) & 3;
+      if (!__any_sync(0xffffffffu, sel != 0)) continue;  // warp-uniform: the shuffles below need every lane
+      const int rank = base + lane;
+      // word holding the rank-th dirty bit: smallest lane j with incl_j > rank (binary search by shuffles)
+      int jsel = 0;
+#pragma unroll
+      for (int sstep = 16; sstep > 0; sstep >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, incl, jsel + sstep - 1);
+        if (v <= rank) jsel += sstep;
+      }
+      jsel = min(jsel, 31);
+      const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
+      const int ex = __shfl_sync(0xffffffffu, excl, jsel);
+      const int t = rank < total ? (wbase + jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
       if (!sel) continue;
       const int k = sel - 1;
-      const unsigned pri = (hash32(t * 2654435761u + round * 0x9E3779B9u) << 14) | static_cast<unsigned>(t);
-      const unsigned ucode = nb_slot(A, t, k);
+      const unsigned pri = tag | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0xFFFu) << 14) | static_cast<unsigned>(t);
+      // Check the claims in dependency order: a triangle whose lock is not mine may be rewritten by its owner
+      // right now, so nothing is read from it (its neighbour codes could be mid-update or a hull marker).
+      if (A.lock[t] != pri) continue;
+      const unsigned ucode = DT_N(t, k);
       const int u = ucode >> 2, ku = ucode & 3;
-      const unsigned n_ca = nb_slot(A, t, (k + 1) % 3), n_ab = nb_slot(A, t, (k + 2) % 3);
-      const unsigned n_bd = nb_slot(A, u, (ku + 1) % 3), n_dc = nb_slot(A, u, (ku + 2) % 3);
-      bool win = A.lock[t] == pri && A.lock[u] == pri;
+      if (A.lock[u] != pri) continue;
+      const unsigned n_ca = DT_N(t, (k + 1) % 3), n_ab = DT_N(t, (k + 2) % 3);
+      const unsigned n_bd = DT_N(u, (ku + 1) % 3), n_dc = DT_N(u, (ku + 2) % 3);
+      bool win = true;
       if (n_ca < kPendingCode) win = win && A.lock[n_ca >> 2] == pri;
       if (n_ab < kPendingCode) win = win && A.lock[n_ab >> 2] == pri;
       if (n_bd < kPendingCode) win = win && A.lock[n_bd >> 2] == pri;
       if (n_dc < kPendingCode) win = win && A.lock[n_dc >> 2] == pri;
       if (!win) continue;
-      const unsigned short a = vert(A, t, k), bq = vert(A, t, (k + 1) % 3), c = vert(A, t, (k + 2) % 3);
-      const unsigned short d = vert(A, u, ku);
+      const unsigned short a = DT_V(t, k), bq = DT_V(t, (k + 1) % 3), c = DT_V(t, (k + 2) % 3);
+      const unsigned short d = DT_V(u, ku);
       // t <- (a,b,d), u <- (a,d,c); the new diagonal (a,d) is opposite v1 in t and opposite v2 in u
       A.v0[t] = a; A.v1[t] = bq; A.v2[t] = d;
       A.n0[t] = static_cast<unsigned short>(n_bd); A.n1[t] = static_cast<unsigned short>((u << 2) | 2);
@@ -413,14 +521,14 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       link_back(A, n_ab, (t << 2) | 2);
       link_back(A, n_dc, (u << 2) | 0);
       link_back(A, n_ca, (u << 2) | 1);
-      atomicOr(&A.dirty[t >> 5], 1u << (t & 31));
-      atomicOr(&A.dirty[u >> 5], 1u << (u & 31));
+      atomicOr(&A.dirty[u >> 5], 1u << (u & 31));  // t's bit is already set
     }
     __syncthreads();
-    for (int t = tid; t < T; t += kDtThreads) A.lock[t] = 0xFFFFFFFFu;
-    __syncthreads();
   }
+#undef DT_V
+#undef DT_N
 
+  if (dbg && tid == 0) dbg[b * 8 + 0] = (int)((clock64() - clk0) >> 4);
   // ------------------------------------------------------------------ output: 16-byte records (v0,v1,v2,0,n0,n1,n2,0)
   for (int t = tid; t < T; t += kDtThreads) {
     const unsigned c0 = A.n0[t], c1 = A.n1[t], c2 = A.n2[t];
@@ -439,7 +547,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
 
 static size_t dt_smem_bytes(int cap, int tcap) {
   return static_cast<size_t>(12) * tcap + 4 * static_cast<size_t>(tcap) + 4 * static_cast<size_t>((tcap + 31) / 32) +
-         2 * static_cast<size_t>(cap + 2);
+         4 * static_cast<size_t>(cap);
 }
 
 }  // namespace fovea
@@ -448,12 +556,13 @@ using namespace fovea;
 
 extern "C" int64_t fovea_delaunay_workspace_bytes(int B, int cap) {
   (void)cap;
-  return static_cast<int64_t>(B) * 4 * 9;  // flip-round count per image + 8 debug words per image
+  // [B] flip rounds + [B,8] stage counters (int32), then [B, cap+2] row starts (uint16)
+  return static_cast<int64_t>(B) * 4 * 9 + static_cast<int64_t>(B) * (cap + 2) * 2;
 }
 
 extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
                               uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream) {
-  FOVEA_REQUIRE(pts && npts && mesh && ntri, "fovea_delaunay: null pointer");
+  FOVEA_REQUIRE(pts && npts && mesh && ntri && workspace, "fovea_delaunay: null pointer");
   FOVEA_REQUIRE(B > 0 && cap >= 4 && tcap >= 2 * cap, "fovea_delaunay: need tcap >= 2*cap (cap=%d tcap=%d)", cap, tcap);
   FOVEA_REQUIRE(max_coord > 0 && max_coord <= 8192,
                 "fovea_delaunay: coordinates must be < 8192 for the exact int64 in-circle test (got %d)", max_coord);
@@ -469,6 +578,6 @@ extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, in
   FOVEA_CUDA(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   delaunay_kernel<<<B, kDtThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       pts, npts, cap, tcap, mesh, ntri, static_cast<int32_t*>(workspace), 20000,
-      workspace ? static_cast<int32_t*>(workspace) + B : nullptr);
+      static_cast<int32_t*>(workspace) + B, reinterpret_cast<unsigned short*>(static_cast<int32_t*>(workspace) + 9 * B));
   return check_launch("fovea_delaunay");
 }

@@ -205,19 +205,20 @@ select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ hints
-// One CTA per image stages the mesh records in shared memory (<= 205 KB) so that the long first-level walks run
-// at shared-memory latency; level 0 = 16x16 probes walked from triangle 0, level 1 = every 32x32-pixel cell
-// walked from the nearest probe.
-constexpr int kHintThreads = 512;
+// One CTA per image stages the mesh records and the points in shared memory (<= 205 KB + 26 KB) so that the long
+// first-level walks run at shared-memory latency.  Three levels: 16x16 probes walked from triangle 0, then
+// 32x32-pixel cells walked from the nearest probe, then the 32x8 hint cells walked from their 32x32 parent.
+constexpr int kHintThreads = 1024;
 
 __global__ void __launch_bounds__(kHintThreads, 1)
-locate_hints_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const int32_t* __restrict__ ntri,
-                    int cap, int tcap, int H, int W, int32_t* __restrict__ hints) {
+locate_hints_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__ npts, const uint4* __restrict__ mesh,
+                    const int32_t* __restrict__ ntri, int cap, int tcap, int H, int W, int32_t* __restrict__ hints,
+                    int32_t* __restrict__ mid_ws) {
   extern __shared__ __align__(16) uint4 srec[];
   __shared__ int coarse[16 * 16];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int T = ntri[b];
-  const int ch = ceil_div(H, FOVEA_HINT_CELL), cw = ceil_div(W, FOVEA_HINT_CELL);
+  const int ch = ceil_div(H, FOVEA_HINT_CELL_H), cw = ceil_div(W, FOVEA_HINT_CELL_W);
   int32_t* hb = hints + static_cast<size_t>(b) * ch * cw;
   if (T <= 0) {
     for (int i = tid; i < ch * cw; i += kHintThreads) hb[i] = 0;
@@ -225,8 +226,11 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ m
   }
   const uint4* mb = mesh + static_cast<size_t>(b) * tcap;
   for (int t = tid; t < T; t += kHintThreads) srec[t] = mb[t];
+  int* spts = reinterpret_cast<int*>(srec + tcap);
+  const int n = npts[b];
+  for (int i = tid; i < n; i += kHintThreads) spts[i] = pts[static_cast<size_t>(b) * cap + i];
   __syncthreads();
-  Mesh m{pts + static_cast<size_t>(b) * cap, srec, T};
+  Mesh m{spts, srec, T};
   if (tid < 256) {
     const int py = tid / 16, px = tid % 16;
     const int qr = min(H - 1, (2 * py + 1) * H / 32), qc = min(W - 1, (2 * px + 1) * W / 32);
@@ -234,12 +238,22 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ m
     coarse[tid] = L.tri < 0 ? 0 : L.tri;
   }
   __syncthreads();
-  for (int i = tid; i < ch * cw; i += kHintThreads) {
+  // level 1: 32 x 32 pixel cells (4 hint cells tall) -> mid_ws [ceil(ch/4), cw]
+  const int mh = ceil_div(ch, 4);
+  int32_t* mid = mid_ws + static_cast<size_t>(b) * mh * cw;
+  for (int i = tid; i < mh * cw; i += kHintThreads) {
     const int cy = i / cw, cx = i - cy * cw;
-    const int qr = min(H - 1, cy * FOVEA_HINT_CELL + FOVEA_HINT_CELL / 2);
-    const int qc = min(W - 1, cx * FOVEA_HINT_CELL + FOVEA_HINT_CELL / 2);
+    const int qr = min(H - 1, cy * 32 + 16), qc = min(W - 1, cx * FOVEA_HINT_CELL_W + FOVEA_HINT_CELL_W / 2);
     const int py = min(15, qr * 16 / H), px = min(15, qc * 16 / W);
     const Located L = locate(m, qr, qc, coarse[py * 16 + px]);
+    mid[i] = L.tri < 0 ? 0 : L.tri;
+  }
+  __syncthreads();
+  for (int i = tid; i < ch * cw; i += kHintThreads) {
+    const int cy = i / cw, cx = i - cy * cw;
+    const int qr = min(H - 1, cy * FOVEA_HINT_CELL_H + FOVEA_HINT_CELL_H / 2);
+    const int qc = min(W - 1, cx * FOVEA_HINT_CELL_W + FOVEA_HINT_CELL_W / 2);
+    const Located L = locate(m, qr, qc, mid[(cy / 4) * cw + cx]);
     hb[i] = L.tri < 0 ? 0 : L.tri;
   }
 }
@@ -250,35 +264,96 @@ struct FillParams {
 };
 
 constexpr int kFillThreads = 256;
+constexpr int kFillTileW = 128, kFillTileH = 8;  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// One triangle held in registers while a thread steps along its 4 pixels.
+template <typename I>
+struct TriState {
+  int t;                 // triangle id
+  int r0, c0, r1, c1, r2, c2;
+  int s;                 // +1 / -1: orientation of the stored vertex order
+  I area;                // |orient(v0,v1,v2)|
+  I e0, e1, e2;          // orientation-normalised sub-areas at the current query
+  unsigned v01, v2;      // packed vertex ids
+  unsigned n0, n1, n2;   // neighbours (0xFFFF = hull)
+};
 
-// Each thread owns 4 consecutive pixels of one row: locate them once, then stream all channels with 128-bit
-// stores.  Addressing is "uniform base + 32-bit per-thread offset" everywhere in the channel loop: the table base
-// advances with the channel group, the per-pixel row offsets (n*Cs) and the pixel offset (y*W+x0) never change.
-template <bool kScores, bool kMask>
-__global__ void __launch_bounds__(kFillThreads)
+template <typename I>
+__device__ __forceinline__ I orient_i(int ar, int ac, int br, int bc, int qr, int qc) {
+  return static_cast<I>(bc - ac) * static_cast<I>(qr - ar) - static_cast<I>(br - ar) * static_cast<I>(qc - ac);
+}
+
+// ownership of a query whose edge function is e w.r.t. the directed edge a->b (see mesh.cuh, edge_owned)
+template <typename I>
+__device__ __forceinline__ bool owns(I e, int s, int dr, int dc, bool hull) {
+  if (e != 0) return e > 0;
+  if (hull) return true;
+  return dr != 0 ? (s * dr > 0) : (s * dc > 0);
+}
+
+template <typename I>
+__device__ __forceinline__ int test_state(const TriState<I>& S) {  // -1 = owned, else neighbour to move to
+  if (S.e0 > 0 && S.e1 > 0 && S.e2 > 0) return -1;
+  if (!owns<I>(S.e0, S.s, S.r2 - S.r1, S.c2 - S.c1, S.n0 == kNoTri)) return static_cast<int>(S.n0);
+  if (!owns<I>(S.e1, S.s, S.r0 - S.r2, S.c0 - S.c2, S.n1 == kNoTri)) return static_cast<int>(S.n1);
+  if (!owns<I>(S.e2, S.s, S.r1 - S.r0, S.c1 - S.c0, S.n2 == kNoTri)) return static_cast<int>(S.n2);
+  return -1;
+}
+
+template <typename I>
+__device__ __forceinline__ void load_state(TriState<I>& S, const uint4* __restrict__ rec, const int32_t* __restrict__ pts,
+                                           int t, int qr, int qc) {
+  const uint4 q = __ldg(rec + t);
+  const int p0 = __ldg(pts + (q.x & 0xFFFFu)), p1 = __ldg(pts + (q.x >> 16)), p2 = __ldg(pts + (q.y & 0xFFFFu));
+  S.t = t;
+  S.r0 = p0 >> 16; S.c0 = p0 & 0xFFFF; S.r1 = p1 >> 16; S.c1 = p1 & 0xFFFF; S.r2 = p2 >> 16; S.c2 = p2 & 0xFFFF;
+  I A = orient_i<I>(S.r0, S.c0, S.r1, S.c1, S.r2, S.c2);
+  S.s = A < 0 ? -1 : 1;
+  S.area = A < 0 ? -A : A;
+  S.e0 = static_cast<I>(S.s) * orient_i<I>(S.r1, S.c1, S.r2, S.c2, qr, qc);
+  S.e1 = static_cast<I>(S.s) * orient_i<I>(S.r2, S.c2, S.r0, S.c0, qr, qc);
+  S.e2 = S.area - S.e0 - S.e1;
+  S.v01 = q.x; S.v2 = q.y & 0xFFFFu;
+  S.n0 = q.z & 0xFFFFu; S.n1 = q.z >> 16; S.n2 = q.w & 0xFFFFu;
+}
+
+// Each thread owns 4 consecutive pixels of one row: locate them (walk once, then step the edge functions in
+// registers), then stream all channels with 128-bit stores.
+template <typename I, bool kScores, bool kMask>
+__global__ void __launch_bounds__(kFillThreads, 3)
 inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
                     const uint4* __restrict__ mesh, const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints,
                     const float* __restrict__ table, float* __restrict__ scores, long long* __restrict__ mask,
                     FillParams p) {
-  const int b = blockIdx.z, y = blockIdx.y;
-  const int x0 = (blockIdx.x * kFillThreads + threadIdx.x) * 4;
-  if (x0 >= p.W) return;
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
+  const int y = blockIdx.y * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
+  if (x0 >= p.W || y >= p.H) return;
   const int hw = p.h * p.w;
   const unsigned pixoff = static_cast<unsigned>(y) * p.W + x0;  // H*W < 2^32 is checked on the host
   const size_t plane = static_cast<size_t>(p.H) * p.W;
   const int32_t* srcb = src + static_cast<size_t>(b) * p.cap;
-  Mesh m{pts + static_cast<size_t>(b) * p.cap, mesh + static_cast<size_t>(b) * p.tcap, ntri[b]};
+  const int32_t* ptsb = pts + static_cast<size_t>(b) * p.cap;
+  const uint4* rec = mesh + static_cast<size_t>(b) * p.tcap;
+  const int T = ntri[b];
 
   const int4 win = *reinterpret_cast<const int4*>(winner + static_cast<size_t>(b) * plane + pixoff);
   const int wn[4] = {win.x, win.y, win.z, win.w};
-  unsigned o0[4], o1[4], o2[4];  // element offsets of the three table rows of each pixel
-  float w0[4], w1[4], w2[4];     // barycentric weights ((1,0,0) for a pixel that received a node)
-  unsigned nanmask = 0;          // pixels whose value is NaN in every channel
-  const int cw = ceil_div(p.W, FOVEA_HINT_CELL);
-  int start = hints[(static_cast<size_t>(b) * ceil_div(p.H, FOVEA_HINT_CELL) + y / FOVEA_HINT_CELL) * cw +
-                    x0 / FOVEA_HINT_CELL];
+  unsigned ob0[4], ob1[4], ob2[4];  // byte offsets of the three table rows of each pixel
+  float w0[4], w1[4], w2[4];        // barycentric weights ((1,0,0) for a pixel that received a node)
+  unsigned nanmask = 0;             // pixels whose value is NaN in every channel
+
+  TriState<I> S;
+  bool have = false;
+  int sn0 = hw, sn1 = hw, sn2 = hw;
+  double inv_area = 0.0;
+  int start = 0;
+  if (wn[0] < 0 || wn[1] < 0 || wn[2] < 0 || wn[3] < 0) {
+    const int cw = ceil_div(p.W, FOVEA_HINT_CELL_W);
+    start = hints[(static_cast<size_t>(b) * ceil_div(p.H, FOVEA_HINT_CELL_H) + y / FOVEA_HINT_CELL_H) * cw +
+                  x0 / FOVEA_HINT_CELL_W];
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int n0 = hw, n1 = hw, n2 = hw;
@@ -286,34 +361,57 @@ inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restric
     if (wn[k] >= 0) {
       n0 = n1 = n2 = wn[k];
     } else {
-      const Located L = locate(m, y, x0 + k, start);
-      if (L.tri >= 0) {  // (outside the triangulation cannot happen with the four corners present: NaN row)
-        start = L.tri;
-        // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 from the transform, c2 = 1 - c0 - c1, in float64
-        const double c0 = static_cast<double>(L.a0) / static_cast<double>(L.area);
-        const double c1 = static_cast<double>(L.a1) / static_cast<double>(L.area);
+      bool ok = have && test_state<I>(S) < 0;
+      if (!ok && T > 0) {
+        int t = have ? S.t : ((start >= 0 && start < T) ? start : 0);
+        for (int step = 0; step < T + 8; ++step) {
+          load_state<I>(S, rec, ptsb, t, y, x0 + k);
+          if (S.area == 0) break;
+          const int nxt = test_state<I>(S);
+          if (nxt < 0) { ok = true; break; }
+          if (static_cast<unsigned>(nxt) == kNoTri) break;
+          t = nxt;
+        }
+        if (!ok) {  // degenerate triangle on the way (host meshes only) or outside the hull: exhaustive search
+          Mesh m{ptsb, rec, T};
+          const Located L = locate_bruteforce(m, y, x0 + k);
+          if (L.tri >= 0) { load_state<I>(S, rec, ptsb, L.tri, y, x0 + k); ok = true; }
+        }
+        have = ok;
+        if (ok) {
+          sn0 = __ldg(srcb + (S.v01 & 0xFFFFu));
+          sn1 = __ldg(srcb + (S.v01 >> 16));
+          sn2 = __ldg(srcb + S.v2);
+          inv_area = 1.0 / static_cast<double>(S.area);
+        }
+      }
+      if (ok) {
+        // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 in float64, c2 = 1 - c0 - c1, then cast to float32
+        const double c0 = static_cast<double>(S.e0) * inv_area;
+        const double c1 = static_cast<double>(S.e1) * inv_area;
         a0 = static_cast<float>(c0);
         a1 = static_cast<float>(c1);
         a2 = static_cast<float>(1.0 - c0 - c1);
-        n0 = srcb[L.v01 & 0xFFFFu];
-        n1 = srcb[L.v01 >> 16];
-        n2 = srcb[L.v2];
+        n0 = sn0; n1 = sn1; n2 = sn2;
       }
+    }
+    if (have) {  // step the edge functions one pixel to the right: d e_i / d col = -s * (row_b - row_a)
+      S.e0 -= static_cast<I>(S.s * (S.r2 - S.r1));
+      S.e1 -= static_cast<I>(S.s * (S.r0 - S.r2));
+      S.e2 -= static_cast<I>(S.s * (S.r1 - S.r0));
     }
     if (n0 == hw || n1 == hw || n2 == hw) {  // a NaN vertex poisons every channel (NaN*w, even for w == 0)
       nanmask |= 1u << k;
       n0 = n1 = n2 = p.zero_residual ? hw + 1 : hw;  // models_instance.py:940: residual NaN -> 0
       a0 = 1.f; a1 = 0.f; a2 = 0.f;
     }
-    o0[k] = static_cast<unsigned>(n0) * p.Cs;
-    o1[k] = static_cast<unsigned>(n1) * p.Cs;
-    o2[k] = static_cast<unsigned>(n2) * p.Cs;
+    ob0[k] = static_cast<unsigned>(n0) * p.Cs * 4u;
+    ob1[k] = static_cast<unsigned>(n1) * p.Cs * 4u;
+    ob2[k] = static_cast<unsigned>(n2) * p.Cs * 4u;
     w0[k] = a0; w1[k] = a1; w2[k] = a2;
   }
-  // Byte offsets of the table rows; the channel loop adds them to one 64-bit base that advances by 16 B per group.
-  unsigned ob0[4], ob1[4], ob2[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { ob0[k] = o0[k] * 4u; ob1[k] = o1[k] * 4u; ob2[k] = o2[k] * 4u; }
+
+  // The channel loop adds the row offsets to one 64-bit base that advances by 16 B per 4-channel group.
   unsigned long long tbase = reinterpret_cast<unsigned long long>(table + static_cast<size_t>(b) * (hw + 2) * p.Cs);
   unsigned long long obase = reinterpret_cast<unsigned long long>(
       kScores ? scores + static_cast<size_t>(b) * p.C * plane + pixoff : nullptr);
@@ -450,19 +548,38 @@ extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int
   return check_launch("fovea_select_points");
 }
 
+extern "C" int64_t fovea_locate_hints_workspace_bytes(int B, int H, int W) {
+  return static_cast<int64_t>(B) * ceil_div(ceil_div(H, FOVEA_HINT_CELL_H), 4) * ceil_div(W, FOVEA_HINT_CELL_W) * 4;
+}
+
 extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* mesh, const int32_t* ntri,
-                                  int B, int cap, int tcap, int H, int W, int32_t* hints, fovea_stream_t stream) {
-  (void)npts;
-  FOVEA_REQUIRE(pts && mesh && ntri && hints && B > 0 && H > 0 && W > 0, "fovea_locate_hints: bad arguments");
-  const size_t smem = static_cast<size_t>(tcap) * sizeof(uint4);
-  if (smem > 220 * 1024) {
-    set_error("fovea_locate_hints: tcap=%d needs %zu B of shared memory (> 220 KB)", tcap, smem);
+                                  int B, int cap, int tcap, int H, int W, int32_t* hints, void* workspace,
+                                  fovea_stream_t stream) {
+  FOVEA_REQUIRE(pts && npts && mesh && ntri && hints && workspace && B > 0 && H > 0 && W > 0,
+                "fovea_locate_hints: bad arguments");
+  const size_t smem = static_cast<size_t>(tcap) * sizeof(uint4) + static_cast<size_t>(cap) * 4;
+  if (smem > 231 * 1024) {
+    set_error("fovea_locate_hints: tcap=%d needs %zu B of shared memory", tcap, smem);
     return FOVEA_ERR_CAPACITY;
   }
   FOVEA_CUDA(cudaFuncSetAttribute(locate_hints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   locate_hints_kernel<<<B, kHintThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      pts, reinterpret_cast<const uint4*>(mesh), ntri, cap, tcap, H, W, hints);
+      pts, npts, reinterpret_cast<const uint4*>(mesh), ntri, cap, tcap, H, W, hints, static_cast<int32_t*>(workspace));
   return check_launch("fovea_locate_hints");
+}
+
+template <typename I>
+static int launch_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const uint4* m4,
+                       const int32_t* ntri, const int32_t* hints, const float* table, float* scores, long long* mk,
+                       const FillParams& p, int B, cudaStream_t s) {
+  dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH), B);
+  if (scores && mk)
+    inverse_fill_kernel<I, true, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
+  else if (scores)
+    inverse_fill_kernel<I, true, false><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
+  else
+    inverse_fill_kernel<I, false, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
+  return check_launch("fovea_inverse_fill");
 }
 
 extern "C" int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
@@ -475,21 +592,16 @@ extern "C" int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, con
   FOVEA_REQUIRE(B > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && h > 0 && w > 0 && H > 1 && W > 1,
                 "fovea_inverse_fill: bad sizes");
   FOVEA_REQUIRE(W % 4 == 0, "fovea_inverse_fill: W=%d must be a multiple of 4 (128-bit stores)", W);
-  FOVEA_REQUIRE(B <= 65535 && H <= 65535, "fovea_inverse_fill: B and H must be <= 65535");
-  FOVEA_REQUIRE(static_cast<long long>(H) * W < (1ll << 32) && static_cast<long long>(h) * w * Cs < (1ll << 31),
+  FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_inverse_fill: B or H too large for the grid");
+  FOVEA_REQUIRE(static_cast<long long>(H) * W < (1ll << 32) && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
                 "fovea_inverse_fill: canvas or value table too large for 32-bit offsets");
   FillParams p{C, Cs, h, w, H, W, cap, tcap, zero_residual};
-  dim3 grid(ceil_div(W, kFillThreads * 4), H, B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
   long long* mk = reinterpret_cast<long long*>(mask);
-  if (scores && mask)
-    inverse_fill_kernel<true, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
-  else if (scores)
-    inverse_fill_kernel<true, false><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
-  else
-    inverse_fill_kernel<false, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
-  return check_launch("fovea_inverse_fill");
+  // coordinates < 16384 keep every orientation determinant inside int32 (|diff| < 2^14, products < 2^28)
+  if (H <= 16384 && W <= 16384) return launch_fill<int>(winner, pts, src, m4, ntri, hints, table, scores, mk, p, B, s);
+  return launch_fill<long long>(winner, pts, src, m4, ntri, hints, table, scores, mk, p, B, s);
 }
 
 extern "C" int fovea_argmax_classes(const float* scores, int B, int C, int64_t HW, int64_t* mask,

@@ -9,12 +9,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfovea_b200.so")
+LIB_PATH = os.environ.get("FOVEA_B200_LIB", os.path.join(_HERE, "libfovea_b200.so"))
 
 FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
-HINT_CELL = 32
+HINT_CELL_W, HINT_CELL_H = 32, 8
 ABI_VERSION = 1
 
 
@@ -42,7 +42,8 @@ PROTOTYPES = {
     "fovea_select_points": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_delaunay_workspace_bytes": (_i64, [_i, _i]),
     "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_locate_hints_workspace_bytes": (_i64, [_i, _i, _i]),
+    "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_argmax_classes": (_i, [_p, _i, _i, _i64, _p, _p]),
 }

@@ -261,10 +261,12 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
         mesh, ntri, _ = delaunay_device(pts, npts, cap, tcap, max(H, W))
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
-    ch, cw = -(-H // _lib.HINT_CELL), -(-W // _lib.HINT_CELL)
+    ch, cw = -(-H // _lib.HINT_CELL_H), -(-W // _lib.HINT_CELL_W)
     hints = torch.empty(B, ch, cw, device=dev, dtype=torch.int32)
+    hws = torch.empty(int(_lib.load().fovea_locate_hints_workspace_bytes(B, H, W)) // 4 + 1, device=dev,
+                      dtype=torch.int32)
     _lib.call("fovea_locate_hints", _ptr(pts), _ptr(npts), _ptr(mesh), _ptr(ntri), B, cap, tcap, H, W, _ptr(hints),
-              _stream())
+              _ptr(hws), _stream())
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, h, w, H, W, cap, tcap, triangulation)
 
 
@@ -276,7 +278,8 @@ def delaunay_device(pts, npts, cap, tcap, max_coord):
     B, dev = pts.shape[0], pts.device
     mesh = torch.empty(B, tcap, 8, device=dev, dtype=torch.uint16)
     ntri = torch.empty(B, device=dev, dtype=torch.int32)
-    ws = torch.zeros(9 * B, device=dev, dtype=torch.int32)  # [B] flip rounds + [B,8] stage counters
+    nbytes = int(_lib.load().fovea_delaunay_workspace_bytes(B, cap))
+    ws = torch.zeros((nbytes + 3) // 4, device=dev, dtype=torch.int32)  # [B] flip rounds, [B,8] counters, scratch
     _lib.call("fovea_delaunay", _ptr(pts), _ptr(npts), B, cap, tcap, int(max_coord), _ptr(mesh), _ptr(ntri),
               _ptr(ws), _stream())
     return mesh, ntri, ws

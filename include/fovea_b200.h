@@ -149,11 +149,15 @@ int64_t fovea_delaunay_workspace_bytes(int B, int cap);
 int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
                    uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream);
 
-/* Walk-start hints for fovea_inverse_fill: hints[b, cy, cx] = a triangle containing (or near) the centre
- * of the FOVEA_HINT_CELL x FOVEA_HINT_CELL pixel cell.  hints [B, ceil(H/cell), ceil(W/cell)] int32 */
-#define FOVEA_HINT_CELL 32
+/* Walk-start hints for fovea_inverse_fill: hints[b, cy, cx] = the triangle containing the centre of the
+ * FOVEA_HINT_CELL_W x FOVEA_HINT_CELL_H pixel cell (one warp tile of the fill kernel is 32 x 4 pixels).
+ * hints [B, ceil(H/FOVEA_HINT_CELL_H), ceil(W/FOVEA_HINT_CELL_W)] int32
+ * workspace: fovea_locate_hints_workspace_bytes(B, H, W) bytes of device memory */
+#define FOVEA_HINT_CELL_W 32
+#define FOVEA_HINT_CELL_H 8
+int64_t fovea_locate_hints_workspace_bytes(int B, int H, int W);
 int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* mesh, const int32_t* ntri, int B,
-                       int cap, int tcap, int H, int W, int32_t* hints, fovea_stream_t stream);
+                       int cap, int tcap, int H, int W, int32_t* hints, void* workspace, fovea_stream_t stream);
 
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
  * fillMissingValues_tensor(..., 'tri') = Interp2D point location + barycentric gather
