@@ -261,12 +261,7 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
         mesh, ntri, _ = delaunay_device(pts, npts, cap, tcap, max(H, W))
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
-    ch, cw = -(-H // _lib.HINT_CELL_H), -(-W // _lib.HINT_CELL_W)
-    hints = torch.empty(B, ch, cw, device=dev, dtype=torch.int32)
-    hws = torch.empty(int(_lib.load().fovea_locate_hints_workspace_bytes(B, H, W)) // 4 + 1, device=dev,
-                      dtype=torch.int32)
-    _lib.call("fovea_locate_hints", _ptr(pts), _ptr(npts), _ptr(mesh), _ptr(ntri), B, cap, tcap, H, W, _ptr(hints),
-              _ptr(hws), _stream())
+    hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, h, w, H, W, cap, tcap, triangulation)
 
 
@@ -283,6 +278,37 @@ def delaunay_device(pts, npts, cap, tcap, max_coord):
     _lib.call("fovea_delaunay", _ptr(pts), _ptr(npts), B, cap, tcap, int(max_coord), _ptr(mesh), _ptr(ntri),
               _ptr(ws), _stream())
     return mesh, ntri, ws
+
+
+def _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W):
+    dev = pts.device
+    ch, cw = -(-H // _lib.HINT_CELL_H), -(-W // _lib.HINT_CELL_W)
+    hints = torch.empty(B, ch, cw, device=dev, dtype=torch.int32)
+    hws = torch.empty(int(_lib.load().fovea_locate_hints_workspace_bytes(B, H, W)) // 4 + 1, device=dev,
+                      dtype=torch.int32)
+    _lib.call("fovea_locate_hints", _ptr(pts), _ptr(npts), _ptr(mesh), _ptr(ntri), B, cap, tcap, H, W, _ptr(hints),
+              _ptr(hws), _stream())
+    return hints
+
+
+def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
+    """Plan for interpolating EVERY pixel of an H x W canvas from an arbitrary site set (Interp2D, interp2d.py:37-91):
+    no pixel carries a node (winner = -1 everywhere); `table_rows` is the index of the NaN row of the value table."""
+    B, cap = pts.shape
+    tcap = mesh.shape[1]
+    winner = torch.full((B, H, W), -1, device=pts.device, dtype=torch.int32)
+    hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, table_rows, 1, H, W, cap, tcap, "given")
+
+
+def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=None, mask=None):
+    """fovea_inverse_fill on a caller-built value table [B, plan.h*plan.w + 2, Cs]."""
+    B = plan.winner.shape[0]
+    _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
+              _ptr(plan.mesh), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), B, int(C), table.shape[2], plan.h,
+              plan.w, plan.H, plan.W, plan.cap, plan.tcap, 1 if zero_residual else 0, _ptr(scores), _ptr(mask),
+              _stream())
+    return scores, mask
 
 
 def box4_table(pred, Cs=None):

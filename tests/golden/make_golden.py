@@ -1,6 +1,7 @@
 """Generate golden vectors from the UNMODIFIED reference (run in the build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py --functions     # create_grid / grid_inv / fill / Interp2D fixtures
+    python tests/golden/make_golden.py --module        # DeformSegmentationModule.forward fixtures
 
 Imports /root/reference through ref_shim.py, runs the reference's own `create_grid`, `F.grid_sample`
 call pattern, NaN-mask inverse sampling and `fillMissingValues_tensor('tri')` (with the reference's own
@@ -95,7 +96,7 @@ def case_interp2d(name, h, w, N, vdim, seed):
     print(name, out.shape)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--functions" in sys.argv:
     torch.set_num_threads(8)
     # BASELINE geometry: saliency 80x80, task 80x80, R=45, replication pad
     m, xs, grid, gi = case_grid("grid_80_R45", (80, 80), (80, 80), 45, (128, 128), B=2, seed=1)
@@ -109,3 +110,83 @@ if __name__ == "__main__":
     case_grid("grid_40x80_R12_zero", (40, 80), (64, 96), 12, (96, 160), B=2, seed=4, pad_mode="zero", rate=2)
     case_grid("grid_32_R10_eval", (32, 32), (32, 32), 10, (64, 64), B=3, seed=5, task_eval=(48, 48))
     case_interp2d("interp2d_64x48", 64, 48, 300, 4, seed=6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Module-level golden: the reference's own DeformSegmentationModule.forward (models/models.py:666-1094) on CPU with
+# its real saliency net (saliency_network.fov_simple) + CompressNet, tiny stand-in encoder/decoder, deform.yaml
+# configuration.  pytorch_toolbelt is absent, so its DiceLoss('multiclass') is the restatement in fovea.models
+# (loss values are outside the hot path; they are stored as a sanity check only).
+# ---------------------------------------------------------------------------------------------------------------
+def case_module(name, upsample, H=256, W=256, B=2, seed=11):
+    import importlib, yaml, io, contextlib
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "foveated-instance-segmentation_b200"))
+    sys.path.insert(0, os.path.dirname(HERE))
+    from fovea.models import MulticlassDiceLoss
+    from tiny_nets import TinyEncoder, TinyDecoder, synthetic_batch
+    rm.DiceLoss = lambda *a, **k: MulticlassDiceLoss()
+    defaults = importlib.import_module("config.defaults")
+    cfg = defaults._C
+
+    def merge(dst, src):
+        for k, v in src.items():
+            if isinstance(v, dict):
+                merge(dst[k], v)
+            elif isinstance(v, str) and not isinstance(dst.get(k), str):
+                import ast
+                dst[k] = ast.literal_eval(v)      # yacs decodes "(80,80)"-style strings the same way
+            else:
+                dst[k] = v
+    merge(cfg, yaml.safe_load(open(os.path.join(ref_shim.REF, "config", "deform.yaml"))))
+    # README.md:73/79 command-line overrides of the shipped recipe
+    cfg.TRAIN.task_input_size = (80, 80)
+    cfg.TRAIN.saliency_input_size = (80, 80)
+    cfg.MODEL.gaussian_radius = 45
+    cfg.TRAIN.deform_joint_loss = True
+    cfg.VAL.no_upsample = True
+    cfg.DATASET.grid_path = ""
+    cfg.MODEL.upsample = upsample
+    cfg.MODEL.rev_deform_interp = "tri"
+    cfg.TRAIN.global_epoch = 1
+    cfg.DIR = "/tmp/fovea_golden"
+    cfg.TRAIN.num_gpus = 1
+    for k in ("saliency_input_size", "task_input_size", "task_input_size_eval", "dynamic_task_input"):
+        cfg.TRAIN[k] = tuple(cfg.TRAIN[k])
+    torch.manual_seed(seed)
+    import saliency_network as rs
+    sal, comp = rs.fov_simple(cfg), rm.CompressNet(cfg)
+    for net in (sal, comp):
+        net.apply(rm.ModelBuilder.weights_init)
+    enc, dec = TinyEncoder(), TinyDecoder(num_class=cfg.DATASET.num_class)
+    m = rm.DeformSegmentationModule(enc, dec, sal, comp, None, cfg)
+    m.eval()
+    captured = {}
+    sal.register_forward_pre_hook(lambda mod, inp: captured.__setitem__("x_low", inp[0].detach().clone()))
+    enc.register_forward_pre_hook(lambda mod, inp: captured.__setitem__("x_sampled", inp[0].detach().clone()))
+    orig_acc = m.pixel_acc
+    m.pixel_acc = lambda p, l: (captured.__setitem__("scored", p.detach().clone()), orig_acc(p, l))[1]
+    feed = synthetic_batch(B, H, W, seed)
+    feed_in = {k: v.clone() for k, v in feed.items()}
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        out = m(feed, is_inference=True, rank=1, cur_iter=-1)
+    names = ["loss", "acc", "edge_loss", "acc_bin_fg", "acc_cls_fbg", "acc_bin_fbg"]
+    res = {n: np.array(float(v)) for n, v in zip(names, out)}
+    sd = {}
+    for tag, net in (("sal", sal), ("comp", comp), ("enc", enc), ("dec", dec)):
+        for k, v in net.state_dict().items():
+            sd[f"sd_{tag}__{k}"] = v.numpy()
+    arrays = dict(H=np.array(H), W=np.array(W), upsample=np.array(upsample), seed=np.array(seed), B=np.array(B),
+                  x_low=captured["x_low"].numpy(), x_sampled=captured["x_sampled"].numpy(),
+                  seg_label_after=feed["seg_label"].numpy(), **res, **sd)
+    if upsample:  # scores at full resolution would be 2*51*H*W floats: keep the argmax mask + a strided sample
+        sc = captured["scored"]
+        arrays["scored_argmax"] = torch.max(torch.nan_to_num(sc, nan=0.0), 1)[1].to(torch.uint8).numpy()
+        arrays["scored_nan"] = np.packbits(torch.isnan(sc[:, 0]).numpy())
+        arrays["scored_sub"] = sc[:, ::5, ::4, ::4].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    print(name, res)
+
+
+if __name__ == "__main__" and "--module" in sys.argv:
+    case_module("module_256_lowres", upsample=False)
+    case_module("module_256_upsample", upsample=True)

@@ -1,0 +1,140 @@
+"""Drop-in module test: fovea.models.DeformSegmentationModule against the reference's own forward
+(tests/golden/module_256_*.npz, produced by tests/golden/make_golden.py --module on CPU with identical weights).
+
+Tolerances: x_low (stock ops) 1e-5.  x_sampled is the image sampled at the *grid*, and the reference's fp32 91x91
+convolution puts its grid ~2e-5 from the exact value (tests/test_parity_gpu.py); on a U[0,1) noise image of width W
+that moves samples by ~2e-5 * W/2 pixels, so |x_sampled - ref| is bounded by ~1e-4 * W * |d img/dx| -- asserted as a
+small median and a bounded maximum.  Losses / accuracies are sanity checks (stock PyTorch code outside the path).
+"""
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from tiny_nets import TinyDecoder, TinyEncoder, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def make_cfg(upsample):
+    return NS(
+        TRAIN=NS(saliency_input_size=(80, 80), task_input_size=(80, 80), task_input_size_eval=(), dynamic_task_input=(1,),
+                 def_saliency_pad_mode="replication", deform_joint_loss=True, opt_deform_LabelEdge_norm=True,
+                 opt_deform_LabelEdge=False, edge_loss_scale=100.0, global_epoch=1, num_gpus=1),
+        MODEL=NS(saliency_output_size_short=0, gaussian_radius=45, gaussian_ap=0.0, upsample=upsample,
+                 rev_deform_interp="tri", uniform_sample="", gt_gradient=False, loss_at_high_res=False,
+                 saliency_net="fovsimple"),
+        DATASET=NS(segm_downsampling_rate=1, num_class=51),
+        VAL=NS(no_upsample=True),
+    )
+
+
+def build(golden, upsample, triangulation):
+    from fovea.models import CompressNet, DeformSegmentationModule
+    from fovea.saliency_network import fov_simple
+    cfg = make_cfg(upsample)
+    nets = {"sal": fov_simple(cfg), "comp": CompressNet(cfg), "enc": TinyEncoder(), "dec": TinyDecoder(num_class=51)}
+    for tag, net in nets.items():
+        sd = {k[len(f"sd_{tag}__"):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(f"sd_{tag}__")}
+        net.load_state_dict(sd, strict=True)
+    m = DeformSegmentationModule(nets["enc"], nets["dec"], nets["sal"], nets["comp"], None, cfg,
+                                 triangulation=triangulation)
+    return m.cuda().eval(), nets
+
+
+@pytest.mark.parametrize("upsample,triangulation", [(False, "device"), (True, "host"), (True, "device")])
+def test_module_forward_matches_reference(golden_dir, upsample, triangulation):
+    name = "module_256_upsample" if upsample else "module_256_lowres"
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    m, nets = build(g, upsample, triangulation)
+    H, W, B = int(g["H"]), int(g["W"]), int(g["B"])
+    feed = {k: v.cuda() for k, v in synthetic_batch(B, H, W, int(g["seed"])).items()}
+    cap = {}
+    nets["sal"].register_forward_pre_hook(lambda mod, inp: cap.__setitem__("x_low", inp[0].detach()))
+    nets["enc"].register_forward_pre_hook(lambda mod, inp: cap.__setitem__("x_sampled", inp[0].detach()))
+    orig = m.pixel_acc
+    m.pixel_acc = lambda p, l: (cap.__setitem__("scored", p.detach()), orig(p, l))[1]
+    with torch.no_grad():
+        out = m(feed, is_inference=True, rank=1, cur_iter=-1)
+    assert len(out) == 6
+    np.testing.assert_allclose(cap["x_low"].cpu().numpy(), g["x_low"], rtol=0, atol=1e-5)
+    err = np.abs(cap["x_sampled"].cpu().numpy() - g["x_sampled"])
+    assert np.median(err) < 2e-4 and err.max() < 1e-4 * W, (np.median(err), err.max())
+    lab = feed["seg_label"].cpu().numpy()
+    assert (lab != g["seg_label_after"]).mean() < 2e-3          # feed_dict['seg_label'] is mutated like the reference
+    for k, v in zip(["loss", "acc", "edge_loss", "acc_bin_fg", "acc_cls_fbg", "acc_bin_fbg"], out):
+        assert abs(float(v) - float(g[k])) <= 2e-2 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
+    if upsample:
+        sc = cap["scored"]
+        assert sc.shape == (B, 51, H, W)
+        mask = torch.max(torch.nan_to_num(sc, nan=0.0), 1)[1].cpu().numpy()
+        agree = (mask == g["scored_argmax"]).mean()
+        nan_ref = np.unpackbits(g["scored_nan"])[: B * H * W].reshape(B, H, W).astype(bool)
+        nan_agree = (torch.isnan(sc[:, 0]).cpu().numpy() == nan_ref).mean()
+        print(f"upsample/{triangulation}: full-res mask agreement {agree:.4f}, NaN-pattern agreement {nan_agree:.4f}")
+        assert agree > 0.93 and nan_agree > 0.97
+
+
+def test_module_training_step_backward():
+    """Gradients reach the saliency network through grid_sample -> create_grid (autograd.Functions on the kernels)."""
+    from fovea.models import CompressNet, DeformSegmentationModule
+    from fovea.saliency_network import fov_simple
+    cfg = make_cfg(False)
+    torch.manual_seed(0)
+    sal, comp, enc, dec = fov_simple(cfg), CompressNet(cfg), TinyEncoder(), TinyDecoder()
+    m = DeformSegmentationModule(enc, dec, sal, comp, None, cfg).cuda().train()
+    feed = {k: v.cuda() for k, v in synthetic_batch(4, 192, 192, 5).items()}
+    loss, acc, edge = m(feed, rank=1, cur_iter=-1)
+    loss.backward()
+    g_sal = torch.cat([p.grad.flatten() for p in sal.parameters() if p.grad is not None])
+    g_enc = torch.cat([p.grad.flatten() for p in enc.parameters()])
+    assert torch.isfinite(g_sal).all() and g_sal.abs().sum() > 0
+    assert torch.isfinite(g_enc).all() and g_enc.abs().sum() > 0
+    assert "filter.weight" in m.state_dict() and m.state_dict()["filter.weight"].shape == (1, 1, 91, 91)
+
+
+def test_create_grid_and_inference_interfaces():
+    from fovea.models import CompressNet, DeformSegmentationModule
+    from fovea.saliency_network import fov_simple
+    from oracle import reference_port as rp
+    cfg = make_cfg(True)
+    m = DeformSegmentationModule(TinyEncoder(), TinyDecoder(), fov_simple(cfg), CompressNet(cfg), None, cfg).cuda().eval()
+    xs, _ = rp.synthetic_saliency(2, seed=4)
+    xs_hm = rp.pad_saliency(xs, 45, 45).cuda()
+    grid, grid_y = m.create_grid(xs_hm)
+    assert grid.shape == (2, 80, 80, 2) and grid_y.shape == (2, 80, 80, 2)
+    grid2, grid_inv = m.create_grid(xs_hm, segSize=(128, 160), x_inv=1 - xs_hm)
+    assert grid_inv.shape == (2, 128, 160, 2)
+    want = rp.grid_inverse(grid2.cpu(), (128, 160), tie="max")
+    assert np.array_equal(grid_inv.cpu().numpy(), want.numpy(), equal_nan=True)
+    feed = {k: v.cuda() for k, v in synthetic_batch(2, 128, 160, 9).items()}
+    with torch.no_grad():
+        cfg.VAL.no_upsample = False
+        pred_sampled, pred, y_sampled = m(feed, segSize=(128, 160))
+    assert pred_sampled.shape == (2, 51, 128, 160) and pred.shape == (2, 51, 80, 80) and y_sampled.shape == (2, 80, 80)
+    assert not torch.isnan(pred_sampled).any()
+
+
+def test_fill_missing_values_and_interp2d_api(golden_dir):
+    """The reference-named entry points on arbitrary tensors / point sets (host triangulation = exact parity)."""
+    from fovea.interp2d import Interp2D
+    from fovea.models import fillMissingValues_tensor
+    from oracle import reference_port as rp
+    g = dict(np.load(os.path.join(golden_dir, "interp2d_64x48.npz")))
+    h, w = (int(v) for v in g["hw"])
+    pts, vals = torch.from_numpy(g["points"]), torch.from_numpy(g["values"])
+    for tri_mode in ("host", "device"):
+        out = Interp2D(h, w, triangulation=tri_mode)(pts.cuda(), vals.cuda()).cpu().numpy()
+        close = np.isclose(out, g["out"], rtol=0, atol=1e-5)
+        print("Interp2D", tri_mode, "agreement", close.mean())
+        assert close.mean() > (0.999 if tri_mode == "host" else 0.7)
+    gi = dict(np.load(os.path.join(golden_dir, "inverse_80_to_128.npz")))
+    t = torch.from_numpy(gi["pred_sampled_nan"][0]).cuda()
+    want = rp.fill_missing_values_tensor(torch.from_numpy(gi["pred_sampled_nan"][0]).clone())
+    got = fillMissingValues_tensor(t, copy=True, triangulation="host").cpu()
+    same_nan = (torch.isnan(got) == torch.isnan(want)).float().mean().item()
+    close = torch.isclose(got, want, rtol=0, atol=1e-5, equal_nan=True).float().mean().item()
+    assert same_nan > 0.999 and close > 0.999, (same_nan, close)
+    assert torch.equal(torch.isnan(t), torch.from_numpy(np.isnan(gi["pred_sampled_nan"][0])).cuda())  # copy=True
