@@ -17,6 +17,10 @@ from tiny_nets import TinyDecoder, TinyEncoder, synthetic_batch
 
 pytestmark = pytest.mark.gpu
 
+# the stock saliency / encoder convolutions must run in true fp32 for a parity check (cuDNN defaults to TF32)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def make_cfg(upsample):
     return NS(
@@ -38,7 +42,10 @@ def build(golden, upsample, triangulation):
     nets = {"sal": fov_simple(cfg), "comp": CompressNet(cfg), "enc": TinyEncoder(), "dec": TinyDecoder(num_class=51)}
     for tag, net in nets.items():
         sd = {k[len(f"sd_{tag}__"):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(f"sd_{tag}__")}
-        net.load_state_dict(sd, strict=True)
+        # strict=False as the reference's ModelBuilder (models/models.py:1213-1216): its SynchronizedBatchNorm2d keeps
+        # extra bookkeeping buffers (_tmp_running_mean, ...); every real parameter / running stat must be present
+        res = net.load_state_dict(sd, strict=False)
+        assert all(k.endswith("num_batches_tracked") for k in res.missing_keys), res.missing_keys
     m = DeformSegmentationModule(nets["enc"], nets["dec"], nets["sal"], nets["comp"], None, cfg,
                                  triangulation=triangulation)
     return m.cuda().eval(), nets
@@ -56,14 +63,30 @@ def test_module_forward_matches_reference(golden_dir, upsample, triangulation):
     nets["enc"].register_forward_pre_hook(lambda mod, inp: cap.__setitem__("x_sampled", inp[0].detach()))
     orig = m.pixel_acc
     m.pixel_acc = lambda p, l: (cap.__setitem__("scored", p.detach()), orig(p, l))[1]
-    with torch.no_grad():
-        out = m(feed, is_inference=True, rank=1, cur_iter=-1)
+    from fovea import ops
+    from oracle import reference_port as rp
+    calls, stock = [], ops.grid_sample
+    ops.grid_sample = lambda inp, grid: (calls.append((inp.detach().cpu(), grid.detach().cpu())), stock(inp, grid))[1]
+    try:
+        with torch.no_grad():
+            out = m(feed, is_inference=True, rank=1, cur_iter=-1)
+    finally:
+        ops.grid_sample = stock
     assert len(out) == 6
     np.testing.assert_allclose(cap["x_low"].cpu().numpy(), g["x_low"], rtol=0, atol=1e-5)
     err = np.abs(cap["x_sampled"].cpu().numpy() - g["x_sampled"])
     assert np.median(err) < 2e-4 and err.max() < 1e-4 * W, (np.median(err), err.max())
+    # feed_dict['seg_label'] is mutated like the reference (models/models.py:951): y_sampled.long().  Truncating a
+    # bilinear sample of a {0,1} disc is a rounding lottery in the reference itself (the four weights of a pixel
+    # whose taps are all 1 sum to 1.0 or 1-ulp: the golden has ~2 % holes inside the disc), so the label is pinned
+    # twice: bit-exact against the oracle's F.grid_sample on the grid this module produced, and within the lottery
+    # rate against the reference's label on its own (CPU-convolution) grid.
     lab = feed["seg_label"].cpu().numpy()
-    assert (lab != g["seg_label_after"]).mean() < 2e-3          # feed_dict['seg_label'] is mutated like the reference
+    (y_in, grid_y) = calls[0]
+    assert y_in.shape[1] == 1
+    want = rp.grid_sample(y_in, grid_y).squeeze(1).long().numpy()
+    assert np.array_equal(lab, want)
+    assert (lab != g["seg_label_after"]).mean() < 2e-2
     for k, v in zip(["loss", "acc", "edge_loss", "acc_bin_fg", "acc_cls_fbg", "acc_bin_fbg"], out):
         assert abs(float(v) - float(g[k])) <= 2e-2 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
     if upsample:
