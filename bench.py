@@ -41,7 +41,7 @@ WORKLOADS = {
     "b16_4096": dict(B=16, H=4096, W=4096, C=51, g=80, R=45),
     "tiny": dict(B=4, H=256, W=256, C=51, g=80, R=45),
 }
-KERNELS_PER_STEP = 8  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay, locate_hints, box4_table, inverse_fill
+KERNELS_PER_STEP = 9  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay, locate_hints, locate_pixels, box4_table, inverse_fill
 
 
 def peaks():
@@ -143,13 +143,8 @@ class Path:
         return x_sampled
 
     def _fill(self, plan, pred, table, want_scores, want_mask):
-        from fovea import _lib
-        from fovea.ops import _ptr, _stream
-        cfg = self.cfg
-        _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
-                  _ptr(plan.mesh), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), cfg["B"], cfg["C"],
-                  table.shape[2], cfg["g"], cfg["g"], cfg["H"], cfg["W"], plan.cap, plan.tcap, 1,
-                  _ptr(self.scores) if want_scores else None, _ptr(self.mask) if want_mask else None, _stream())
+        self.ops._fill(plan, table, self.cfg["C"], True, self.scores if want_scores else None,
+                       self.mask if want_mask else None)
 
 
 def cpu_reference_time(cfg, frames, reps, seed=0):
@@ -285,6 +280,18 @@ def main():
                "d2h_bytes_per_step": hmask.numel() * 8, "steps": k,
                "what": "pinned host image+saliency+pred -> H2D -> path (scores + fused argmax) -> D2H int64 masks"}
 
+    # ---------------- write-only ceiling of the fill kernel's store pattern (diagnostic, outside the timed region)
+    ceil_ms = []
+    for i in range(4):
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        path.ops.probe_store_ceiling(path.scores)
+        b2.record()
+        torch.cuda.synchronize()
+        if i:
+            ceil_ms.append(a.elapsed_time(b2))
+    store_ceiling = 4.0 * C * H * W * B / (min(ceil_ms) * 1e-3) / 1e9
+
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 4.0 * C * H * W * B
@@ -301,7 +308,8 @@ def main():
             "clocks": clocks.summary(),
             "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": fill_ms},
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": fill_ms,
+                         "store_only_ceiling_gbs": store_ceiling},
         }
         if e2e:
             line["e2e"] = e2e

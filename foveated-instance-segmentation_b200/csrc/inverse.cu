@@ -258,15 +258,18 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------ A8+A9+A10
-struct FillParams {
-  int C, Cs, h, w, H, W, cap, tcap, zero_residual;
-};
+// ------------------------------------------------------------------------------------------------ A9 location
+// Stage 3 is split in two kernels.  locate_pixels (below) resolves, for every full-resolution pixel, which low-res
+// node or which triangle of the mesh produces its value -- 4 B per pixel, a function of the sampling grid only.
+// inverse_fill then streams the C channels of every pixel from that map with no walks and no divergent loops, so
+// the store-bound kernel runs at a register count / occupancy chosen for streaming, and the location work can
+// overlap the encoder on a side stream (it does not depend on `pred`).
+//
+//   loc[b,y,x] >= 0        : id of the triangle that owns pixel (y,x)          (interp2d.py:58 find_simplex)
+//   loc[b,y,x] = -(n+1)    : the pixel received low-res node n directly        (models/models.py:650-651);
+//                            n == h*w: no value (outside the triangulation)    -> the NaN row of the value table
 
-constexpr int kFillThreads = 256;
-constexpr int kFillTileW = 128, kFillTileH = 8;  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
-
-// One triangle held in registers while a thread steps along its 4 pixels.
+// One triangle held in registers while a thread steps along its run of pixels.
 template <typename I>
 struct TriState {
   int t;                 // triangle id
@@ -274,7 +277,6 @@ struct TriState {
   int s;                 // +1 / -1: orientation of the stored vertex order
   I area;                // |orient(v0,v1,v2)|
   I e0, e1, e2;          // orientation-normalised sub-areas at the current query
-  unsigned v01, v2;      // packed vertex ids
   unsigned n0, n1, n2;   // neighbours (0xFFFF = hull)
 };
 
@@ -313,18 +315,97 @@ __device__ __forceinline__ void load_state(TriState<I>& S, const uint4* __restri
   S.e0 = static_cast<I>(S.s) * orient_i<I>(S.r1, S.c1, S.r2, S.c2, qr, qc);
   S.e1 = static_cast<I>(S.s) * orient_i<I>(S.r2, S.c2, S.r0, S.c0, qr, qc);
   S.e2 = S.area - S.e0 - S.e1;
-  S.v01 = q.x; S.v2 = q.y & 0xFFFFu;
   S.n0 = q.z & 0xFFFFu; S.n1 = q.z >> 16; S.n2 = q.w & 0xFFFFu;
 }
 
-// Each thread owns 4 consecutive pixels of one row: locate them (walk once, then step the edge functions in
-// registers), then stream all channels with 128-bit stores.
+constexpr int kLocThreads = 256;
+constexpr int kLocRun = FOVEA_HINT_CELL_W;           // pixels one thread walks along its row (= one hint cell)
+constexpr int kLocTileW = 8 * kLocRun, kLocTileH = 32;  // CTA tile: 2 warps across x 4 down; warp = 4 runs x 8 rows
+
+template <typename I>
+__global__ void __launch_bounds__(kLocThreads)
+locate_pixels_kernel(const int32_t* __restrict__ winner, const int32_t* __restrict__ pts, const uint4* __restrict__ mesh,
+                     const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints, int32_t* __restrict__ loc,
+                     int hw, int H, int W, int cap, int tcap) {
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * kLocTileW + ((warp & 1) * 4 + (lane & 3)) * kLocRun;
+  const int y = blockIdx.y * kLocTileH + (warp >> 1) * 8 + (lane >> 2);
+  if (x0 >= W || y >= H) return;
+  const int32_t* ptsb = pts + static_cast<size_t>(b) * cap;
+  const uint4* rec = mesh + static_cast<size_t>(b) * tcap;
+  const int T = ntri[b];
+  const size_t row = (static_cast<size_t>(b) * H + y) * W;
+  const int start = hints[(static_cast<size_t>(b) * ceil_div(H, FOVEA_HINT_CELL_H) + y / FOVEA_HINT_CELL_H) *
+                              ceil_div(W, FOVEA_HINT_CELL_W) + x0 / FOVEA_HINT_CELL_W];
+  const int none = -(hw + 1);
+  const int run = min(kLocRun, W - x0);  // W % 4 == 0 (checked on the host)
+
+  TriState<I> S;
+  bool have = false;
+  for (int q = 0; q < run; q += 4) {
+    const int4 win = *reinterpret_cast<const int4*>(winner + row + x0 + q);
+    const int wn[4] = {win.x, win.y, win.z, win.w};
+    int out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + q + k;
+      if (wn[k] >= 0) {
+        out[k] = -(wn[k] + 1);
+      } else {
+        bool ok = have && test_state<I>(S) < 0;
+        if (!ok && T > 0) {
+          int t = have ? S.t : ((start >= 0 && start < T) ? start : 0);
+          for (int step = 0; step < T + 8; ++step) {
+            load_state<I>(S, rec, ptsb, t, y, x);
+            if (S.area == 0) break;
+            const int nxt = test_state<I>(S);
+            if (nxt < 0) { ok = true; break; }
+            if (static_cast<unsigned>(nxt) == kNoTri) break;
+            t = nxt;
+          }
+          if (!ok) {  // degenerate triangle on the way (host meshes only) or outside the hull: exhaustive search
+            Mesh m{ptsb, rec, T};
+            const Located L = locate_bruteforce(m, y, x);
+            if (L.tri >= 0) { load_state<I>(S, rec, ptsb, L.tri, y, x); ok = true; }
+          }
+          have = ok;
+        }
+        out[k] = ok ? S.t : none;
+      }
+      if (have) {  // step the edge functions one pixel to the right: d e_i / d col = -s * (row_b - row_a)
+        S.e0 -= static_cast<I>(S.s * (S.r2 - S.r1));
+        S.e1 -= static_cast<I>(S.s * (S.r0 - S.r2));
+        S.e2 -= static_cast<I>(S.s * (S.r1 - S.r0));
+      }
+    }
+    *reinterpret_cast<int4*>(loc + row + x0 + q) = make_int4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ A8+A9+A10
+struct FillParams {
+  int C, Cs, h, w, H, W, cap, tcap, zero_residual;
+};
+
+constexpr int kFillThreads = 256;
+constexpr int kFillTileW = 128, kFillTileH = 8;  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
+
+// r = p ? *addr : r   as ONE predicated 128-bit load (no branch, no register copy)
+__device__ __forceinline__ void ldg_if(float4& r, unsigned long long addr, bool p) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)
+      : "l"(addr), "r"(static_cast<unsigned>(p)));
+}
+
+// Each thread owns 4 consecutive pixels of one row: resolve their table rows + barycentric weights from `loc`
+// (exact integer edge functions, stepped in registers while the triangle does not change), then stream all channels
+// with 128-bit stores.  Table rows are re-loaded only where they differ from the previous pixel's.
 template <typename I, bool kScores, bool kMask>
 __global__ void __launch_bounds__(kFillThreads, 3)
-inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
-                    const uint4* __restrict__ mesh, const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints,
-                    const float* __restrict__ table, float* __restrict__ scores, long long* __restrict__ mask,
-                    FillParams p) {
+inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
+                    const uint4* __restrict__ mesh, const float* __restrict__ table, float* __restrict__ scores,
+                    long long* __restrict__ mask, FillParams p) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
@@ -336,70 +417,49 @@ inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restric
   const int32_t* srcb = src + static_cast<size_t>(b) * p.cap;
   const int32_t* ptsb = pts + static_cast<size_t>(b) * p.cap;
   const uint4* rec = mesh + static_cast<size_t>(b) * p.tcap;
-  const int T = ntri[b];
 
-  const int4 win = *reinterpret_cast<const int4*>(winner + static_cast<size_t>(b) * plane + pixoff);
-  const int wn[4] = {win.x, win.y, win.z, win.w};
+  const int4 l4 = __ldcs(reinterpret_cast<const int4*>(loc + static_cast<size_t>(b) * plane + pixoff));
+  const int lc[4] = {l4.x, l4.y, l4.z, l4.w};
   unsigned ob0[4], ob1[4], ob2[4];  // byte offsets of the three table rows of each pixel
   float w0[4], w1[4], w2[4];        // barycentric weights ((1,0,0) for a pixel that received a node)
   unsigned nanmask = 0;             // pixels whose value is NaN in every channel
+  unsigned reload = 1;              // bit k: pixel k's table rows differ from pixel k-1's
 
-  TriState<I> S;
-  bool have = false;
-  int sn0 = hw, sn1 = hw, sn2 = hw;
+  int cur = -1, sn0 = hw, sn1 = hw, sn2 = hw;
+  I e0 = 0, e1 = 0, d0 = 0, d1 = 0;
   double inv_area = 0.0;
-  int start = 0;
-  if (wn[0] < 0 || wn[1] < 0 || wn[2] < 0 || wn[3] < 0) {
-    const int cw = ceil_div(p.W, FOVEA_HINT_CELL_W);
-    start = hints[(static_cast<size_t>(b) * ceil_div(p.H, FOVEA_HINT_CELL_H) + y / FOVEA_HINT_CELL_H) * cw +
-                  x0 / FOVEA_HINT_CELL_W];
-  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    int n0 = hw, n1 = hw, n2 = hw;
+    int n0, n1, n2;
     float a0 = 1.f, a1 = 0.f, a2 = 0.f;
-    if (wn[k] >= 0) {
-      n0 = n1 = n2 = wn[k];
+    if (lc[k] < 0) {
+      n0 = n1 = n2 = -(lc[k] + 1);
     } else {
-      bool ok = have && test_state<I>(S) < 0;
-      if (!ok && T > 0) {
-        int t = have ? S.t : ((start >= 0 && start < T) ? start : 0);
-        for (int step = 0; step < T + 8; ++step) {
-          load_state<I>(S, rec, ptsb, t, y, x0 + k);
-          if (S.area == 0) break;
-          const int nxt = test_state<I>(S);
-          if (nxt < 0) { ok = true; break; }
-          if (static_cast<unsigned>(nxt) == kNoTri) break;
-          t = nxt;
-        }
-        if (!ok) {  // degenerate triangle on the way (host meshes only) or outside the hull: exhaustive search
-          Mesh m{ptsb, rec, T};
-          const Located L = locate_bruteforce(m, y, x0 + k);
-          if (L.tri >= 0) { load_state<I>(S, rec, ptsb, L.tri, y, x0 + k); ok = true; }
-        }
-        have = ok;
-        if (ok) {
-          sn0 = __ldg(srcb + (S.v01 & 0xFFFFu));
-          sn1 = __ldg(srcb + (S.v01 >> 16));
-          sn2 = __ldg(srcb + S.v2);
-          inv_area = 1.0 / static_cast<double>(S.area);
-        }
+      if (lc[k] != cur) {
+        cur = lc[k];
+        const uint4 q = __ldg(rec + cur);
+        const unsigned i0 = q.x & 0xFFFFu, i1 = q.x >> 16, i2 = q.y & 0xFFFFu;
+        const int p0 = __ldg(ptsb + i0), p1 = __ldg(ptsb + i1), p2 = __ldg(ptsb + i2);
+        sn0 = __ldg(srcb + i0); sn1 = __ldg(srcb + i1); sn2 = __ldg(srcb + i2);
+        const int r0 = p0 >> 16, c0 = p0 & 0xFFFF, r1 = p1 >> 16, c1 = p1 & 0xFFFF, r2 = p2 >> 16, c2 = p2 & 0xFFFF;
+        const I A = orient_i<I>(r0, c0, r1, c1, r2, c2);
+        const I s = A < 0 ? -1 : 1;
+        e0 = s * orient_i<I>(r1, c1, r2, c2, y, x0 + k);
+        e1 = s * orient_i<I>(r2, c2, r0, c0, y, x0 + k);
+        d0 = s * static_cast<I>(r2 - r1);  // d e_i / d col = -s * (row_b - row_a)
+        d1 = s * static_cast<I>(r0 - r2);
+        inv_area = 1.0 / static_cast<double>(A < 0 ? -A : A);
       }
-      if (ok) {
-        // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 in float64, c2 = 1 - c0 - c1, then cast to float32
-        const double c0 = static_cast<double>(S.e0) * inv_area;
-        const double c1 = static_cast<double>(S.e1) * inv_area;
-        a0 = static_cast<float>(c0);
-        a1 = static_cast<float>(c1);
-        a2 = static_cast<float>(1.0 - c0 - c1);
-        n0 = sn0; n1 = sn1; n2 = sn2;
-      }
+      // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 in float64, c2 = 1 - c0 - c1, then cast to float32
+      const double c0 = static_cast<double>(e0) * inv_area;
+      const double c1 = static_cast<double>(e1) * inv_area;
+      a0 = static_cast<float>(c0);
+      a1 = static_cast<float>(c1);
+      a2 = static_cast<float>(1.0 - c0 - c1);
+      n0 = sn0; n1 = sn1; n2 = sn2;
     }
-    if (have) {  // step the edge functions one pixel to the right: d e_i / d col = -s * (row_b - row_a)
-      S.e0 -= static_cast<I>(S.s * (S.r2 - S.r1));
-      S.e1 -= static_cast<I>(S.s * (S.r0 - S.r2));
-      S.e2 -= static_cast<I>(S.s * (S.r1 - S.r0));
-    }
+    e0 -= d0;  // advance to column x0 + k + 1 (harmless while no triangle is held: d == 0)
+    e1 -= d1;
     if (n0 == hw || n1 == hw || n2 == hw) {  // a NaN vertex poisons every channel (NaN*w, even for w == 0)
       nanmask |= 1u << k;
       n0 = n1 = n2 = p.zero_residual ? hw + 1 : hw;  // models_instance.py:940: residual NaN -> 0
@@ -409,6 +469,7 @@ inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restric
     ob1[k] = static_cast<unsigned>(n1) * p.Cs * 4u;
     ob2[k] = static_cast<unsigned>(n2) * p.Cs * 4u;
     w0[k] = a0; w1[k] = a1; w2[k] = a2;
+    if (k > 0 && (ob0[k] != ob0[k - 1] || ob1[k] != ob1[k - 1] || ob2[k] != ob2[k - 1])) reload |= 1u << k;
   }
 
   // The channel loop adds the row offsets to one 64-bit base that advances by 16 B per 4-channel group.
@@ -423,12 +484,13 @@ inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restric
 
   for (int c = 0; c < p.Cs; c += 4, tbase += 16ull) {
     float v[4][4];  // [pixel][channel]
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rc = ra;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      // unconditional loads: neighbouring pixels usually share a triangle, so these are L1 broadcast hits
-      const float4 ra = __ldg(reinterpret_cast<const float4*>(tbase + ob0[k]));
-      const float4 rb = __ldg(reinterpret_cast<const float4*>(tbase + ob1[k]));
-      const float4 rc = __ldg(reinterpret_cast<const float4*>(tbase + ob2[k]));
+      const bool ld = (reload >> k) & 1u;
+      ldg_if(ra, tbase + ob0[k], ld);
+      ldg_if(rb, tbase + ob1[k], ld);
+      ldg_if(rc, tbase + ob2[k], ld);
       // interp2d.py:85-89: mul, then sum over the three vertices in order (separate roundings, no FMA)
       v[k][0] = __fadd_rn(__fadd_rn(__fmul_rn(ra.x, w0[k]), __fmul_rn(rb.x, w1[k])), __fmul_rn(rc.x, w2[k]));
       v[k][1] = __fadd_rn(__fadd_rn(__fmul_rn(ra.y, w0[k]), __fmul_rn(rb.y, w1[k])), __fmul_rn(rc.y, w2[k]));
@@ -460,6 +522,21 @@ inverse_fill_kernel(const int32_t* __restrict__ winner, const int32_t* __restric
     mp[0] = make_longlong2(besti[0], besti[1]);
     mp[1] = make_longlong2(besti[2], besti[3]);
   }
+}
+
+// Diagnostic: the store pattern of inverse_fill with no computation (same tiling, same 128-bit streaming stores,
+// one 4-pixel store per channel plane) -- the practical write-only ceiling the fill kernel is measured against.
+__global__ void __launch_bounds__(kFillThreads)
+store_ceiling_kernel(float* __restrict__ scores, int C, int H, int W) {
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
+  const int y = blockIdx.y * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
+  if (x0 >= W || y >= H) return;
+  const size_t plane = static_cast<size_t>(H) * W;
+  float* o = scores + static_cast<size_t>(b) * C * plane + static_cast<size_t>(y) * W + x0;
+  const float f = static_cast<float>(lane);
+  for (int c = 0; c < C; ++c, o += plane) __stcs(reinterpret_cast<float4*>(o), make_float4(f, f + 1.f, f + 2.f, f + 3.f));
 }
 
 // torch.argmax(scores, dim=1) as a stand-alone streaming pass
@@ -568,26 +645,43 @@ extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const
   return check_launch("fovea_locate_hints");
 }
 
+extern "C" int fovea_locate_pixels(const int32_t* winner, const int32_t* pts, const int32_t* npts,
+                                   const uint16_t* mesh, const int32_t* ntri, const int32_t* hints, int B, int h,
+                                   int w, int H, int W, int cap, int tcap, int32_t* loc, fovea_stream_t stream) {
+  (void)npts;
+  FOVEA_REQUIRE(winner && pts && mesh && ntri && hints && loc, "fovea_locate_pixels: null pointer");
+  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1, "fovea_locate_pixels: bad sizes");
+  FOVEA_REQUIRE(W % 4 == 0, "fovea_locate_pixels: W=%d must be a multiple of 4 (128-bit accesses)", W);
+  FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kLocTileH) <= 65535, "fovea_locate_pixels: B or H too large for the grid");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
+  dim3 grid(ceil_div(W, kLocTileW), ceil_div(H, kLocTileH), B);
+  // coordinates < 16384 keep every orientation determinant inside int32 (|diff| < 2^14, products < 2^28)
+  if (H <= 16384 && W <= 16384)
+    locate_pixels_kernel<int><<<grid, kLocThreads, 0, s>>>(winner, pts, m4, ntri, hints, loc, h * w, H, W, cap, tcap);
+  else
+    locate_pixels_kernel<long long><<<grid, kLocThreads, 0, s>>>(winner, pts, m4, ntri, hints, loc, h * w, H, W, cap,
+                                                                 tcap);
+  return check_launch("fovea_locate_pixels");
+}
+
 template <typename I>
-static int launch_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const uint4* m4,
-                       const int32_t* ntri, const int32_t* hints, const float* table, float* scores, long long* mk,
-                       const FillParams& p, int B, cudaStream_t s) {
+static int launch_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint4* m4, const float* table,
+                       float* scores, long long* mk, const FillParams& p, int B, cudaStream_t s) {
   dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH), B);
   if (scores && mk)
-    inverse_fill_kernel<I, true, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
+    inverse_fill_kernel<I, true, true><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   else if (scores)
-    inverse_fill_kernel<I, true, false><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
+    inverse_fill_kernel<I, true, false><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   else
-    inverse_fill_kernel<I, false, true><<<grid, kFillThreads, 0, s>>>(winner, pts, src, m4, ntri, hints, table, scores, mk, p);
+    inverse_fill_kernel<I, false, true><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   return check_launch("fovea_inverse_fill");
 }
 
-extern "C" int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
-                                  const uint16_t* mesh, const int32_t* ntri, const int32_t* hints, const float* table,
-                                  int B, int C, int Cs, int h, int w, int H, int W, int cap, int tcap,
-                                  int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream) {
-  (void)npts;
-  FOVEA_REQUIRE(winner && pts && src && mesh && ntri && hints && table, "fovea_inverse_fill: null pointer");
+extern "C" int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint16_t* mesh,
+                                  const float* table, int B, int C, int Cs, int h, int w, int H, int W, int cap,
+                                  int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream) {
+  FOVEA_REQUIRE(loc && pts && src && mesh && table, "fovea_inverse_fill: null pointer");
   FOVEA_REQUIRE(scores || mask, "fovea_inverse_fill: neither scores nor mask requested");
   FOVEA_REQUIRE(B > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && h > 0 && w > 0 && H > 1 && W > 1,
                 "fovea_inverse_fill: bad sizes");
@@ -599,9 +693,16 @@ extern "C" int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
   long long* mk = reinterpret_cast<long long*>(mask);
-  // coordinates < 16384 keep every orientation determinant inside int32 (|diff| < 2^14, products < 2^28)
-  if (H <= 16384 && W <= 16384) return launch_fill<int>(winner, pts, src, m4, ntri, hints, table, scores, mk, p, B, s);
-  return launch_fill<long long>(winner, pts, src, m4, ntri, hints, table, scores, mk, p, B, s);
+  if (H <= 16384 && W <= 16384) return launch_fill<int>(loc, pts, src, m4, table, scores, mk, p, B, s);
+  return launch_fill<long long>(loc, pts, src, m4, table, scores, mk, p, B, s);
+}
+
+extern "C" int fovea_probe_store_ceiling(float* scores, int B, int C, int H, int W, fovea_stream_t stream) {
+  FOVEA_REQUIRE(scores && B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "fovea_probe_store_ceiling: bad arguments");
+  FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_probe_store_ceiling: B or H too large");
+  dim3 grid(ceil_div(W, kFillTileW), ceil_div(H, kFillTileH), B);
+  store_ceiling_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(scores, C, H, W);
+  return check_launch("fovea_probe_store_ceiling");
 }
 
 extern "C" int fovea_argmax_classes(const float* scores, int B, int C, int64_t HW, int64_t* mask,

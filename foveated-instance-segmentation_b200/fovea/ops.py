@@ -193,7 +193,8 @@ class InversePlan:
     npts: torch.Tensor     # [B] int32
     mesh: torch.Tensor     # [B,tcap,8] uint16: (v0,v1,v2,0,n0,n1,n2,0) per triangle
     ntri: torch.Tensor     # [B] int32
-    hints: torch.Tensor    # [B,ceil(H/32),ceil(W/32)] int32
+    hints: torch.Tensor    # [B,ceil(H/8),ceil(W/32)] int32 walk-start triangles
+    loc: torch.Tensor      # [B,H,W] int32 per-pixel source: triangle id, or -(node+1)
     h: int
     w: int
     H: int
@@ -262,7 +263,8 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
     hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
-    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, h, w, H, W, cap, tcap, triangulation)
+    loc = _locate(winner, pts, npts, mesh, ntri, hints, h, w, cap, tcap)
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, loc, h, w, H, W, cap, tcap, triangulation)
 
 
 def delaunay_device(pts, npts, cap, tcap, max_coord):
@@ -291,6 +293,17 @@ def _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W):
     return hints
 
 
+def _locate(winner, pts, npts, mesh, ntri, hints, h, w, cap, tcap):
+    """interp2d.py:58 (find_simplex for every pixel) merged with the A7 winners: the per-pixel source map `loc`."""
+    B, H, W = winner.shape
+    if W % 4:
+        raise FoveaError(f"canvas width {W} must be a multiple of 4 (128-bit accesses)")
+    loc = torch.empty_like(winner)
+    _lib.call("fovea_locate_pixels", _ptr(winner), _ptr(pts), _ptr(npts), _ptr(mesh), _ptr(ntri), _ptr(hints), B, h, w,
+              H, W, cap, tcap, _ptr(loc), _stream())
+    return loc
+
+
 def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
     """Plan for interpolating EVERY pixel of an H x W canvas from an arbitrary site set (Interp2D, interp2d.py:37-91):
     no pixel carries a node (winner = -1 everywhere); `table_rows` is the index of the NaN row of the value table."""
@@ -298,17 +311,21 @@ def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
     tcap = mesh.shape[1]
     winner = torch.full((B, H, W), -1, device=pts.device, dtype=torch.int32)
     hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
-    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, table_rows, 1, H, W, cap, tcap, "given")
+    loc = _locate(winner, pts, npts, mesh, ntri, hints, table_rows, 1, cap, tcap)
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, loc, table_rows, 1, H, W, cap, tcap, "given")
 
 
 def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=None, mask=None):
     """fovea_inverse_fill on a caller-built value table [B, plan.h*plan.w + 2, Cs]."""
     B = plan.winner.shape[0]
-    _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
-              _ptr(plan.mesh), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), B, int(C), table.shape[2], plan.h,
-              plan.w, plan.H, plan.W, plan.cap, plan.tcap, 1 if zero_residual else 0, _ptr(scores), _ptr(mask),
-              _stream())
+    _fill(plan, table, int(C), zero_residual, scores, mask)
     return scores, mask
+
+
+def _fill(plan, table, C, zero_residual, scores, mask):
+    _lib.call("fovea_inverse_fill", _ptr(plan.loc), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.mesh), _ptr(table),
+              plan.loc.shape[0], C, table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.cap, plan.tcap,
+              1 if zero_residual else 0, _ptr(scores), _ptr(mask), _stream())
 
 
 def box4_table(pred, Cs=None):
@@ -329,7 +346,6 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
     if (h, w) != (plan.h, plan.w) or B != plan.winner.shape[0]:
         raise FoveaError(f"inverse_fill: pred {tuple(p.shape)} does not match the plan ({B}x{plan.h}x{plan.w})")
     table = box4_table(p)
-    Cs = table.shape[2]
     scores = None
     if want_scores:
         scores = out if out is not None else torch.empty(B, Cc, plan.H, plan.W, device=p.device, dtype=torch.float32)
@@ -337,10 +353,15 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
     mask = None
     if want_mask:
         mask = mask_out if mask_out is not None else torch.empty(B, plan.H, plan.W, device=p.device, dtype=torch.int64)
-    _lib.call("fovea_inverse_fill", _ptr(plan.winner), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.npts),
-              _ptr(plan.mesh), _ptr(plan.ntri), _ptr(plan.hints), _ptr(table), B, Cc, Cs, h, w,
-              plan.H, plan.W, plan.cap, plan.tcap, 1 if zero_residual else 0, _ptr(scores), _ptr(mask), _stream())
+    _fill(plan, table, Cc, zero_residual, scores, mask)
     return scores, mask
+
+
+def probe_store_ceiling(scores):
+    """Diagnostic: overwrite `scores` [B,C,H,W] with the store pattern of fovea_inverse_fill and no computation."""
+    s = _req(scores, torch.float32, "scores", 4)
+    B, Cc, H, W = s.shape
+    _lib.call("fovea_probe_store_ceiling", _ptr(s), B, Cc, H, W, _stream())
 
 
 def argmax_classes(scores):

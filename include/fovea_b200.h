@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 1
+#define FOVEA_ABI_VERSION 2
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -149,8 +149,8 @@ int64_t fovea_delaunay_workspace_bytes(int B, int cap);
 int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
                    uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream);
 
-/* Walk-start hints for fovea_inverse_fill: hints[b, cy, cx] = the triangle containing the centre of the
- * FOVEA_HINT_CELL_W x FOVEA_HINT_CELL_H pixel cell (one warp tile of the fill kernel is 32 x 4 pixels).
+/* Walk-start hints for fovea_locate_pixels: hints[b, cy, cx] = the triangle containing the centre of the
+ * FOVEA_HINT_CELL_W x FOVEA_HINT_CELL_H pixel cell (one thread of the locate kernel walks one cell-wide row run).
  * hints [B, ceil(H/FOVEA_HINT_CELL_H), ceil(W/FOVEA_HINT_CELL_W)] int32
  * workspace: fovea_locate_hints_workspace_bytes(B, H, W) bytes of device memory */
 #define FOVEA_HINT_CELL_W 32
@@ -159,18 +159,35 @@ int64_t fovea_locate_hints_workspace_bytes(int B, int H, int W);
 int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* mesh, const int32_t* ntri, int B,
                        int cap, int tcap, int H, int W, int32_t* hints, void* workspace, fovea_stream_t stream);
 
+/* A9 point location, interp2d.py:58 (Delaunay.find_simplex over every pixel, spatial/qhull.pyx:2075-2163), merged
+ * with the A7 winners into one per-pixel source map -- a function of the sampling grid only (not of the scores):
+ *   loc[b,y,x] >= 0      id of the mesh triangle that owns pixel (y,x).  A pixel exactly on an edge belongs to
+ *                        the triangle a top-left fill rule picks (csrc/mesh.cuh), so the map does not depend on
+ *                        walk order;
+ *   loc[b,y,x] = -(n+1)  the pixel received low-res node n directly (winner[b,y,x] = n);  n = h*w: the pixel has no
+ *                        value (outside the triangulation / empty mesh) and reads the NaN row of the value table.
+ *   winner [B,H,W] int32 from fovea_grid_inv_scatter (all -1 = interpolate every pixel, Interp2D);  hints from
+ *   fovea_locate_hints;  loc [B,H,W] int32 (may alias winner);  W % 4 == 0. */
+int fovea_locate_pixels(const int32_t* winner, const int32_t* pts, const int32_t* npts, const uint16_t* mesh,
+                        const int32_t* ntri, const int32_t* hints, int B, int h, int w, int H, int W, int cap,
+                        int tcap, int32_t* loc, fovea_stream_t stream);
+
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
- * fillMissingValues_tensor(..., 'tri') = Interp2D point location + barycentric gather
- * (models/models.py:939-940, interp2d.py:58-91), residual NaN -> 0 (models_instance.py:940) and
- * torch.argmax over classes (models/models.py:1044), in one pass over the full-resolution canvas.
+ * fillMissingValues_tensor(..., 'tri') = Interp2D barycentric gather (models/models.py:939-940,
+ * interp2d.py:65-91), residual NaN -> 0 (models_instance.py:940) and torch.argmax over classes
+ * (models/models.py:1044), in ONE pass over the full-resolution canvas: the score tensor is written exactly once.
+ *   loc    [B,H,W] from fovea_locate_pixels
  *   table  [B, h*w+2, Cs] from fovea_box4_table
  *   scores [B,C,H,W] fp32   (NULL = do not materialise)
  *   mask   [B,H,W]  int64   (NULL = do not compute)
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
-int fovea_inverse_fill(const int32_t* winner, const int32_t* pts, const int32_t* src, const int32_t* npts,
-                       const uint16_t* mesh, const int32_t* ntri, const int32_t* hints, const float* table, int B,
-                       int C, int Cs, int h, int w, int H, int W, int cap, int tcap, int zero_residual,
-                       float* scores, int64_t* mask, fovea_stream_t stream);
+int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint16_t* mesh,
+                       const float* table, int B, int C, int Cs, int h, int w, int H, int W, int cap, int tcap,
+                       int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
+
+/* Diagnostic (bench.py): the store pattern of fovea_inverse_fill with no computation -- same tiling, one 128-bit
+ * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout. */
+int fovea_probe_store_ceiling(float* scores, int B, int C, int H, int W, fovea_stream_t stream);
 
 /* torch.argmax(scores, dim=1) as a stand-alone pass (models/models.py:1044): first maximum wins, NaN is
  * treated as the maximum (torch semantics).  scores [B,C,H,W] -> mask [B,H,W] int64 */
