@@ -167,7 +167,7 @@ int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* 
  *   loc[b,y,x] = -(n+1)  the pixel received low-res node n directly (winner[b,y,x] = n);  n = h*w: the pixel has no
  *                        value (outside the triangulation / empty mesh) and reads the NaN row of the value table.
  *   winner [B,H,W] int32 from fovea_grid_inv_scatter (all -1 = interpolate every pixel, Interp2D);  hints from
- *   fovea_locate_hints;  loc [B,H,W] int32 (may alias winner);  W % 4 == 0. */
+ *   fovea_locate_hints;  loc [B,H,W] int32 (a separate buffer: must not alias winner);  W % 4 == 0. */
 int fovea_locate_pixels(const int32_t* winner, const int32_t* pts, const int32_t* npts, const uint16_t* mesh,
                         const int32_t* ntri, const int32_t* hints, int B, int h, int w, int H, int W, int cap,
                         int tcap, int32_t* loc, fovea_stream_t stream);
