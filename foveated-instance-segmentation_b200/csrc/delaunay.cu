@@ -295,6 +295,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   // ------------------------------------------------------------------ 3. pockets (left, then right)
   // cprev[m]: bits 0..12 = previous alive chain vertex (kCNone = chain start), bit 13 DEAD, bit 14 SELECTED, bit 15 EAR
   constexpr unsigned kCIdx = 0x1FFFu, kCNone = 0x1FFFu, kCDead = 0x2000u, kCSel = 0x4000u, kCEar = 0x8000u;
+  int ntri_run = nstrip_tris;  // triangles so far (identical in every thread)
   for (int side = 0; side < 2; ++side) {
     auto cpt = [&](int m) { return side == 0 ? static_cast<int>(A.rowStart[m]) : static_cast<int>(A.rowStart[m + 1]) - 1; };
     auto cpri = [&](int m, int round) {
@@ -336,12 +337,22 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
         A.cprev[m] = static_cast<unsigned short>(cp | kCSel);
       }
       if (!__syncthreads_or(selected_any)) break;
-      // phase 2b: clip the selected ears (their neighbours are not selected, so the list surgery is race-free)
+      // phase 2b: clip the selected ears (their neighbours are not selected, so the list surgery is race-free).
+      // Triangle ids come from a block scan over the selected ears, not from an atomic counter: the numbering -- and
+      // with it the flip priorities and the final choice among co-circular alternatives -- is the same on every run.
+      int mysel = 0;
+      for (int m = tid; m < R; m += kDtThreads) {
+        const unsigned cp = A.cprev[m];
+        if (!(cp & kCDead) && (cp & kCSel)) ++mysel;
+      }
+      int nsel;
+      int E_next = ntri_run + block_scan_excl(mysel, warp_sums, nsel);
+      ntri_run += nsel;
       for (int m = tid; m < R; m += kDtThreads) {
         const unsigned cp = A.cprev[m];
         if ((cp & kCDead) || !(cp & kCSel)) continue;
         const int pv = cp & kCIdx, nx = A.cnext[m];
-        const int E = atomicAdd(&s_ntri, 1);
+        const int E = E_next++;
         const int P = cpt(pv), M = cpt(m), N = cpt(nx);
         // left : (P,M,N) is ccw: edge(P,M) opposite v2, edge(M,N) opposite v0, edge(N,P) opposite v1
         // right: (P,N,M) is ccw: edge(P,M) opposite v1, edge(M,N) opposite v0, edge(P,N) opposite v2
@@ -372,7 +383,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     }
     __syncthreads();
   }
-  const int T = s_ntri;
+  const int T = ntri_run;
   if (dbg && tid == 0) { dbg[b * 8 + 0] = 3; dbg[b * 8 + 6] = T; }
   __syncthreads();
 

@@ -129,16 +129,26 @@ def grid_resize(grid, out_size):
 
 # ------------------------------------------------------------------------------------------------ stage 2
 
+def _req_gather_source(t, name):
+    """The image a gather kernel reads: a CUDA tensor, or a PINNED host tensor (unified virtual addressing makes its
+    data_ptr dereferenceable on the device: the kernel then pulls only the 32-byte sectors it touches over PCIe)."""
+    if isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned():
+        if t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous():
+            raise FoveaError(f"{name}: a pinned host source must be a contiguous 4-D float32 tensor")
+        return t
+    return _req(t, torch.float32, name, 4)
+
+
 class _GridSampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, grid):
-        x = _req(inp, torch.float32, "input", 4)
+        x = _req_gather_source(inp, "input")
         g = _req(grid, torch.float32, "grid", 4)
         B, Cc, H, W = x.shape
         if g.shape[0] != B or g.shape[3] != 2:
             raise FoveaError(f"grid_sample: grid {tuple(g.shape)} does not match input {tuple(x.shape)}")
         h, w = g.shape[1], g.shape[2]
-        out = torch.empty(B, Cc, h, w, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, Cc, h, w, device=g.device, dtype=torch.float32)
         _lib.call("fovea_grid_sample_fwd", _ptr(x), _ptr(g), B, Cc, H, W, h, w, _ptr(out), _stream())
         ctx.save_for_backward(x, g)
         return out
@@ -150,6 +160,8 @@ class _GridSampleFn(torch.autograd.Function):
         h, w = g.shape[1], g.shape[2]
         go = _req(grad_out, torch.float32, "grad_out")
         need_in, need_grid = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_in and not x.is_cuda:
+            raise FoveaError("grid_sample backward: a pinned host source cannot receive a gradient")
         gi = torch.zeros_like(x) if need_in else None
         gg = torch.empty_like(g) if need_grid else None
         if need_in or need_grid:

@@ -167,3 +167,16 @@ def test_device_triangulation_scores_agree_with_host_qhull(ops, H, W):
     win = plan_d.winner.long()
     b, ys, xs_ = torch.where(win >= 0)
     assert torch.equal(sd[b, :, ys, xs_], sh[b, :, ys, xs_])
+
+
+def test_device_delaunay_is_deterministic(ops):
+    """Same points -> bit-identical mesh on every run (triangle ids come from scans, priorities from hashes of ids)."""
+    grid = _plan_points(ops, 1024, 1024, seed=7, B=3)
+    plans = [ops.build_inverse_plan(grid.cuda(), (1024, 1024), nchan=51, triangulation="device") for _ in range(3)]
+    torch.cuda.synchronize()
+    for p in plans[1:]:
+        assert torch.equal(p.ntri, plans[0].ntri)
+        for b in range(3):
+            T = int(p.ntri[b])
+            assert torch.equal(p.mesh[b, :T].view(torch.int16), plans[0].mesh[b, :T].view(torch.int16))
+        assert torch.equal(p.loc, plans[0].loc)

@@ -161,3 +161,35 @@ def test_fill_missing_values_and_interp2d_api(golden_dir):
     close = torch.isclose(got, want, rtol=0, atol=1e-5, equal_nan=True).float().mean().item()
     assert same_nan > 0.999 and close > 0.999, (same_nan, close)
     assert torch.equal(torch.isnan(t), torch.from_numpy(np.isnan(gi["pred_sampled_nan"][0])).cuda())  # copy=True
+
+
+def test_resample_pipeline_matches_direct_path():
+    """fovea.pipeline.ResamplePipeline (3 streams x 2 slots, host buffers) gives the same masks as the direct ops path,
+    for both image-ingest modes (bulk H2D copy / on-demand PCIe gather from the pinned host image)."""
+    from fovea import ops
+    from fovea.pipeline import ResamplePipeline
+    from oracle import reference_port as rp
+    B, C, H, W, g, R = 3, 7, 256, 320, 80, 45
+    batches = []
+    for seed in range(4):
+        xs, _ = rp.synthetic_saliency(B, seed=seed)
+        pred = rp.synthetic_pred(B, C, seed=seed)
+        x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(seed))
+        batches.append((x.pin_memory(), xs.pin_memory(), pred.pin_memory()))
+    g1x, g1y = (t.cuda() for t in ops.separable_factors(rp.gaussian_filter_weight(R, R, R)))
+    want = []
+    for x, xs, pred in batches:
+        grid = ops.saliency_to_grid(xs.cuda(), g1x, g1y, g, g, R, R, "replication", (g, g))
+        plan = ops.build_inverse_plan(grid, (H, W), nchan=C, triangulation="device")
+        _, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=False, want_mask=True)
+        want.append((ops.grid_sample(x.cuda(), grid).cpu(), mask.cpu()))
+    for on_host in (False, True):
+        pipe = ResamplePipeline(B, C, H, W, g, R, torch.device("cuda", 0), "device", depth=2, image_on_host=on_host)
+        outs = [torch.empty(B, H, W, dtype=torch.int64).pin_memory() for _ in batches]
+        sampled = [pipe.submit(*bt, out) for bt, out in zip(batches, outs)]
+        pipe.drain()
+        for (xs_want, mask_want), got, xs_got in zip(want, outs, sampled):
+            assert torch.equal(xs_got.cpu(), xs_want), f"x_sampled differs (image_on_host={on_host})"
+            assert torch.equal(got, mask_want), f"{int((got != mask_want).sum())} mask pixels differ (image_on_host={on_host})"
+    with pytest.raises(Exception):
+        pipe.submit(batches[0][0].clone(), batches[0][1], batches[0][2], outs[0])   # unpinned image is refused
