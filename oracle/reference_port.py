@@ -9,9 +9,12 @@ Parity status: the reference ships no tests or golden vectors for this path (SUR
 oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF: `tests/golden/make_golden.py` imports the
 unmodified `/root/reference/models/models.py` + `interp2d.py` through `tests/golden/ref_shim.py` and stores
 their outputs on seeded inputs in `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks every function
-below against them.  One caveat stays "parity unpinned": the reference's vendored Qhull fork
-(`spatial/qhull_src`, 2019.1) cannot be built here, so Delaunay tie-breaking among co-circular lattice
-points is pinned against stock SciPy's Qhull (same options, `spatial/qhull.pyx:1874-1883`), not the fork.
+below against them.  The Delaunay triangulation (`delaunay()` below, stock SciPy Qhull) is additionally pinned
+against the reference's OWN vendored Qhull 2019.1, compiled from `/root/reference/spatial/qhull_src` into
+`oracle/_ref/libqhull_ref.so` (oracle/Makefile, oracle/qhull_ref.py): identical simplices, orientation, order
+and neighbours on every point set of the path (`tests/test_oracle_qhull_ref.py`).  What stays unpinned: the
+fork's Cython `find_simplex(return_c=True)` (`spatial/qhull.pyx:2075-2163`) cannot be built; stock SciPy's
+`find_simplex` + `transform` stand in for it (same algorithm and eps).
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """
