@@ -306,6 +306,11 @@ def main():
             ceil_ms.append(a.elapsed_time(b2))
     store_ceiling = 4.0 * C * H * W * B / (min(ceil_ms) * 1e-3) / 1e9
 
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 4.0 * C * H * W * B
@@ -321,7 +326,7 @@ def main():
             else (KERNELS_PER_STEP - 1) * args.steps,
             "clocks": clocks.summary(),
             "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": fill_ms,
                          "store_only_ceiling_gbs": store_ceiling},
         }
