@@ -5,6 +5,7 @@
 // models/models.py:1044 (argmax).  The reference materialises grid_inv [B,H,W,2], the sampled scores, a NaN
 // mask, a [3,H*W,C] gather and the final scores; here the full-resolution tensor is written exactly once.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "mesh.cuh"
@@ -462,18 +463,49 @@ struct FillParams {
 constexpr int kFillThreads = 256;
 constexpr int kFillTileW = 128, kFillTileH = 8;  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
 
-// r = p ? *addr : r   as ONE predicated 128-bit load (no branch, no register copy)
-__device__ __forceinline__ void ldg_if(float4& r, unsigned long long addr, bool p) {
-  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
-      : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)
-      : "l"(addr), "r"(static_cast<unsigned>(p)));
+// The table rows of the three vertices of one pixel, G channels each.
+template <int G>
+struct Rows {
+  float a[G], b[G], c[G];
+};
+
+// r = p ? (rows at pa, pb, pc) : unchanged -- three predicated loads under ONE predicate (no branch, no register
+// copies): the rows of a pixel are re-read only if they differ from its left neighbour's.  G = 4: 128-bit loads;
+// G = 8: the 256-bit loads of sm_100 (LDG.E.256), which halve the number of L1 requests per output byte.
+template <int G>
+__device__ __forceinline__ void ldg3_if(Rows<G>& r, unsigned long long pa, unsigned long long pb, unsigned long long pc,
+                                        unsigned p);
+
+template <>
+__device__ __forceinline__ void ldg3_if<4>(Rows<4>& r, unsigned long long pa, unsigned long long pb,
+                                           unsigned long long pc, unsigned p) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %15, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%12];\n\t"
+      "@q ld.global.nc.v4.f32 {%4,%5,%6,%7}, [%13];\n\t"
+      "@q ld.global.nc.v4.f32 {%8,%9,%10,%11}, [%14];\n\t}"
+      : "+f"(r.a[0]), "+f"(r.a[1]), "+f"(r.a[2]), "+f"(r.a[3]), "+f"(r.b[0]), "+f"(r.b[1]), "+f"(r.b[2]), "+f"(r.b[3]),
+        "+f"(r.c[0]), "+f"(r.c[1]), "+f"(r.c[2]), "+f"(r.c[3])
+      : "l"(pa), "l"(pb), "l"(pc), "r"(p));
+}
+
+template <>
+__device__ __forceinline__ void ldg3_if<8>(Rows<8>& r, unsigned long long pa, unsigned long long pb,
+                                           unsigned long long pc, unsigned p) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %27, 0;\n\t"
+      "@q ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+      "@q ld.global.nc.v8.f32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+      "@q ld.global.nc.v8.f32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t}"
+      : "+f"(r.a[0]), "+f"(r.a[1]), "+f"(r.a[2]), "+f"(r.a[3]), "+f"(r.a[4]), "+f"(r.a[5]), "+f"(r.a[6]), "+f"(r.a[7]),
+        "+f"(r.b[0]), "+f"(r.b[1]), "+f"(r.b[2]), "+f"(r.b[3]), "+f"(r.b[4]), "+f"(r.b[5]), "+f"(r.b[6]), "+f"(r.b[7]),
+        "+f"(r.c[0]), "+f"(r.c[1]), "+f"(r.c[2]), "+f"(r.c[3]), "+f"(r.c[4]), "+f"(r.c[5]), "+f"(r.c[6]), "+f"(r.c[7])
+      : "l"(pa), "l"(pb), "l"(pc), "r"(p));
 }
 
 // Each thread owns 4 consecutive pixels of one row: resolve their table rows + barycentric weights from `loc`
 // (exact integer edge functions, stepped in registers while the triangle does not change), then stream all channels
 // with 128-bit stores.  Table rows are re-loaded only where they differ from the previous pixel's.
-template <typename I, bool kScores, bool kMask>
-__global__ void __launch_bounds__(kFillThreads, 3)
+template <typename I, bool kScores, bool kMask, int G>
+__global__ void __launch_bounds__(kFillThreads, G == 8 ? 2 : 4)
 inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
                     const uint4* __restrict__ mesh, const float* __restrict__ table, float* __restrict__ scores,
                     long long* __restrict__ mask, FillParams p) {
@@ -491,10 +523,10 @@ inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__
 
   const int4 l4 = __ldcs(reinterpret_cast<const int4*>(loc + static_cast<size_t>(b) * plane + pixoff));
   const int lc[4] = {l4.x, l4.y, l4.z, l4.w};
-  unsigned ob0[4], ob1[4], ob2[4];  // byte offsets of the three table rows of each pixel
+  unsigned nd0[4], nd1[4], nd2[4];  // table rows (node ids) of the three vertices of each pixel
   float w0[4], w1[4], w2[4];        // barycentric weights ((1,0,0) for a pixel that received a node)
   unsigned nanmask = 0;             // pixels whose value is NaN in every channel
-  unsigned reload = 1;              // bit k: pixel k's table rows differ from pixel k-1's
+  unsigned reload[4] = {1u, 0u, 0u, 0u};  // pixel k's table rows differ from pixel k-1's
 
   int cur = -1, sn0 = hw, sn1 = hw, sn2 = hw;
   I e0 = 0, e1 = 0, d0 = 0, d1 = 0;
@@ -536,14 +568,16 @@ inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__
       n0 = n1 = n2 = p.zero_residual ? hw + 1 : hw;  // models_instance.py:940: residual NaN -> 0
       a0 = 1.f; a1 = 0.f; a2 = 0.f;
     }
-    ob0[k] = static_cast<unsigned>(n0) * p.Cs * 4u;
-    ob1[k] = static_cast<unsigned>(n1) * p.Cs * 4u;
-    ob2[k] = static_cast<unsigned>(n2) * p.Cs * 4u;
+    nd0[k] = static_cast<unsigned>(n0);
+    nd1[k] = static_cast<unsigned>(n1);
+    nd2[k] = static_cast<unsigned>(n2);
     w0[k] = a0; w1[k] = a1; w2[k] = a2;
-    if (k > 0 && (ob0[k] != ob0[k - 1] || ob1[k] != ob1[k - 1] || ob2[k] != ob2[k - 1])) reload |= 1u << k;
+    if (k > 0) reload[k] = (nd0[k] != nd0[k - 1]) | (nd1[k] != nd1[k - 1]) | (nd2[k] != nd2[k - 1]);
   }
 
-  // The channel loop adds the row offsets to one 64-bit base that advances by 16 B per 4-channel group.
+  // The channel loop forms each row address as base + node * row_bytes (one IMAD.WIDE); the base advances by 4*G bytes
+  // per G-channel group.
+  const unsigned row_bytes = static_cast<unsigned>(p.Cs) * 4u;
   unsigned long long tbase = reinterpret_cast<unsigned long long>(table + static_cast<size_t>(b) * (hw + 2) * p.Cs);
   unsigned long long obase = reinterpret_cast<unsigned long long>(
       kScores ? scores + static_cast<size_t>(b) * p.C * plane + pixoff : nullptr);
@@ -553,23 +587,24 @@ inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int besti[4] = {0, 0, 0, 0};
 
-  for (int c = 0; c < p.Cs; c += 4, tbase += 16ull) {
-    float v[4][4];  // [pixel][channel]
-    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rc = ra;
+
+  for (int c = 0; c < p.Cs; c += G, tbase += 4ull * G) {
+    float v[4][G];  // [pixel][channel]
+    Rows<G> r;
+#pragma unroll
+    for (int e = 0; e < G; ++e) r.a[e] = r.b[e] = r.c[e] = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const bool ld = (reload >> k) & 1u;
-      ldg_if(ra, tbase + ob0[k], ld);
-      ldg_if(rb, tbase + ob1[k], ld);
-      ldg_if(rc, tbase + ob2[k], ld);
+      ldg3_if<G>(r, tbase + static_cast<unsigned long long>(nd0[k]) * row_bytes,
+                 tbase + static_cast<unsigned long long>(nd1[k]) * row_bytes,
+                 tbase + static_cast<unsigned long long>(nd2[k]) * row_bytes, reload[k]);
       // interp2d.py:85-89: mul, then sum over the three vertices in order (separate roundings, no FMA)
-      v[k][0] = __fadd_rn(__fadd_rn(__fmul_rn(ra.x, w0[k]), __fmul_rn(rb.x, w1[k])), __fmul_rn(rc.x, w2[k]));
-      v[k][1] = __fadd_rn(__fadd_rn(__fmul_rn(ra.y, w0[k]), __fmul_rn(rb.y, w1[k])), __fmul_rn(rc.y, w2[k]));
-      v[k][2] = __fadd_rn(__fadd_rn(__fmul_rn(ra.z, w0[k]), __fmul_rn(rb.z, w1[k])), __fmul_rn(rc.z, w2[k]));
-      v[k][3] = __fadd_rn(__fadd_rn(__fmul_rn(ra.w, w0[k]), __fmul_rn(rb.w, w1[k])), __fmul_rn(rc.w, w2[k]));
+#pragma unroll
+      for (int e = 0; e < G; ++e)
+        v[k][e] = __fadd_rn(__fadd_rn(__fmul_rn(r.a[e], w0[k]), __fmul_rn(r.b[e], w1[k])), __fmul_rn(r.c[e], w2[k]));
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < G; ++e) {
       if (c + e < p.C) {
         if (kScores) {
           __stcs(reinterpret_cast<float4*>(obase), make_float4(v[0][e], v[1][e], v[2][e], v[3][e]));
@@ -736,16 +771,24 @@ extern "C" int fovea_locate_pixels(const int32_t* winner, const int32_t* pts, co
   return check_launch("fovea_locate_pixels");
 }
 
-template <typename I>
+// Measured on B200 (64 frames of 1024^2, C = 51): G = 4 (128-bit loads, 64 registers, 4 CTAs/SM) 2.58 ms;
+// G = 8 (256-bit loads, 128 registers, 2 CTAs/SM) 2.82 ms -- half the L1 requests, but too few warps to hide the
+// L2 round trip of every newly touched 32-byte table sector.  FOVEA_FILL_G=8 selects the wide path for A/B runs.
+static bool fill_wide_requested() {
+  static const bool v = [] { const char* e = getenv("FOVEA_FILL_G"); return e && e[0] == '8'; }();
+  return v;
+}
+
+template <typename I, int G>
 static int launch_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint4* m4, const float* table,
                        float* scores, long long* mk, const FillParams& p, int B, cudaStream_t s) {
   dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH), B);
   if (scores && mk)
-    inverse_fill_kernel<I, true, true><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
+    inverse_fill_kernel<I, true, true, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   else if (scores)
-    inverse_fill_kernel<I, true, false><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
+    inverse_fill_kernel<I, true, false, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   else
-    inverse_fill_kernel<I, false, true><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
+    inverse_fill_kernel<I, false, true, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   return check_launch("fovea_inverse_fill");
 }
 
@@ -764,8 +807,12 @@ extern "C" int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
   long long* mk = reinterpret_cast<long long*>(mask);
-  if (H <= 16384 && W <= 16384) return launch_fill<int>(loc, pts, src, m4, table, scores, mk, p, B, s);
-  return launch_fill<long long>(loc, pts, src, m4, table, scores, mk, p, B, s);
+  // 8-channel groups (256-bit table loads) need 32-byte aligned rows: Cs % 8 == 0 and a 32-byte aligned table
+  const bool wide = Cs % 8 == 0 && (reinterpret_cast<uintptr_t>(table) & 31u) == 0 && fill_wide_requested();
+  if (H <= 16384 && W <= 16384)
+    return wide ? launch_fill<int, 8>(loc, pts, src, m4, table, scores, mk, p, B, s)
+                : launch_fill<int, 4>(loc, pts, src, m4, table, scores, mk, p, B, s);
+  return launch_fill<long long, 4>(loc, pts, src, m4, table, scores, mk, p, B, s);
 }
 
 extern "C" int fovea_probe_store_ceiling(float* scores, int B, int C, int H, int W, fovea_stream_t stream) {

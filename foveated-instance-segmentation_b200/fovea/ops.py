@@ -344,7 +344,7 @@ def box4_table(pred, Cs=None):
     """A8 at the nodes: [B, h*w+2, Cs] value table (row h*w NaN, row h*w+1 zeros), models/models.py:935-937."""
     p = _req(pred.detach(), torch.float32, "pred", 4)
     B, Cc, h, w = p.shape
-    Cs = Cs or (Cc + 3) // 4 * 4
+    Cs = Cs or (Cc + 7) // 8 * 8        # multiple of 8: the fill kernel reads rows with 256-bit loads
     table = torch.empty(B, h * w + 2, Cs, device=p.device, dtype=torch.float32)
     _lib.call("fovea_box4_table", _ptr(p), B, Cc, h, w, Cs, _ptr(table), _stream())
     return table
