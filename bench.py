@@ -295,16 +295,21 @@ def main():
                        "image over PCIe (h2d bytes = saliency + pred + an upper bound of one 32-byte sector per tap)"}
 
     # ---------------- write-only ceiling of the fill kernel's store pattern (diagnostic, outside the timed region)
-    ceil_ms = []
-    for i in range(4):
-        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        path.ops.probe_store_ceiling(path.scores)
-        b2.record()
-        torch.cuda.synchronize()
-        if i:
-            ceil_ms.append(a.elapsed_time(b2))
-    store_ceiling = 4.0 * C * H * W * B / (min(ceil_ms) * 1e-3) / 1e9
+    def probe(side):
+        times = []
+        for i in range(4):
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            path.ops.probe_store_ceiling(path.scores, side)
+            b2.record()
+            torch.cuda.synchronize()
+            if i:
+                times.append(a.elapsed_time(b2))
+        return 4.0 * C * H * W * B / (min(times) * 1e-3) / 1e9
+
+    store_ceiling = probe(None)
+    # the same stores preceded by a 4-byte-per-pixel read (what the fill kernel's `loc` map costs at the DRAM)
+    store_read_ceiling = probe(torch.zeros(B, H, W, device=dev, dtype=torch.int32))
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -328,7 +333,8 @@ def main():
             "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": fill_ms,
-                         "store_only_ceiling_gbs": store_ceiling},
+                         "store_only_ceiling_gbs": store_ceiling,
+                         "store_plus_4B_per_px_read_ceiling_gbs": store_read_ceiling},
         }
         if e2e:
             line["e2e"] = e2e

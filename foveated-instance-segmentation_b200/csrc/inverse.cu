@@ -460,8 +460,15 @@ struct FillParams {
   int C, Cs, h, w, H, W, cap, tcap, zero_residual;
 };
 
-constexpr int kFillThreads = 256;
-constexpr int kFillTileW = 128, kFillTileH = 8;  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
+#ifndef FOVEA_FILL_THREADS
+#define FOVEA_FILL_THREADS 256
+#endif
+constexpr int kFillThreads = FOVEA_FILL_THREADS;
+#ifndef FOVEA_FILL_TILES_Y
+#define FOVEA_FILL_TILES_Y 1
+#endif
+constexpr int kFillTilesY = FOVEA_FILL_TILES_Y;  // vertically adjacent tiles streamed by one CTA
+constexpr int kFillTileW = 128, kFillTileH = kFillThreads / 32;  // 4 warps across, each 32 x 4 pixels  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
 
 // The table rows of the three vertices of one pixel, G channels each.
 template <int G>
@@ -505,15 +512,10 @@ __device__ __forceinline__ void ldg3_if<8>(Rows<8>& r, unsigned long long pa, un
 // (exact integer edge functions, stepped in registers while the triangle does not change), then stream all channels
 // with 128-bit stores.  Table rows are re-loaded only where they differ from the previous pixel's.
 template <typename I, bool kScores, bool kMask, int G>
-__global__ void __launch_bounds__(kFillThreads, G == 8 ? 2 : 4)
-inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
-                    const uint4* __restrict__ mesh, const float* __restrict__ table, float* __restrict__ scores,
-                    long long* __restrict__ mask, FillParams p) {
-  const int b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
-  const int y = blockIdx.y * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
-  if (x0 >= p.W || y >= p.H) return;
+__device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts,
+                                          const int32_t* __restrict__ src, const uint4* __restrict__ mesh,
+                                          const float* __restrict__ table, float* __restrict__ scores,
+                                          long long* __restrict__ mask, const FillParams& p, int b, int x0, int y) {
   const int hw = p.h * p.w;
   const unsigned pixoff = static_cast<unsigned>(y) * p.W + x0;  // H*W < 2^32 is checked on the host
   const size_t plane = static_cast<size_t>(p.H) * p.W;
@@ -630,18 +632,42 @@ inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__
   }
 }
 
+// One CTA streams kFillTilesY vertically adjacent 128 x 8 tiles: neighbouring tiles share most of their triangles, so
+// the table rows fetched for one tile are L1 hits for the next (CTAs are handed to SMs round-robin, so ACROSS CTAs
+// there is no such reuse).
+template <typename I, bool kScores, bool kMask, int G>
+__global__ void __launch_bounds__(kFillThreads, (G == 8 ? 2 : 4) * 256 / kFillThreads)
+inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
+                    const uint4* __restrict__ mesh, const float* __restrict__ table, float* __restrict__ scores,
+                    long long* __restrict__ mask, FillParams p) {
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
+  if (x0 >= p.W) return;
+  for (int ty = 0; ty < kFillTilesY; ++ty) {
+    const int y = (blockIdx.y * kFillTilesY + ty) * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
+    if (y >= p.H) return;
+    fill_tile<I, kScores, kMask, G>(loc, pts, src, mesh, table, scores, mask, p, b, x0, y);
+  }
+}
+
 // Diagnostic: the store pattern of inverse_fill with no computation (same tiling, same 128-bit streaming stores,
 // one 4-pixel store per channel plane) -- the practical write-only ceiling the fill kernel is measured against.
 __global__ void __launch_bounds__(kFillThreads)
-store_ceiling_kernel(float* __restrict__ scores, int C, int H, int W) {
+store_ceiling_kernel(float* __restrict__ scores, const int4* __restrict__ side_read, int C, int H, int W) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
   const int y = blockIdx.y * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
   if (x0 >= W || y >= H) return;
   const size_t plane = static_cast<size_t>(H) * W;
-  float* o = scores + static_cast<size_t>(b) * C * plane + static_cast<size_t>(y) * W + x0;
-  const float f = static_cast<float>(lane);
+  const size_t pix = static_cast<size_t>(y) * W + x0;
+  float* o = scores + static_cast<size_t>(b) * C * plane + pix;
+  float f = static_cast<float>(lane);
+  if (side_read) {  // the 4-byte-per-pixel read stream the fill kernel carries (its `loc` map)
+    const int4 l = __ldcs(side_read + (static_cast<size_t>(b) * plane + pix) / 4);
+    f += static_cast<float>(l.x ^ l.y ^ l.z ^ l.w);
+  }
   for (int c = 0; c < C; ++c, o += plane) __stcs(reinterpret_cast<float4*>(o), make_float4(f, f + 1.f, f + 2.f, f + 3.f));
 }
 
@@ -782,7 +808,7 @@ static bool fill_wide_requested() {
 template <typename I, int G>
 static int launch_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint4* m4, const float* table,
                        float* scores, long long* mk, const FillParams& p, int B, cudaStream_t s) {
-  dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH), B);
+  dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH * kFillTilesY), B);
   if (scores && mk)
     inverse_fill_kernel<I, true, true, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
   else if (scores)
@@ -815,11 +841,13 @@ extern "C" int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const 
   return launch_fill<long long, 4>(loc, pts, src, m4, table, scores, mk, p, B, s);
 }
 
-extern "C" int fovea_probe_store_ceiling(float* scores, int B, int C, int H, int W, fovea_stream_t stream) {
+extern "C" int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, int C, int H, int W,
+                                         fovea_stream_t stream) {
   FOVEA_REQUIRE(scores && B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "fovea_probe_store_ceiling: bad arguments");
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_probe_store_ceiling: B or H too large");
   dim3 grid(ceil_div(W, kFillTileW), ceil_div(H, kFillTileH), B);
-  store_ceiling_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(scores, C, H, W);
+  store_ceiling_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, reinterpret_cast<const int4*>(side_read), C, H, W);
   return check_launch("fovea_probe_store_ceiling");
 }
 

@@ -46,7 +46,7 @@ PROTOTYPES = {
     "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "fovea_probe_store_ceiling": (_i, [_p, _i, _i, _i, _i, _p]),
+    "fovea_probe_store_ceiling": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "fovea_argmax_classes": (_i, [_p, _i, _i, _i64, _p, _p]),
 }
 

@@ -369,11 +369,14 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
     return scores, mask
 
 
-def probe_store_ceiling(scores):
-    """Diagnostic: overwrite `scores` [B,C,H,W] with the store pattern of fovea_inverse_fill and no computation."""
+def probe_store_ceiling(scores, side_read=None):
+    """Diagnostic: overwrite `scores` [B,C,H,W] with the store pattern of fovea_inverse_fill and no computation;
+    `side_read` [B,H,W] int32 adds the fill kernel's 4-byte-per-pixel read stream."""
     s = _req(scores, torch.float32, "scores", 4)
     B, Cc, H, W = s.shape
-    _lib.call("fovea_probe_store_ceiling", _ptr(s), B, Cc, H, W, _stream())
+    if side_read is not None:
+        side_read = _req(side_read, torch.int32, "side_read", 3)
+    _lib.call("fovea_probe_store_ceiling", _ptr(s), _ptr(side_read), B, Cc, H, W, _stream())
 
 
 def argmax_classes(scores):

@@ -186,8 +186,11 @@ int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const int32_t* sr
                        int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
 
 /* Diagnostic (bench.py): the store pattern of fovea_inverse_fill with no computation -- same tiling, one 128-bit
- * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout. */
-int fovea_probe_store_ceiling(float* scores, int B, int C, int H, int W, fovea_stream_t stream);
+ * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout.
+ * side_read (may be NULL): a [B,H,W] int32 buffer read once, 16 bytes per thread, like the fill kernel's `loc` map --
+ * shows what a 2 % read stream mixed into the write stream costs at the DRAM. */
+int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, int C, int H, int W,
+                              fovea_stream_t stream);
 
 /* torch.argmax(scores, dim=1) as a stand-alone pass (models/models.py:1044): first maximum wins, NaN is
  * treated as the maximum (torch semantics).  scores [B,C,H,W] -> mask [B,H,W] int64 */
