@@ -193,7 +193,7 @@ def run_reference(args, cfg, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="b64_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -229,25 +229,46 @@ def main():
     x, xs, pred = make_inputs(cfg, seed=rank, device=dev)
     path = Path(cfg, dev, args.triangulation)
 
-    # ---------------- device-resident throughput (`value`)
+    # ---------------- device-resident, serial schedule: one stream, every kernel of a step after the previous one.
+    # The fill kernel is timed here (CUDA events on its stream), with nothing else on the GPU: this is the roofline.
     for _ in range(args.warmup):
         path.step(x, xs, pred)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        path.step(x, xs, pred, time_fill=True)
+    e1.record()
+    barrier()
+    serial_ms = e0.elapsed_time(e1)
+    fill_ms = sum(a.elapsed_time(b) for a, b in path.fill_ms) / max(1, len(path.fill_ms))
+
+    # ---------------- device-resident throughput (`value`): the product's DevicePipeline -- the same K steps, with the
+    # saliency-only half of step i+1 (grid, A7, A9 selection, Delaunay, point location) on a high-priority stream
+    # overlapping the HBM-bound fill of step i.  Every step's full work happens inside the timed region.
+    from fovea.pipeline import DevicePipeline
+    dpipe = DevicePipeline(B, C, H, W, cfg["g"], cfg["R"], dev, args.triangulation, depth=2, scores=path.scores)
+    for _ in range(args.warmup):
+        dpipe.submit(x, xs, pred)
+    dpipe.fence()
+    barrier()
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
         for _ in range(args.steps):
-            path.step(x, xs, pred, time_fill=True)
+            dpipe.submit(x, xs, pred, time_fill=True)
+        dpipe.fence()
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
-    fill_ms = sum(a.elapsed_time(b) for a, b in path.fill_ms) / max(1, len(path.fill_ms))
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    fill_ms_overlapped = sum(a.elapsed_time(b) for a, b in dpipe.fill_events) / max(1, len(dpipe.fill_events))
+    t = torch.tensor([ms, serial_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, serial_ms = float(t[0].item()), float(t[1].item())
     value = world * B * args.steps / (ms * 1e-3)
+    del dpipe
 
     # ---------------- end to end from host buffers (`e2e`): the public ResamplePipeline, three streams
     e2e = None
@@ -326,13 +347,19 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, **cfg, "frames_per_gpu": B, "triangulation": args.triangulation,
                        "stages": "grid+grid_sample+inverse_fill(tri), scores mode",
+                       "schedule": "fovea.pipeline.DevicePipeline: plan of step i+1 (high-priority stream) overlaps "
+                                   "the fill of step i; serial_ms_per_step = the same steps on one stream",
                        "l2": "output per step (4*C*H*W*B bytes) exceeds the 126 MB L2; no flush needed"},
+            "serial_ms_per_step": serial_ms / args.steps,
+            "path_hbm_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
             "gpu_launches": KERNELS_PER_STEP * args.steps if args.triangulation == "device"
             else (KERNELS_PER_STEP - 1) * args.steps,
             "clocks": clocks.summary(),
             "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": fill_ms,
+                         "timed_in": "the serial-schedule region (kernel alone on the GPU, events on its stream)",
+                         "ms_per_launch_overlapped": fill_ms_overlapped,
                          "store_only_ceiling_gbs": store_ceiling,
                          "store_plus_4B_per_px_read_ceiling_gbs": store_read_ceiling},
         }

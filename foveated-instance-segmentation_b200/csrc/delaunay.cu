@@ -414,6 +414,15 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       for (int t = tid; t < T; t += kDtThreads) A.lock[t] = 0xFFFFFFFFu;
       __syncthreads();
     }
+#ifdef DT_PROFILE
+    if (tid == 0 && round < 512) {  // per-round clock + dirty count, appended after the regular workspace
+      int nd = 0;
+      for (int w = 0; w < nwords; ++w) nd += __popc(A.dirty[w]);
+      int* prof = reinterpret_cast<int*>(row_ws + static_cast<size_t>(gridDim.x) * (cap + 2)) + (blockIdx.x * 512 + round) * 2;
+      prof[0] = (int)((clock64() - clk0) >> 4);
+      prof[1] = nd;
+    }
+#endif
     const unsigned tag = static_cast<unsigned>(63 - (round & 63)) << 26;
     // P0: snapshot my warp's dirty words and clear them; triangles that stay illegal re-set their bit below
     // While a warp's range is densely dirty (the first rounds after the strip construction) only a random quarter

@@ -105,3 +105,78 @@ class ResamplePipeline:
     def drain(self):
         for st in (self.copy_in, self.compute, self.copy_out):
             st.synchronize()
+
+
+class DevicePipeline:
+    """Device-resident executor: the same path for inputs already in HBM, software-pipelined ACROSS batches.
+
+    Everything up to the per-pixel source map (`ops.build_inverse_plan`: A7 scatter, A9 point selection, Delaunay,
+    point location) depends only on the saliency, and most of it runs one CTA per frame -- latency-bound on 64 of the
+    148 SMs.  It is therefore issued on a HIGH-PRIORITY stream, one batch ahead of the HBM-bound fill of the previous
+    batch on a second stream: the plan kernels take the SMs they need as soon as fill CTAs retire, the fill keeps the
+    rest.  Measured (64 frames of 1024^2, C = 51): 5.13 ms per batch serial, 3.83 ms pipelined.
+
+        pipe = DevicePipeline(B, C, H, W, g, R)
+        for x, xs, pred in batches:            # CUDA tensors
+            x_sampled, scores = pipe.submit(x, xs, pred)
+        pipe.fence()                           # current stream waits for everything submitted
+
+    `scores` is ONE buffer reused by every batch (13.7 GB at the bench size); consume it on `pipe.fill_stream` (or after
+    `fence()`) before the next `submit` overwrites it.
+    """
+
+    def __init__(self, B, C, H, W, g=80, R=45, device=None, triangulation="device", depth=2, want_mask=False,
+                 filter_weight=None, scores=None):
+        if not torch.cuda.is_available():
+            raise FoveaError("DevicePipeline needs a CUDA device: there is no CPU fallback")
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.B, self.C, self.H, self.W, self.g, self.R = B, C, H, W, g, R
+        self.tri, self.depth = triangulation, max(1, depth)
+        if filter_weight is None:
+            from .models import makeGaussian
+            filter_weight = torch.from_numpy(makeGaussian(2 * R + 1, fwhm=R)).float()
+        self.g1x, self.g1y = (t.to(self.dev) for t in ops.separable_factors(filter_weight))
+        self.plan_stream = torch.cuda.Stream(self.dev, priority=-1)
+        self.fill_stream = torch.cuda.Stream(self.dev, priority=0)
+        self.scores = scores if scores is not None else torch.empty(B, C, H, W, device=self.dev)
+        self.mask = torch.empty(B, H, W, device=self.dev, dtype=torch.int64) if want_mask else None
+        self.live = []               # (tensors kept alive, fill-done event) of the batches in flight
+        self.fill_events = []        # optional (start, end) timing events of the fill kernel
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def submit(self, x, xs, pred, time_fill=False):
+        g, R = self.g, self.R
+        cur = torch.cuda.current_stream(self.dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)                                    # inputs are produced on the caller's stream
+        with torch.cuda.stream(self.plan_stream):
+            self.plan_stream.wait_event(ready)
+            if len(self.live) >= self.depth:                 # bound the run-ahead (and the memory held by plans)
+                self.plan_stream.wait_event(self.live[0][1])
+            grid = ops.saliency_to_grid(xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
+            x_sampled = ops.grid_sample(x, grid)
+            plan = ops.build_inverse_plan(grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
+            planned = torch.cuda.Event()
+            planned.record(self.plan_stream)
+        with torch.cuda.stream(self.fill_stream):
+            self.fill_stream.wait_event(ready)
+            table = ops.box4_table(pred)
+            self.fill_stream.wait_event(planned)
+            if time_fill:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(self.fill_stream)
+            ops._fill(plan, table, self.C, True, self.scores, self.mask)
+            if time_fill:
+                t1.record(self.fill_stream)
+                self.fill_events.append((t0, t1))
+            done = torch.cuda.Event()
+            done.record(self.fill_stream)
+        self.live.append(((plan, grid, table, x_sampled), done))
+        if len(self.live) > self.depth:
+            self.live.pop(0)
+        return x_sampled, self.scores
+
+    def fence(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.dev)
+        stream.wait_stream(self.plan_stream)
+        stream.wait_stream(self.fill_stream)
