@@ -270,53 +270,96 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__
 //   loc[b,y,x] = -(n+1)    : the pixel received low-res node n directly        (models/models.py:650-651);
 //                            n == h*w: no value (outside the triangulation)    -> the NaN row of the value table
 
-// One triangle held in registers while a thread steps along its run of pixels.
-template <typename I>
-struct TriState {
-  int t;                 // triangle id
-  int r0, c0, r1, c1, r2, c2;
-  int s;                 // +1 / -1: orientation of the stored vertex order
-  I area;                // |orient(v0,v1,v2)|
-  I e0, e1, e2;          // orientation-normalised sub-areas at the current query
-  unsigned n0, n1, n2;   // neighbours (0xFFFF = hull)
+// ---- per-triangle setup records ------------------------------------------------------------------------------
+// Everything the walkers and the fill need about a triangle, derived once per triangle from (mesh, pts, src) instead
+// of once per visit: one 64-byte record = four independent 16-byte loads, no pts/src indirection.
+//   e_i(y,x) = A_i*y + B_i*x + C_i  is the orientation-normalised edge function of the edge OPPOSITE vertex i
+//   (> 0 inside; e_0/area, e_1/area are the barycentric coordinates of vertices 0 and 1).  All exact int32 for
+//   coordinates < 16384.  Pixel (y,x) belongs to the triangle iff e_i >= m_i for i = 0,1,2, where m_i = 0 if the
+//   tie rule of mesh.cuh gives an exactly-on-edge pixel to this triangle (or the edge is on the hull), else 1.
+//   q0 = (A0, B0, C0, A1)   q1 = (B1, C1, A2, B2)   q2 = (C2, n0 | n1 << 16, n2 | m << 16, area)
+//   q3 = (src0 | src1 << 16, src2, 1/area as a double)            area == 0: degenerate, owns nothing
+struct TriRec {
+  uint4 q0, q1, q2, q3;
 };
 
-template <typename I>
-__device__ __forceinline__ I orient_i(int ar, int ac, int br, int bc, int qr, int qc) {
-  return static_cast<I>(bc - ac) * static_cast<I>(qr - ar) - static_cast<I>(br - ar) * static_cast<I>(qc - ac);
+__global__ void __launch_bounds__(256)
+triangle_setup_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__ src, const uint4* __restrict__ mesh,
+                      const int32_t* __restrict__ ntri, TriRec* __restrict__ recs, int cap, int tcap) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntri[b]) return;
+  const int32_t* ptsb = pts + static_cast<size_t>(b) * cap;
+  const int32_t* srcb = src + static_cast<size_t>(b) * cap;
+  const uint4 q = __ldg(mesh + static_cast<size_t>(b) * tcap + t);
+  const unsigned i0 = q.x & 0xFFFFu, i1 = q.x >> 16, i2 = q.y & 0xFFFFu;
+  const unsigned n0 = q.z & 0xFFFFu, n1 = q.z >> 16, n2 = q.w & 0xFFFFu;
+  const int p0 = __ldg(ptsb + i0), p1 = __ldg(ptsb + i1), p2 = __ldg(ptsb + i2);
+  const int r[3] = {p0 >> 16, p1 >> 16, p2 >> 16}, c[3] = {p0 & 0xFFFF, p1 & 0xFFFF, p2 & 0xFFFF};
+  const int area2 = (c[1] - c[0]) * (r[2] - r[0]) - (r[1] - r[0]) * (c[2] - c[0]);  // orient(p0,p1,p2)
+  const int s = area2 < 0 ? -1 : 1;
+  const unsigned nb[3] = {n0, n1, n2};
+  int A[3], Bc[3], Cc[3];
+  unsigned m = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {  // edge opposite vertex i runs from vertex (i+1)%3 to vertex (i+2)%3
+    const int ar = r[(i + 1) % 3], ac = c[(i + 1) % 3], br = r[(i + 2) % 3], bc = c[(i + 2) % 3];
+    const int dr = br - ar, dc = bc - ac;
+    A[i] = s * dc;
+    Bc[i] = -s * dr;
+    Cc[i] = s * (dr * ac - dc * ar);
+    const bool tie_owned = nb[i] == kNoTri || (dr != 0 ? (s * dr > 0) : (s * dc > 0));  // mesh.cuh edge_owned at e == 0
+    if (!tie_owned) m |= 1u << i;
+  }
+  const int area = area2 < 0 ? -area2 : area2;
+  const double inv = area ? 1.0 / static_cast<double>(area) : 0.0;
+  TriRec R;
+  R.q0 = make_uint4(A[0], Bc[0], Cc[0], A[1]);
+  R.q1 = make_uint4(Bc[1], Cc[1], A[2], Bc[2]);
+  R.q2 = make_uint4(Cc[2], n0 | (n1 << 16), n2 | (m << 16), area);
+  R.q3 = make_uint4(static_cast<unsigned>(__ldg(srcb + i0)) | (static_cast<unsigned>(__ldg(srcb + i1)) << 16),
+                    static_cast<unsigned>(__ldg(srcb + i2)), static_cast<unsigned>(__double2loint(inv)),
+                    static_cast<unsigned>(__double2hiint(inv)));
+  recs[static_cast<size_t>(b) * tcap + t] = R;
 }
 
-// ownership of a query whose edge function is e w.r.t. the directed edge a->b (see mesh.cuh, edge_owned)
-template <typename I>
-__device__ __forceinline__ bool owns(I e, int s, int dr, int dc, bool hull) {
-  if (e != 0) return e > 0;
-  if (hull) return true;
-  return dr != 0 ? (s * dr > 0) : (s * dc > 0);
+// One triangle held in registers while a lane walks: its three edge functions evaluated at the lane's pixel.
+struct WalkState {
+  int t;
+  int e0, e1, e2;      // edge functions at the current pixel
+  int b0, b1, b2;      // d e_i / d col
+  unsigned n01, n2m;   // n0 | n1 << 16,  n2 | m << 16
+  int area;
+};
+
+__device__ __forceinline__ void walk_load(WalkState& S, const TriRec* __restrict__ recs, int t, int y, int x) {
+  const uint4* r = reinterpret_cast<const uint4*>(recs + t);
+  const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+  S.t = t;
+  S.b0 = static_cast<int>(q0.y); S.b1 = static_cast<int>(q1.x); S.b2 = static_cast<int>(q1.w);
+  S.e0 = static_cast<int>(q0.x) * y + S.b0 * x + static_cast<int>(q0.z);
+  S.e1 = static_cast<int>(q0.w) * y + S.b1 * x + static_cast<int>(q1.y);
+  S.e2 = static_cast<int>(q1.z) * y + S.b2 * x + static_cast<int>(q2.x);
+  S.n01 = q2.y; S.n2m = q2.z;
+  S.area = static_cast<int>(q2.w);
 }
 
-template <typename I>
-__device__ __forceinline__ int test_state(const TriState<I>& S) {  // -1 = owned, else neighbour to move to
-  if (S.e0 > 0 && S.e1 > 0 && S.e2 > 0) return -1;
-  if (!owns<I>(S.e0, S.s, S.r2 - S.r1, S.c2 - S.c1, S.n0 == kNoTri)) return static_cast<int>(S.n0);
-  if (!owns<I>(S.e1, S.s, S.r0 - S.r2, S.c0 - S.c2, S.n1 == kNoTri)) return static_cast<int>(S.n1);
-  if (!owns<I>(S.e2, S.s, S.r1 - S.r0, S.c1 - S.c0, S.n2 == kNoTri)) return static_cast<int>(S.n2);
+// -1: the pixel belongs to S.t; otherwise the neighbour across the first edge that rejects it (kNoTri = hull)
+__device__ __forceinline__ int walk_test(const WalkState& S) {
+  const unsigned m = S.n2m >> 16;
+  if (S.e0 < static_cast<int>(m & 1u)) return static_cast<int>(S.n01 & 0xFFFFu);
+  if (S.e1 < static_cast<int>((m >> 1) & 1u)) return static_cast<int>(S.n01 >> 16);
+  if (S.e2 < static_cast<int>((m >> 2) & 1u)) return static_cast<int>(S.n2m & 0xFFFFu);
   return -1;
 }
 
-template <typename I>
-__device__ __forceinline__ void load_state(TriState<I>& S, const uint4* __restrict__ rec, const int32_t* __restrict__ pts,
-                                           int t, int qr, int qc) {
-  const uint4 q = __ldg(rec + t);
-  const int p0 = __ldg(pts + (q.x & 0xFFFFu)), p1 = __ldg(pts + (q.x >> 16)), p2 = __ldg(pts + (q.y & 0xFFFFu));
-  S.t = t;
-  S.r0 = p0 >> 16; S.c0 = p0 & 0xFFFF; S.r1 = p1 >> 16; S.c1 = p1 & 0xFFFF; S.r2 = p2 >> 16; S.c2 = p2 & 0xFFFF;
-  I A = orient_i<I>(S.r0, S.c0, S.r1, S.c1, S.r2, S.c2);
-  S.s = A < 0 ? -1 : 1;
-  S.area = A < 0 ? -A : A;
-  S.e0 = static_cast<I>(S.s) * orient_i<I>(S.r1, S.c1, S.r2, S.c2, qr, qc);
-  S.e1 = static_cast<I>(S.s) * orient_i<I>(S.r2, S.c2, S.r0, S.c0, qr, qc);
-  S.e2 = S.area - S.e0 - S.e1;
-  S.n0 = q.z & 0xFFFFu; S.n1 = q.z >> 16; S.n2 = q.w & 0xFFFFu;
+__device__ __noinline__ int walk_bruteforce(const TriRec* __restrict__ recs, int T, int y, int x) {
+  WalkState S;
+  for (int t = 0; t < T; ++t) {
+    walk_load(S, recs, t, y, x);
+    if (S.area != 0 && walk_test(S) < 0) return t;
+  }
+  return -1;
 }
 
 constexpr int kLocThreads = 256;
@@ -326,13 +369,12 @@ constexpr int kLocStride = kLocRun + 1;              // shared-memory row stride
 static_assert(kLocRun == 32, "one run = one bit mask = one coalesced 128-byte row of the staging tile");
 
 // floor(num / den) for 0 <= num, 0 < den, saturated at `cap` (only quotients below the run length matter)
-template <typename I>
-__device__ __forceinline__ int floor_div_capped(I num, I den, int cap) {
+__device__ __forceinline__ int floor_div_capped(int num, int den, int cap) {
   const float qf = fminf(__fdividef(static_cast<float>(num), static_cast<float>(den)), static_cast<float>(cap));
   int q = static_cast<int>(qf);
   if (q >= cap) return cap;
-  if (static_cast<I>(q) * den > num) --q;             // float rounding is within one unit for q < cap <= 64
-  else if (static_cast<I>(q + 1) * den <= num) ++q;
+  if (q * den > num) --q;             // float rounding is within one unit for q < cap <= 64
+  else if ((q + 1) * den <= num) ++q;
   return q;
 }
 
@@ -343,11 +385,10 @@ __device__ __forceinline__ int floor_div_capped(I num, I den, int cap) {
 // transitions in lock step, and the per-pixel work is one shared-memory store.  Pixels that received a node (A7
 // winners) are masked out up front, so the densely filled fovea costs no walks at all.  The tile is then merged with
 // the winners and written with coalesced 128-byte rows.
-template <typename I>
 __global__ void __launch_bounds__(kLocThreads)
-locate_pixels_kernel(const int32_t* __restrict__ winner, const int32_t* __restrict__ pts, const uint4* __restrict__ mesh,
+locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restrict__ trirec,
                      const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints, int32_t* __restrict__ loc,
-                     int hw, int H, int W, int cap, int tcap) {
+                     int hw, int H, int W, int tcap) {
   __shared__ int tile_all[kLocThreads / 32][32 * kLocStride];
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,39 +417,35 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const int32_t* __restri
   if (T <= 0)  // empty mesh: nothing owns anything
     for (unsigned m = need; m; m &= m - 1) mine[__ffs(m) - 1] = none;
   if (need != 0 && T > 0) {
-    const int32_t* ptsb = pts + static_cast<size_t>(b) * cap;
-    const uint4* rec = mesh + static_cast<size_t>(b) * tcap;
+    const TriRec* recs = trirec + static_cast<size_t>(b) * tcap;
     const int start = hints[(static_cast<size_t>(b) * ceil_div(H, FOVEA_HINT_CELL_H) + y / FOVEA_HINT_CELL_H) *
                                 ceil_div(W, FOVEA_HINT_CELL_W) + x0 / FOVEA_HINT_CELL_W];
-    TriState<I> S;
+    WalkState S;
     bool have = false;
     int sx = 0;  // column (relative to x0) the edge functions of S are evaluated at
     while (need) {
       const int j = __ffs(need) - 1;  // next pixel that needs a triangle
       const int x = x0 + j;
       bool ok = false;
-      if (have) {  // move the held triangle's edge functions to column x:  d e_i / d col = -s * (row_b - row_a)
-        const I dj = static_cast<I>(j - sx);
-        S.e0 -= dj * static_cast<I>(S.s * (S.r2 - S.r1));
-        S.e1 -= dj * static_cast<I>(S.s * (S.r0 - S.r2));
-        S.e2 -= dj * static_cast<I>(S.s * (S.r1 - S.r0));
+      if (have) {  // move the held triangle's edge functions to column x
+        const int dj = j - sx;
+        S.e0 += dj * S.b0; S.e1 += dj * S.b1; S.e2 += dj * S.b2;
         sx = j;
-        ok = test_state<I>(S) < 0;
+        ok = walk_test(S) < 0;
       }
       if (!ok) {
         int t = have ? S.t : ((start >= 0 && start < T) ? start : 0);
         for (int step = 0; step < T + 8; ++step) {
-          load_state<I>(S, rec, ptsb, t, y, x);
+          walk_load(S, recs, t, y, x);
           if (S.area == 0) break;
-          const int nxt = test_state<I>(S);
+          const int nxt = walk_test(S);
           if (nxt < 0) { ok = true; break; }
           if (static_cast<unsigned>(nxt) == kNoTri) break;
           t = nxt;
         }
         if (!ok) {  // degenerate triangle on the way (host meshes only) or outside the hull: exhaustive search
-          Mesh m{ptsb, rec, T};
-          const Located L = locate_bruteforce(m, y, x);
-          if (L.tri >= 0) { load_state<I>(S, rec, ptsb, L.tri, y, x); ok = true; }
+          const int tb = walk_bruteforce(recs, T, y, x);
+          if (tb >= 0) { walk_load(S, recs, tb, y, x); ok = true; }
         }
         have = ok;
         sx = j;
@@ -418,25 +455,13 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const int32_t* __restri
         need &= need - 1;
         continue;
       }
-      // how many pixels to the right does S.t still own?  e_i(x + k) = e_i - k d_i must stay >= m_i (m_i = 0 where the
-      // tie rule gives the edge to this triangle, else 1); only edges the row is running towards (d_i > 0) can end it
+      // how many pixels to the right does S.t still own?  e_i(x + k) = e_i + k B_i must stay >= m_i; only edges the
+      // row is running towards (B_i < 0) can end the span
+      const unsigned m = S.n2m >> 16;
       int more = kLocRun;
-      {
-        const I d0 = static_cast<I>(S.s * (S.r2 - S.r1)), d1 = static_cast<I>(S.s * (S.r0 - S.r2)),
-                d2 = static_cast<I>(S.s * (S.r1 - S.r0));
-        if (d0 > 0) {
-          const I m = owns<I>(0, S.s, S.r2 - S.r1, S.c2 - S.c1, S.n0 == kNoTri) ? 0 : 1;
-          more = min(more, floor_div_capped<I>(S.e0 - m, d0, kLocRun));
-        }
-        if (d1 > 0) {
-          const I m = owns<I>(0, S.s, S.r0 - S.r2, S.c0 - S.c2, S.n1 == kNoTri) ? 0 : 1;
-          more = min(more, floor_div_capped<I>(S.e1 - m, d1, kLocRun));
-        }
-        if (d2 > 0) {
-          const I m = owns<I>(0, S.s, S.r1 - S.r0, S.c1 - S.c0, S.n2 == kNoTri) ? 0 : 1;
-          more = min(more, floor_div_capped<I>(S.e2 - m, d2, kLocRun));
-        }
-      }
+      if (S.b0 < 0) more = min(more, floor_div_capped(S.e0 - static_cast<int>(m & 1u), -S.b0, kLocRun));
+      if (S.b1 < 0) more = min(more, floor_div_capped(S.e1 - static_cast<int>((m >> 1) & 1u), -S.b1, kLocRun));
+      if (S.b2 < 0) more = min(more, floor_div_capped(S.e2 - static_cast<int>((m >> 2) & 1u), -S.b2, kLocRun));
       const int last = min(j + more, kLocRun - 1);                       // last owned column of this run
       need &= ~((last >= 31 ? 0xffffffffu : ((2u << last) - 1u)));       // every pixel up to `last` is settled
       for (int jj = j; jj <= last; ++jj) mine[jj] = S.t;                 // (entries of node pixels are ignored below)
@@ -511,17 +536,14 @@ __device__ __forceinline__ void ldg3_if<8>(Rows<8>& r, unsigned long long pa, un
 // Each thread owns 4 consecutive pixels of one row: resolve their table rows + barycentric weights from `loc`
 // (exact integer edge functions, stepped in registers while the triangle does not change), then stream all channels
 // with 128-bit stores.  Table rows are re-loaded only where they differ from the previous pixel's.
-template <typename I, bool kScores, bool kMask, int G>
-__device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts,
-                                          const int32_t* __restrict__ src, const uint4* __restrict__ mesh,
+template <bool kScores, bool kMask, int G>
+__device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const TriRec* __restrict__ trirec,
                                           const float* __restrict__ table, float* __restrict__ scores,
                                           long long* __restrict__ mask, const FillParams& p, int b, int x0, int y) {
   const int hw = p.h * p.w;
   const unsigned pixoff = static_cast<unsigned>(y) * p.W + x0;  // H*W < 2^32 is checked on the host
   const size_t plane = static_cast<size_t>(p.H) * p.W;
-  const int32_t* srcb = src + static_cast<size_t>(b) * p.cap;
-  const int32_t* ptsb = pts + static_cast<size_t>(b) * p.cap;
-  const uint4* rec = mesh + static_cast<size_t>(b) * p.tcap;
+  const TriRec* recs = trirec + static_cast<size_t>(b) * p.tcap;
 
   const int4 l4 = __ldcs(reinterpret_cast<const int4*>(loc + static_cast<size_t>(b) * plane + pixoff));
   const int lc[4] = {l4.x, l4.y, l4.z, l4.w};
@@ -531,7 +553,7 @@ __device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const
   unsigned reload[4] = {1u, 0u, 0u, 0u};  // pixel k's table rows differ from pixel k-1's
 
   int cur = -1, sn0 = hw, sn1 = hw, sn2 = hw;
-  I e0 = 0, e1 = 0, d0 = 0, d1 = 0;
+  int e0 = 0, e1 = 0, d0 = 0, d1 = 0;
   double inv_area = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -540,20 +562,16 @@ __device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const
     if (lc[k] < 0) {
       n0 = n1 = n2 = -(lc[k] + 1);
     } else {
-      if (lc[k] != cur) {
+      if (lc[k] != cur) {  // one setup record = three independent 16-byte loads (no pts / src indirection)
         cur = lc[k];
-        const uint4 q = __ldg(rec + cur);
-        const unsigned i0 = q.x & 0xFFFFu, i1 = q.x >> 16, i2 = q.y & 0xFFFFu;
-        const int p0 = __ldg(ptsb + i0), p1 = __ldg(ptsb + i1), p2 = __ldg(ptsb + i2);
-        sn0 = __ldg(srcb + i0); sn1 = __ldg(srcb + i1); sn2 = __ldg(srcb + i2);
-        const int r0 = p0 >> 16, c0 = p0 & 0xFFFF, r1 = p1 >> 16, c1 = p1 & 0xFFFF, r2 = p2 >> 16, c2 = p2 & 0xFFFF;
-        const I A = orient_i<I>(r0, c0, r1, c1, r2, c2);
-        const I s = A < 0 ? -1 : 1;
-        e0 = s * orient_i<I>(r1, c1, r2, c2, y, x0 + k);
-        e1 = s * orient_i<I>(r2, c2, r0, c0, y, x0 + k);
-        d0 = s * static_cast<I>(r2 - r1);  // d e_i / d col = -s * (row_b - row_a)
-        d1 = s * static_cast<I>(r0 - r2);
-        inv_area = 1.0 / static_cast<double>(A < 0 ? -A : A);
+        const uint4* r = reinterpret_cast<const uint4*>(recs + cur);
+        const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q3 = __ldg(r + 3);
+        d0 = static_cast<int>(q0.y);
+        d1 = static_cast<int>(q1.x);
+        e0 = static_cast<int>(q0.x) * y + d0 * (x0 + k) + static_cast<int>(q0.z);
+        e1 = static_cast<int>(q0.w) * y + d1 * (x0 + k) + static_cast<int>(q1.y);
+        sn0 = static_cast<int>(q3.x & 0xFFFFu); sn1 = static_cast<int>(q3.x >> 16); sn2 = static_cast<int>(q3.y);
+        inv_area = __hiloint2double(static_cast<int>(q3.w), static_cast<int>(q3.z));
       }
       // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 in float64, c2 = 1 - c0 - c1, then cast to float32
       const double c0 = static_cast<double>(e0) * inv_area;
@@ -563,8 +581,8 @@ __device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const
       a2 = static_cast<float>(1.0 - c0 - c1);
       n0 = sn0; n1 = sn1; n2 = sn2;
     }
-    e0 -= d0;  // advance to column x0 + k + 1 (harmless while no triangle is held: d == 0)
-    e1 -= d1;
+    e0 += d0;  // advance to column x0 + k + 1 (harmless while no triangle is held: d == 0)
+    e1 += d1;
     if (n0 == hw || n1 == hw || n2 == hw) {  // a NaN vertex poisons every channel (NaN*w, even for w == 0)
       nanmask |= 1u << k;
       n0 = n1 = n2 = p.zero_residual ? hw + 1 : hw;  // models_instance.py:940: residual NaN -> 0
@@ -635,11 +653,10 @@ __device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const
 // One CTA streams kFillTilesY vertically adjacent 128 x 8 tiles: neighbouring tiles share most of their triangles, so
 // the table rows fetched for one tile are L1 hits for the next (CTAs are handed to SMs round-robin, so ACROSS CTAs
 // there is no such reuse).
-template <typename I, bool kScores, bool kMask, int G>
+template <bool kScores, bool kMask, int G>
 __global__ void __launch_bounds__(kFillThreads, (G == 8 ? 2 : 4) * 256 / kFillThreads)
-inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__ pts, const int32_t* __restrict__ src,
-                    const uint4* __restrict__ mesh, const float* __restrict__ table, float* __restrict__ scores,
-                    long long* __restrict__ mask, FillParams p) {
+inverse_fill_kernel(const int32_t* __restrict__ loc, const TriRec* __restrict__ trirec, const float* __restrict__ table,
+                    float* __restrict__ scores, long long* __restrict__ mask, FillParams p) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
@@ -647,7 +664,7 @@ inverse_fill_kernel(const int32_t* __restrict__ loc, const int32_t* __restrict__
   for (int ty = 0; ty < kFillTilesY; ++ty) {
     const int y = (blockIdx.y * kFillTilesY + ty) * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
     if (y >= p.H) return;
-    fill_tile<I, kScores, kMask, G>(loc, pts, src, mesh, table, scores, mask, p, b, x0, y);
+    fill_tile<kScores, kMask, G>(loc, trirec, table, scores, mask, p, b, x0, y);
   }
 }
 
@@ -777,23 +794,28 @@ extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const
   return check_launch("fovea_locate_hints");
 }
 
-extern "C" int fovea_locate_pixels(const int32_t* winner, const int32_t* pts, const int32_t* npts,
-                                   const uint16_t* mesh, const int32_t* ntri, const int32_t* hints, int B, int h,
-                                   int w, int H, int W, int cap, int tcap, int32_t* loc, fovea_stream_t stream) {
-  (void)npts;
-  FOVEA_REQUIRE(winner && pts && mesh && ntri && hints && loc, "fovea_locate_pixels: null pointer");
+extern "C" int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t* mesh, const int32_t* ntri,
+                                    int B, int cap, int tcap, int max_coord, void* trirec, fovea_stream_t stream) {
+  FOVEA_REQUIRE(pts && src && mesh && ntri && trirec && B > 0 && cap > 0 && tcap > 0, "fovea_triangle_setup: bad arguments");
+  FOVEA_REQUIRE(max_coord > 0 && max_coord <= 16384,
+                "fovea_triangle_setup: coordinates must be < 16384 for exact int32 edge functions (got %d)", max_coord);
+  FOVEA_REQUIRE(B <= 65535, "fovea_triangle_setup: B too large for the grid");
+  dim3 grid(ceil_div(tcap, 256), B);
+  triangle_setup_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pts, src, reinterpret_cast<const uint4*>(mesh), ntri, static_cast<TriRec*>(trirec), cap, tcap);
+  return check_launch("fovea_triangle_setup");
+}
+
+extern "C" int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t* ntri,
+                                   const int32_t* hints, int B, int h, int w, int H, int W, int tcap, int32_t* loc,
+                                   fovea_stream_t stream) {
+  FOVEA_REQUIRE(winner && trirec && ntri && hints && loc, "fovea_locate_pixels: null pointer");
   FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1, "fovea_locate_pixels: bad sizes");
-  FOVEA_REQUIRE(W % 4 == 0, "fovea_locate_pixels: W=%d must be a multiple of 4 (128-bit accesses)", W);
+  FOVEA_REQUIRE(H <= 16384 && W <= 16384, "fovea_locate_pixels: canvas side must be <= 16384");
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kLocTileH) <= 65535, "fovea_locate_pixels: B or H too large for the grid");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
   dim3 grid(ceil_div(W, kLocTileW), ceil_div(H, kLocTileH), B);
-  // coordinates < 16384 keep every orientation determinant inside int32 (|diff| < 2^14, products < 2^28)
-  if (H <= 16384 && W <= 16384)
-    locate_pixels_kernel<int><<<grid, kLocThreads, 0, s>>>(winner, pts, m4, ntri, hints, loc, h * w, H, W, cap, tcap);
-  else
-    locate_pixels_kernel<long long><<<grid, kLocThreads, 0, s>>>(winner, pts, m4, ntri, hints, loc, h * w, H, W, cap,
-                                                                 tcap);
+  locate_pixels_kernel<<<grid, kLocThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      winner, static_cast<const TriRec*>(trirec), ntri, hints, loc, h * w, H, W, tcap);
   return check_launch("fovea_locate_pixels");
 }
 
@@ -805,40 +827,38 @@ static bool fill_wide_requested() {
   return v;
 }
 
-template <typename I, int G>
-static int launch_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint4* m4, const float* table,
-                       float* scores, long long* mk, const FillParams& p, int B, cudaStream_t s) {
+template <int G>
+static int launch_fill(const int32_t* loc, const TriRec* recs, const float* table, float* scores, long long* mk,
+                       const FillParams& p, int B, cudaStream_t s) {
   dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH * kFillTilesY), B);
   if (scores && mk)
-    inverse_fill_kernel<I, true, true, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
+    inverse_fill_kernel<true, true, G><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   else if (scores)
-    inverse_fill_kernel<I, true, false, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
+    inverse_fill_kernel<true, false, G><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   else
-    inverse_fill_kernel<I, false, true, G><<<grid, kFillThreads, 0, s>>>(loc, pts, src, m4, table, scores, mk, p);
+    inverse_fill_kernel<false, true, G><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   return check_launch("fovea_inverse_fill");
 }
 
-extern "C" int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint16_t* mesh,
-                                  const float* table, int B, int C, int Cs, int h, int w, int H, int W, int cap,
-                                  int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream) {
-  FOVEA_REQUIRE(loc && pts && src && mesh && table, "fovea_inverse_fill: null pointer");
+extern "C" int fovea_inverse_fill(const int32_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h,
+                                  int w, int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask,
+                                  fovea_stream_t stream) {
+  FOVEA_REQUIRE(loc && trirec && table, "fovea_inverse_fill: null pointer");
   FOVEA_REQUIRE(scores || mask, "fovea_inverse_fill: neither scores nor mask requested");
   FOVEA_REQUIRE(B > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && h > 0 && w > 0 && H > 1 && W > 1,
                 "fovea_inverse_fill: bad sizes");
   FOVEA_REQUIRE(W % 4 == 0, "fovea_inverse_fill: W=%d must be a multiple of 4 (128-bit stores)", W);
+  FOVEA_REQUIRE(H <= 16384 && W <= 16384, "fovea_inverse_fill: canvas side must be <= 16384");
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_inverse_fill: B or H too large for the grid");
-  FOVEA_REQUIRE(static_cast<long long>(H) * W < (1ll << 32) && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
-                "fovea_inverse_fill: canvas or value table too large for 32-bit offsets");
-  FillParams p{C, Cs, h, w, H, W, cap, tcap, zero_residual};
+  FOVEA_REQUIRE(static_cast<long long>(h) * w + 2 < 65536 && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
+                "fovea_inverse_fill: value table too large (rows must fit 16 bits, bytes 32 bits)");
+  FillParams p{C, Cs, h, w, H, W, 0, tcap, zero_residual};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const uint4* m4 = reinterpret_cast<const uint4*>(mesh);
+  const TriRec* recs = static_cast<const TriRec*>(trirec);
   long long* mk = reinterpret_cast<long long*>(mask);
   // 8-channel groups (256-bit table loads) need 32-byte aligned rows: Cs % 8 == 0 and a 32-byte aligned table
   const bool wide = Cs % 8 == 0 && (reinterpret_cast<uintptr_t>(table) & 31u) == 0 && fill_wide_requested();
-  if (H <= 16384 && W <= 16384)
-    return wide ? launch_fill<int, 8>(loc, pts, src, m4, table, scores, mk, p, B, s)
-                : launch_fill<int, 4>(loc, pts, src, m4, table, scores, mk, p, B, s);
-  return launch_fill<long long, 4>(loc, pts, src, m4, table, scores, mk, p, B, s);
+  return wide ? launch_fill<8>(loc, recs, table, scores, mk, p, B, s) : launch_fill<4>(loc, recs, table, scores, mk, p, B, s);
 }
 
 extern "C" int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, int C, int H, int W,

@@ -206,6 +206,7 @@ class InversePlan:
     mesh: torch.Tensor     # [B,tcap,8] uint16: (v0,v1,v2,0,n0,n1,n2,0) per triangle
     ntri: torch.Tensor     # [B] int32
     hints: torch.Tensor    # [B,ceil(H/8),ceil(W/32)] int32 walk-start triangles
+    trirec: torch.Tensor   # [B,tcap,16] int32: 64-byte per-triangle setup records (edge functions, 1/area, rows)
     loc: torch.Tensor      # [B,H,W] int32 per-pixel source: triangle id, or -(node+1)
     h: int
     w: int
@@ -275,8 +276,9 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
     hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
-    loc = _locate(winner, pts, npts, mesh, ntri, hints, h, w, cap, tcap)
-    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, loc, h, w, H, W, cap, tcap, triangulation)
+    trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W))
+    loc = _locate(winner, trirec, ntri, hints, h, w, tcap)
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, h, w, H, W, cap, tcap, triangulation)
 
 
 def delaunay_device(pts, npts, cap, tcap, max_coord):
@@ -305,14 +307,23 @@ def _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W):
     return hints
 
 
-def _locate(winner, pts, npts, mesh, ntri, hints, h, w, cap, tcap):
+def _triangle_setup(pts, src, mesh, ntri, cap, tcap, max_coord):
+    """Per-triangle setup records (edge functions, tie bits, 1/area, value rows) for the walkers and the fill."""
+    B = pts.shape[0]
+    trirec = torch.empty(B, tcap, 16, device=pts.device, dtype=torch.int32)
+    _lib.call("fovea_triangle_setup", _ptr(pts), _ptr(src), _ptr(mesh), _ptr(ntri), B, cap, tcap, int(max_coord),
+              _ptr(trirec), _stream())
+    return trirec
+
+
+def _locate(winner, trirec, ntri, hints, h, w, tcap):
     """interp2d.py:58 (find_simplex for every pixel) merged with the A7 winners: the per-pixel source map `loc`."""
     B, H, W = winner.shape
     if W % 4:
         raise FoveaError(f"canvas width {W} must be a multiple of 4 (128-bit accesses)")
     loc = torch.empty_like(winner)
-    _lib.call("fovea_locate_pixels", _ptr(winner), _ptr(pts), _ptr(npts), _ptr(mesh), _ptr(ntri), _ptr(hints), B, h, w,
-              H, W, cap, tcap, _ptr(loc), _stream())
+    _lib.call("fovea_locate_pixels", _ptr(winner), _ptr(trirec), _ptr(ntri), _ptr(hints), B, h, w, H, W, tcap,
+              _ptr(loc), _stream())
     return loc
 
 
@@ -323,8 +334,9 @@ def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
     tcap = mesh.shape[1]
     winner = torch.full((B, H, W), -1, device=pts.device, dtype=torch.int32)
     hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
-    loc = _locate(winner, pts, npts, mesh, ntri, hints, table_rows, 1, cap, tcap)
-    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, loc, table_rows, 1, H, W, cap, tcap, "given")
+    trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W))
+    loc = _locate(winner, trirec, ntri, hints, table_rows, 1, tcap)
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, table_rows, 1, H, W, cap, tcap, "given")
 
 
 def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=None, mask=None):
@@ -335,9 +347,9 @@ def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=
 
 
 def _fill(plan, table, C, zero_residual, scores, mask):
-    _lib.call("fovea_inverse_fill", _ptr(plan.loc), _ptr(plan.pts), _ptr(plan.src), _ptr(plan.mesh), _ptr(table),
-              plan.loc.shape[0], C, table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.cap, plan.tcap,
-              1 if zero_residual else 0, _ptr(scores), _ptr(mask), _stream())
+    _lib.call("fovea_inverse_fill", _ptr(plan.loc), _ptr(plan.trirec), _ptr(table), plan.loc.shape[0], C,
+              table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.tcap, 1 if zero_residual else 0, _ptr(scores),
+              _ptr(mask), _stream())
 
 
 def box4_table(pred, Cs=None):

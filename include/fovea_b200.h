@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 2
+#define FOVEA_ABI_VERSION 3
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -159,6 +159,16 @@ int64_t fovea_locate_hints_workspace_bytes(int B, int H, int W);
 int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* mesh, const int32_t* ntri, int B,
                        int cap, int tcap, int H, int W, int32_t* hints, void* workspace, fovea_stream_t stream);
 
+/* Per-triangle setup records: everything the point location and the fill need about a triangle, derived once per
+ * triangle from (mesh, pts, src): the three orientation-normalised edge functions e_i(y,x) = A_i*y + B_i*x + C_i
+ * (exact int32), the tie-ownership bit of each edge (top-left rule, csrc/mesh.cuh), the neighbours, |area|, 1/area
+ * (float64, as interp2d.py:58 / spatial/qhull.pyx:1210-1264 compute the barycentric transform) and the value-table rows
+ * of the three vertices.  Layout: csrc/inverse.cu `struct TriRec` (64 bytes).
+ *   trirec [B, tcap, 16] int32 (64-byte records);  max_coord = max(H, W) <= 16384. */
+#define FOVEA_TRIREC_BYTES 64
+int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t* mesh, const int32_t* ntri, int B,
+                         int cap, int tcap, int max_coord, void* trirec, fovea_stream_t stream);
+
 /* A9 point location, interp2d.py:58 (Delaunay.find_simplex over every pixel, spatial/qhull.pyx:2075-2163), merged
  * with the A7 winners into one per-pixel source map -- a function of the sampling grid only (not of the scores):
  *   loc[b,y,x] >= 0      id of the mesh triangle that owns pixel (y,x).  A pixel exactly on an edge belongs to
@@ -166,24 +176,24 @@ int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* 
  *                        walk order;
  *   loc[b,y,x] = -(n+1)  the pixel received low-res node n directly (winner[b,y,x] = n);  n = h*w: the pixel has no
  *                        value (outside the triangulation / empty mesh) and reads the NaN row of the value table.
- *   winner [B,H,W] int32 from fovea_grid_inv_scatter (all -1 = interpolate every pixel, Interp2D);  hints from
- *   fovea_locate_hints;  loc [B,H,W] int32 (a separate buffer: must not alias winner);  W % 4 == 0. */
-int fovea_locate_pixels(const int32_t* winner, const int32_t* pts, const int32_t* npts, const uint16_t* mesh,
-                        const int32_t* ntri, const int32_t* hints, int B, int h, int w, int H, int W, int cap,
-                        int tcap, int32_t* loc, fovea_stream_t stream);
+ *   winner [B,H,W] int32 from fovea_grid_inv_scatter (all -1 = interpolate every pixel, Interp2D);  trirec from
+ *   fovea_triangle_setup;  hints from fovea_locate_hints;  loc [B,H,W] int32 (a separate buffer: must not alias
+ *   winner);  H, W <= 16384. */
+int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t* ntri, const int32_t* hints, int B,
+                        int h, int w, int H, int W, int tcap, int32_t* loc, fovea_stream_t stream);
 
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
  * fillMissingValues_tensor(..., 'tri') = Interp2D barycentric gather (models/models.py:939-940,
  * interp2d.py:65-91), residual NaN -> 0 (models_instance.py:940) and torch.argmax over classes
  * (models/models.py:1044), in ONE pass over the full-resolution canvas: the score tensor is written exactly once.
  *   loc    [B,H,W] from fovea_locate_pixels
- *   table  [B, h*w+2, Cs] from fovea_box4_table
+ *   trirec [B,tcap,16] from fovea_triangle_setup
+ *   table  [B, h*w+2, Cs] from fovea_box4_table   (h*w+2 < 65536)
  *   scores [B,C,H,W] fp32   (NULL = do not materialise)
  *   mask   [B,H,W]  int64   (NULL = do not compute)
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
-int fovea_inverse_fill(const int32_t* loc, const int32_t* pts, const int32_t* src, const uint16_t* mesh,
-                       const float* table, int B, int C, int Cs, int h, int w, int H, int W, int cap, int tcap,
-                       int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
+int fovea_inverse_fill(const int32_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
+                       int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
 
 /* Diagnostic (bench.py): the store pattern of fovea_inverse_fill with no computation -- same tiling, one 128-bit
  * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout.
