@@ -17,7 +17,9 @@ struct GridParams {
   float scale_y, scale_x;  // gh/out_h, gw/out_w as aten computes them
 };
 
-constexpr int kGridThreads = 512;
+constexpr int kGridThreads = 512;   // backward kernel
+constexpr int kFwdThreads = 1024;   // forward kernel
+constexpr int kTile = 4;            // outputs per thread and pass (register tile along the filtered axis)
 
 __device__ __forceinline__ int src_index(int t_padded, int R, int n, int mode) {
   return mode == FOVEA_PAD_NONE ? t_padded : pad_map(t_padded - R, n, mode);
@@ -28,76 +30,150 @@ __device__ __forceinline__ float p_basis_value(int t_padded, int R, int n) {
   return static_cast<float>(static_cast<double>(t_padded - R) / (static_cast<double>(n) - 1.0));
 }
 
-__global__ void __launch_bounds__(kGridThreads, 1)
+// Shared-memory plan of the forward kernel (floats unless noted), in this order:
+//   gxz [Kx + 2*(kTile-1)]   column-pass filter, zero-padded by kTile-1 on both sides (no bounds tests in the loops)
+//   gyz [Ky + 2*(kTile-1)]   row-pass filter, likewise
+//   p0  [Gw]  p1 [Gh]        P_basis along padded columns / rows
+//   rmap [Gh] (int)          padded row -> row of S0/S1 (src_h = the all-zero row for zero padding)
+//   cmap [Gw] (int)          padded col -> source column (-1 = zero tap)          (fused padding only)
+//   S0, S1 [(src_h+1)][gw]   row-filtered xs and P0*xs (+ one zero row)
+//   U   max([src_h][Gw] staged padded rows (fused padding), [2][gh][gw] clamped raw grid)   -- reused
+struct FwdSmem {
+  float *gxz, *gyz, *p0, *p1, *S0, *S1, *U;
+  int *rmap, *cmap;
+};
+
+__host__ __device__ inline size_t fwd_smem_floats(int gh, int gw, int Rx, int Ry, int src_h, bool staged) {
+  const int Kx = 2 * Rx + 1, Ky = 2 * Ry + 1, Gh = gh + 2 * Rx, Gw = gw + 2 * Ry;
+  size_t u = 2 * static_cast<size_t>(gh) * gw;
+  if (staged && static_cast<size_t>(src_h) * Gw > u) u = static_cast<size_t>(src_h) * Gw;
+  return static_cast<size_t>(Kx + Ky + 4 * (kTile - 1)) + 2 * (Gw + Gh) + 2 * static_cast<size_t>(src_h + 1) * gw + u;
+}
+
+// kStaged: the (fused-padding) source rows are expanded to padded rows in shared memory once, so the row pass reads
+// them without index arithmetic; for FOVEA_PAD_NONE the padded map is read from global memory (L1) directly.
+template <bool kStaged>
+__global__ void __launch_bounds__(kFwdThreads, 1)
 grid_fwd_kernel(const float* __restrict__ xs, const float* __restrict__ g1x, const float* __restrict__ g1y,
                 float* __restrict__ grid, float* __restrict__ sums, GridParams p) {
   extern __shared__ float smem[];
   const int Kx = 2 * p.Rx + 1, Ky = 2 * p.Ry + 1;
   const int Gh = p.gh + 2 * p.Rx, Gw = p.gw + 2 * p.Ry;
-  float* gx = smem;                  // [Kx]
-  float* gy = gx + Kx;               // [Ky]
-  float* p0 = gy + Ky;               // [Gw]  P_basis[0] along padded columns
-  float* p1 = p0 + Gw;               // [Gh]  P_basis[1] along padded rows
-  float* S0 = p1 + Gh;               // [src_h][gw]  row-filtered xs
-  float* S1 = S0 + p.src_h * p.gw;   // [src_h][gw]  row-filtered P0*xs
-  float* raw = S1 + p.src_h * p.gw;  // [2][gh][gw]  clamped grid before the resize
+  constexpr int Z = kTile - 1;
+  FwdSmem m;
+  m.gxz = smem;
+  m.gyz = m.gxz + Kx + 2 * Z;
+  m.p0 = m.gyz + Ky + 2 * Z;
+  m.p1 = m.p0 + Gw;
+  m.rmap = reinterpret_cast<int*>(m.p1 + Gh);
+  m.cmap = m.rmap + Gh;
+  m.S0 = reinterpret_cast<float*>(m.cmap + Gw);
+  m.S1 = m.S0 + (p.src_h + 1) * p.gw;
+  m.U = m.S1 + (p.src_h + 1) * p.gw;
 
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
   const float* xb = xs + static_cast<size_t>(b) * p.src_h * p.src_w;
 
-  for (int i = tid; i < Kx; i += kGridThreads) gx[i] = g1x[i];
-  for (int i = tid; i < Ky; i += kGridThreads) gy[i] = g1y[i];
-  for (int i = tid; i < Gw; i += kGridThreads) p0[i] = p_basis_value(i, p.Ry, p.gw);
-  for (int i = tid; i < Gh; i += kGridThreads) p1[i] = p_basis_value(i, p.Rx, p.gh);
+  for (int i = tid; i < Kx + 2 * Z; i += kFwdThreads) m.gxz[i] = (i >= Z && i < Z + Kx) ? g1x[i - Z] : 0.f;
+  for (int i = tid; i < Ky + 2 * Z; i += kFwdThreads) m.gyz[i] = (i >= Z && i < Z + Ky) ? g1y[i - Z] : 0.f;
+  for (int i = tid; i < Gw; i += kFwdThreads) {
+    m.p0[i] = p_basis_value(i, p.Ry, p.gw);
+    m.cmap[i] = src_index(i, p.Ry, p.gw, p.pad_mode);
+  }
+  for (int i = tid; i < Gh; i += kFwdThreads) {
+    m.p1[i] = p_basis_value(i, p.Rx, p.gh);
+    const int r = src_index(i, p.Rx, p.gh, p.pad_mode);
+    m.rmap[i] = r < 0 ? p.src_h : r;
+  }
+  for (int i = tid; i < p.gw; i += kFwdThreads) m.S0[p.src_h * p.gw + i] = m.S1[p.src_h * p.gw + i] = 0.f;
   __syncthreads();
+  if (kStaged) {  // padded rows: xp[r][u] = xs[r][cmap[u]] (0 for a zero tap)
+    for (int idx = tid; idx < p.src_h * Gw; idx += kFwdThreads) {
+      const int r = idx / Gw, u = idx - r * Gw;
+      const int c = m.cmap[u];
+      m.U[idx] = c >= 0 ? __ldg(xb + r * p.src_w + c) : 0.f;
+    }
+    __syncthreads();
+  }
 
-  // ---- row pass: S0[r][j] = sum_b gy[b] xs[r][col(j+b)],  S1 likewise with P0(j+b) folded in
-  for (int idx = tid; idx < p.src_h * p.gw; idx += kGridThreads) {
-    const int r = idx / p.gw, j = idx - r * p.gw;
-    const float* row = xb + static_cast<size_t>(r) * p.src_w;
-    float s0 = 0.f, s1 = 0.f;
-    for (int t = 0; t < Ky; ++t) {
-      const int c = src_index(j + t, p.Ry, p.gw, p.pad_mode);
-      if (c >= 0) {
-        const float v = __ldg(row + c);
-        s0 = fmaf(gy[t], v, s0);
-        s1 = fmaf(gy[t], p0[j + t] * v, s1);
+  // ---- row pass: S0[r][j] = sum_t gy[t] xp[r][j+t],  S1 likewise with P0(j+t) folded in.  One thread produces
+  // kTile consecutive j of one row: every padded element is loaded once and feeds 2*kTile FMAs; the filter taps slide
+  // through a register window.  Each output still accumulates its taps in ascending order (as the untiled loop did).
+  const int jt = ceil_div(p.gw, kTile);
+  for (int item = tid; item < p.src_h * jt; item += kFwdThreads) {
+    const int r = item / jt, j0 = (item - r * jt) * kTile;
+    const float* row = kStaged ? m.U + r * Gw : xb + static_cast<size_t>(r) * p.src_w;
+    float a0[kTile], a1[kTile], g[kTile];
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) { a0[k] = a1[k] = 0.f; g[k] = 0.f; }
+    // output j0+k uses tap t = u - (j0+k); window g[k] = gyz[Z + u - j0 - k]
+    const int u_end = min(j0 + kTile - 1 + Ky, Gw);
+    for (int u = j0; u < u_end; ++u) {
+#pragma unroll
+      for (int k = kTile - 1; k > 0; --k) g[k] = g[k - 1];
+      g[0] = m.gyz[Z + u - j0];
+      const float v = kStaged ? row[u] : __ldg(row + u);
+      const float pv = m.p0[u] * v;
+#pragma unroll
+      for (int k = 0; k < kTile; ++k) {
+        a0[k] = fmaf(g[k], v, a0[k]);
+        a1[k] = fmaf(g[k], pv, a1[k]);
       }
     }
-    S0[idx] = s0;
-    S1[idx] = s1;
+#pragma unroll
+    for (int k = 0; k < kTile; ++k)
+      if (j0 + k < p.gw) {
+        m.S0[r * p.gw + j0 + k] = a0[k];
+        m.S1[r * p.gw + j0 + k] = a1[k];
+      }
   }
   __syncthreads();
 
-  // ---- column pass + quotient + clamp (models/models.py:609-615)
+  // ---- column pass + quotient + clamp (models/models.py:609-615): kTile consecutive i of one column per thread
+  float* raw = m.U;  // the staged rows are dead now
   float* sums_b = sums ? sums + static_cast<size_t>(b) * 3 * p.gh * p.gw : nullptr;
-  for (int idx = tid; idx < p.gh * p.gw; idx += kGridThreads) {
-    const int i = idx / p.gw, j = idx - i * p.gw;
-    float den = 0.f, nx = 0.f, ny = 0.f;
-    for (int t = 0; t < Kx; ++t) {
-      const int r = src_index(i + t, p.Rx, p.gh, p.pad_mode);
-      if (r >= 0) {
-        const float a = S0[r * p.gw + j];
-        den = fmaf(gx[t], a, den);
-        ny = fmaf(gx[t], p1[i + t] * a, ny);
-        nx = fmaf(gx[t], S1[r * p.gw + j], nx);
+  const int it = ceil_div(p.gh, kTile);
+  for (int item = tid; item < it * p.gw; item += kFwdThreads) {
+    const int ib = item / p.gw, j = item - ib * p.gw, i0 = ib * kTile;
+    float den[kTile], nx[kTile], ny[kTile], g[kTile];
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) { den[k] = nx[k] = ny[k] = 0.f; g[k] = 0.f; }
+    const int v_end = min(i0 + kTile - 1 + Kx, Gh);
+    for (int v = i0; v < v_end; ++v) {
+#pragma unroll
+      for (int k = kTile - 1; k > 0; --k) g[k] = g[k - 1];
+      g[0] = m.gxz[Z + v - i0];
+      const int r = m.rmap[v];
+      const float a = m.S0[r * p.gw + j], s1 = m.S1[r * p.gw + j];
+      const float pa = m.p1[v] * a;
+#pragma unroll
+      for (int k = 0; k < kTile; ++k) {
+        den[k] = fmaf(g[k], a, den[k]);
+        ny[k] = fmaf(g[k], pa, ny[k]);
+        nx[k] = fmaf(g[k], s1, nx[k]);
       }
     }
-    if (sums_b) {
-      sums_b[idx] = den;
-      sums_b[p.gh * p.gw + idx] = nx;
-      sums_b[2 * p.gh * p.gw + idx] = ny;
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) {
+      const int i = i0 + k;
+      if (i >= p.gh) break;
+      const int idx = i * p.gw + j;
+      if (sums_b) {
+        sums_b[idx] = den[k];
+        sums_b[p.gh * p.gw + idx] = nx[k];
+        sums_b[2 * p.gh * p.gw + idx] = ny[k];
+      }
+      raw[idx] = fminf(fmaxf(__fadd_rn(__fmul_rn(__fdiv_rn(nx[k], den[k]), 2.f), -1.f), -1.f), 1.f);
+      raw[p.gh * p.gw + idx] = fminf(fmaxf(__fadd_rn(__fmul_rn(__fdiv_rn(ny[k], den[k]), 2.f), -1.f), -1.f), 1.f);
     }
-    raw[idx] = fminf(fmaxf(__fadd_rn(__fmul_rn(__fdiv_rn(nx, den), 2.f), -1.f), -1.f), 1.f);
-    raw[p.gh * p.gw + idx] = fminf(fmaxf(__fadd_rn(__fmul_rn(__fdiv_rn(ny, den), 2.f), -1.f), -1.f), 1.f);
   }
   __syncthreads();
 
   // ---- nn.Upsample(bilinear) to the task size + NCHW->NHWC (models/models.py:621-637)
   float2* gout = reinterpret_cast<float2*>(grid) + static_cast<size_t>(b) * p.out_h * p.out_w;
   const bool identity = (p.out_h == p.gh) && (p.out_w == p.gw);
-  for (int idx = tid; idx < p.out_h * p.out_w; idx += kGridThreads) {
+  for (int idx = tid; idx < p.out_h * p.out_w; idx += kFwdThreads) {
     float2 o;
     if (identity) {
       o.x = raw[idx];
@@ -312,15 +388,21 @@ extern "C" int fovea_grid_fwd(const float* xs, int B, int gh, int gw, int Rx, in
   FOVEA_REQUIRE(xs && g1x && g1y && grid, "fovea_grid_fwd: null pointer");
   GridParams p;
   if (int rc = fill_params(p, B, gh, gw, Rx, Ry, pad_mode, out_h, out_w)) return rc;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(2 * Rx + 1) + (2 * Ry + 1) + (gw + 2 * Ry) + (gh + 2 * Rx) +
-                                       2 * static_cast<size_t>(p.src_h) * gw + 2 * static_cast<size_t>(gh) * gw);
+  const bool staged = pad_mode != FOVEA_PAD_NONE;
+  const size_t smem = sizeof(float) * fwd_smem_floats(gh, gw, Rx, Ry, p.src_h, staged);
   if (smem > 227 * 1024) {
     set_error("fovea_grid_fwd: %zu B of shared memory needed (> 227 KB) for gh=%d gw=%d Rx=%d Ry=%d", smem, gh, gw, Rx,
               Ry);
     return FOVEA_ERR_CAPACITY;
   }
-  FOVEA_CUDA(cudaFuncSetAttribute(grid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  grid_fwd_kernel<<<B, kGridThreads, smem, static_cast<cudaStream_t>(stream)>>>(xs, g1x, g1y, grid, sums, p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (staged) {
+    FOVEA_CUDA(cudaFuncSetAttribute(grid_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    grid_fwd_kernel<true><<<B, kFwdThreads, smem, s>>>(xs, g1x, g1y, grid, sums, p);
+  } else {
+    FOVEA_CUDA(cudaFuncSetAttribute(grid_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    grid_fwd_kernel<false><<<B, kFwdThreads, smem, s>>>(xs, g1x, g1y, grid, sums, p);
+  }
   return check_launch("fovea_grid_fwd");
 }
 
