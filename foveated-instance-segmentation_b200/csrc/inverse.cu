@@ -402,13 +402,18 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restric
   const int none = -(hw + 1);
 
   // ---- which pixels of my run need a triangle?  (bit j of `need`: pixel x0 + j received no node)
+  // ---- stage the winners: tile[l][j] = -(n+1) for a pixel that received node n (its final value); bit j of `need` =
+  // pixel x0 + j received no node and needs a triangle.  (Fully unrolled: all 32 independent loads are in flight at once.)
   unsigned need = 0;
+#pragma unroll
   for (int l = 0; l < 32; ++l) {
     const int yy = wy0 + (l >> 2), xx = wx0 + (l & 3) * kLocRun + lane;
-    const bool unfilled = yy < H && xx < W && __ldg(winner + img + static_cast<size_t>(yy) * W + xx) < 0;
-    const unsigned m = __ballot_sync(0xffffffffu, unfilled);
+    const int n = (yy < H && xx < W) ? __ldg(winner + img + static_cast<size_t>(yy) * W + xx) : 0;
+    tile[l * kLocStride + lane] = -(n + 1);
+    const unsigned m = __ballot_sync(0xffffffffu, n < 0);
     if (l == lane) need = m;
   }
+  __syncwarp();
 
   const int x0 = wx0 + (lane & 3) * kLocRun;
   const int y = wy0 + (lane >> 2);
@@ -463,20 +468,18 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restric
       if (S.b1 < 0) more = min(more, floor_div_capped(S.e1 - static_cast<int>((m >> 1) & 1u), -S.b1, kLocRun));
       if (S.b2 < 0) more = min(more, floor_div_capped(S.e2 - static_cast<int>((m >> 2) & 1u), -S.b2, kLocRun));
       const int last = min(j + more, kLocRun - 1);                       // last owned column of this run
-      need &= ~((last >= 31 ? 0xffffffffu : ((2u << last) - 1u)));       // every pixel up to `last` is settled
-      for (int jj = j; jj <= last; ++jj) mine[jj] = S.t;                 // (entries of node pixels are ignored below)
+      const unsigned upto = last >= 31 ? 0xffffffffu : ((2u << last) - 1u);
+      for (unsigned e = need & upto; e; e &= e - 1) mine[__ffs(e) - 1] = S.t;  // node pixels keep their own value
+      need &= ~upto;                                                     // every pixel up to `last` is settled
     }
   }
   __syncwarp();
 
-  // ---- merge with the winners and write: row l of the staging tile is 32 consecutive pixels = one 128-byte segment
+  // ---- write the tile: row l of the staging tile is 32 consecutive pixels = one 128-byte segment
+#pragma unroll 8
   for (int l = 0; l < 32; ++l) {
     const int yy = wy0 + (l >> 2), xx = wx0 + (l & 3) * kLocRun + lane;
-    if (yy < H && xx < W) {
-      const size_t o = img + static_cast<size_t>(yy) * W + xx;
-      const int n = __ldg(winner + o);
-      loc[o] = n >= 0 ? -(n + 1) : tile[l * kLocStride + lane];
-    }
+    if (yy < H && xx < W) loc[img + static_cast<size_t>(yy) * W + xx] = tile[l * kLocStride + lane];
   }
 }
 
