@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "mesh.cuh"
+#include "select.cuh"
 #include "taps.cuh"
 
 namespace fovea {
@@ -111,41 +112,6 @@ box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int
 }
 
 // ------------------------------------------------------------------------------------------------ A9 points
-struct SelectParams {
-  int h, w, H, W, cap;
-  int scaled;           // 1: dilation runs on the nearest-downscaled mask (max(C,H,W) > 512)
-  int hs, ws;           // downscaled size
-  float dn_y, dn_x;     // H/hs, W/ws  (nearest downscale source scale)
-  float up_y, up_x;     // hs/H, ws/W  (nearest upscale source scale)
-};
-
-__device__ __forceinline__ bool invalid_at(const int32_t* win, int H, int W, int y, int x) {
-  return y >= 0 && y < H && x >= 0 && x < W && win[static_cast<size_t>(y) * W + x] < 0;
-}
-
-// dilated(y,x) of getPixelsForInterp: does the 3x3 cross around (y,x) touch an invalid pixel?
-__device__ bool dilation_covers(const int32_t* win, const SelectParams& p, int y, int x) {
-  if (!p.scaled) {
-    return invalid_at(win, p.H, p.W, y - 1, x) || invalid_at(win, p.H, p.W, y + 1, x) ||
-           invalid_at(win, p.H, p.W, y, x - 1) || invalid_at(win, p.H, p.W, y, x + 1) ||
-           invalid_at(win, p.H, p.W, y, x);
-  }
-  // nearest upscale: dilated[y][x] = dilated_s[ys][xs]
-  const int ys = min(static_cast<int>(floorf(static_cast<float>(y) * p.up_y)), p.hs - 1);
-  const int xs = min(static_cast<int>(floorf(static_cast<float>(x) * p.up_x)), p.ws - 1);
-  const int dy[5] = {0, -1, 1, 0, 0}, dx[5] = {0, 0, 0, -1, 1};
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const int yy = ys + dy[k], xx = xs + dx[k];
-    if (yy < 0 || yy >= p.hs || xx < 0 || xx >= p.ws) continue;  // conv2d zero padding
-    // nearest downscale: scaled[yy][xx] = invalid[min(floor(yy*H/hs), H-1)][...]
-    const int sy = min(static_cast<int>(floorf(static_cast<float>(yy) * p.dn_y)), p.H - 1);
-    const int sx = min(static_cast<int>(floorf(static_cast<float>(xx) * p.dn_x)), p.W - 1);
-    if (win[static_cast<size_t>(sy) * p.W + sx] < 0) return true;
-  }
-  return false;
-}
-
 constexpr int kSelThreads = 1024;
 constexpr int kSelMax = 8192;
 
@@ -167,7 +133,7 @@ select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict_
     if (win[static_cast<size_t>(v) * p.W + u] != node) continue;  // lost a collision
     const bool corner = (v == 0 || v == p.H - 1) && (u == 0 || u == p.W - 1);
     if (corner) continue;  // corners are appended below, exactly once
-    if (!dilation_covers(win, p, v, u)) continue;
+    if (!dilation_covers<false>(win, p, v, u)) continue;
     const int slot = atomicAdd(&count, 1);
     keys[slot] = (static_cast<unsigned long long>((v << 16) | u) << 32) | static_cast<unsigned>(node);
   }
@@ -756,20 +722,7 @@ extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int
     return FOVEA_ERR_CAPACITY;
   }
   SelectParams p;
-  p.h = h; p.w = w; p.H = H; p.W = W; p.cap = cap;
-  const int mx = nchan > H ? (nchan > W ? nchan : W) : (H > W ? H : W);
-  p.scaled = mx > 512;
-  p.hs = H; p.ws = W; p.dn_y = p.dn_x = p.up_y = p.up_x = 1.f;
-  if (p.scaled) {  // models/models.py:183-187, Python float (double) arithmetic then int()
-    const double dr = static_cast<double>(mx) / 512.0;
-    p.hs = static_cast<int>(static_cast<double>(H) / dr);
-    p.ws = static_cast<int>(static_cast<double>(W) / dr);
-    FOVEA_REQUIRE(p.hs > 0 && p.ws > 0, "fovea_select_points: downscaled mask is empty (%dx%d)", p.hs, p.ws);
-    p.dn_y = static_cast<float>(H) / static_cast<float>(p.hs);
-    p.dn_x = static_cast<float>(W) / static_cast<float>(p.ws);
-    p.up_y = static_cast<float>(p.hs) / static_cast<float>(H);
-    p.up_x = static_cast<float>(p.ws) / static_cast<float>(W);
-  }
+  if (int rc = make_select_params(p, h, w, H, W, nchan, cap, "fovea_select_points")) return rc;
   const int smem = kSelMax * static_cast<int>(sizeof(unsigned long long));
   FOVEA_CUDA(cudaFuncSetAttribute(select_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   select_points_kernel<<<B, kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(

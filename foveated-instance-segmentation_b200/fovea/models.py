@@ -86,17 +86,46 @@ class CompressNet(nn.Module):
         return self.conv_last(self.act(x))
 
 
+def _fill_nearest(t):
+    """interp_mode='nearest' on a CUDA tensor [C,H,W] (models/models.py:213-250, 259-272): every NaN pixel takes the value
+    of the nearest site = valid pixel with a NaN pixel directly above/below (getPixelsForInterp_NB; cv2.dilate reads the
+    [C,H,W] array as rows=C, cols=H, channels=W, so its cross never looks left/right); no forced corners."""
+    C, H, W = t.shape
+    invalid = torch.isnan(t[0])
+    valid = ~invalid
+    n = int(valid.sum())
+    if n == 0:
+        return t                                  # no site: the reference's KD-tree would fail on an empty point set
+    if n + 2 >= 65536:
+        raise FoveaError(f"fillMissingValues_tensor('nearest'): {n} valid pixels exceed the value-table limit (65533)")
+    winner = torch.full((1, H, W), -1, device=t.device, dtype=torch.int32)
+    winner[0][valid] = torch.arange(n, device=t.device, dtype=torch.int32)
+    Cs = (C + 7) // 8 * 8
+    table = torch.zeros(1, n + 2, Cs, device=t.device, dtype=torch.float32)
+    table[0, :n, :C] = t[:, valid].T
+    table[0, n] = float("nan")
+    loc = ops.nearest_locate(winner, n, 1, C)
+    plan = ops.InversePlan(winner, None, None, None, None, None, None,
+                           torch.zeros(1, 1, 16, device=t.device, dtype=torch.int32), loc, n, 1, H, W, n + 4, 1, "nearest")
+    out = torch.empty(1, C, H, W, device=t.device, dtype=torch.float32)
+    ops.inverse_fill_table(plan, table, C, zero_residual=False, scores=out)
+    t[:, invalid] = out[0][:, invalid]            # :272
+    return t
+
+
 def fillMissingValues_tensor(target_for_interp, copy=False, interp_mode="tri", triangulation="device"):
-    """models/models.py:159-286 for interp_mode='tri' on a CUDA tensor [C,H,W]; in place unless `copy`.
+    """models/models.py:159-286 for interp_mode='tri' | 'nearest' on a CUDA tensor [C,H,W]; in place unless `copy`.
 
     The NaN pattern is taken from channel 0 (the reference's own point extraction uses `mask_for_interp[0]`,
     :265, and requires the pattern to be identical across channels for its `.view(C,-1)`, :268)."""
-    if interp_mode != "tri":
-        raise NotImplementedError("only rev_deform_interp='tri' runs on the GPU path ('nearest'/'BI' are the "
-                                  "reference's host SciPy modes)")
+    if interp_mode not in ("tri", "nearest"):
+        raise NotImplementedError("rev_deform_interp='BI' (host SciPy LinearNDInterpolator) is not on the GPU path; "
+                                  "use 'tri' (the same piecewise-linear interpolant) or 'nearest'")
     t = target_for_interp.clone() if copy else target_for_interp
     if not t.is_cuda:
         raise FoveaError("fillMissingValues_tensor: expected a CUDA tensor (there is no CPU fallback)")
+    if interp_mode == "nearest":
+        return _fill_nearest(t)
     C, H, W = t.shape
     invalid = torch.isnan(t[0])
     if not bool(invalid.any()):                                                  # :254-255
@@ -262,9 +291,14 @@ class DeformSegmentationModule(SegmentationModuleBase):
 
     def inverse_upsample(self, pred, grid, segSize, zero_residual, want_mask=False):
         """grid_inv + F.grid_sample(pred, grid_inv) + NaN mask + per-sample 'tri' fill (models.py:933-940) fused."""
-        if self.cfg.MODEL.rev_deform_interp != "tri":
-            raise NotImplementedError("rev_deform_interp must be 'tri' on the GPU path")
-        plan = ops.build_inverse_plan(grid.detach(), segSize, nchan=pred.shape[1], triangulation=self.triangulation)
+        mode = self.cfg.MODEL.rev_deform_interp
+        if mode == "nearest":                      # config/deform.yaml:17
+            plan = ops.build_nearest_plan(grid.detach(), segSize, nchan=pred.shape[1])
+        elif mode == "tri":
+            plan = ops.build_inverse_plan(grid.detach(), segSize, nchan=pred.shape[1], triangulation=self.triangulation)
+        else:
+            raise NotImplementedError("rev_deform_interp must be 'tri' or 'nearest' on the GPU path ('BI' is the host "
+                                      "SciPy LinearNDInterpolator: the same interpolant as 'tri')")
         return ops.inverse_fill(plan, pred, want_scores=True, want_mask=want_mask, zero_residual=zero_residual)
 
     # -- forward ------------------------------------------------------------------------------------------------

@@ -327,6 +327,29 @@ def _locate(winner, trirec, ntri, hints, h, w, tcap):
     return loc
 
 
+def nearest_locate(winner, h, w, nchan):
+    """rev_deform_interp='nearest' (models/models.py:213-250, 259-272): per-pixel source map from the winner map alone --
+    every unfilled pixel points at the table row of its nearest interpolation site (exact integer distances)."""
+    win = _req(winner, torch.int32, "winner", 3)
+    B, H, W = win.shape
+    nbytes = int(_lib.load().fovea_nearest_workspace_bytes(B, H, W))
+    ws = torch.empty((nbytes + 3) // 4, device=win.device, dtype=torch.int32)
+    loc = torch.empty_like(win)
+    _lib.call("fovea_nearest_locate", _ptr(win), B, int(h), int(w), H, W, int(nchan), _ptr(ws), _ptr(loc), _stream())
+    return loc
+
+
+def build_nearest_plan(grid, segSize, nchan) -> InversePlan:
+    """A7 scatter + nearest-site labelling: the 'nearest' counterpart of build_inverse_plan (no triangulation)."""
+    g = _req(grid.detach(), torch.float32, "grid", 4)
+    B, h, w, _ = g.shape
+    H, W = int(segSize[0]), int(segSize[1])
+    winner = grid_inv_scatter(g, (H, W))
+    loc = nearest_locate(winner, h, w, nchan)
+    dummy = torch.zeros(1, 1, 16, device=g.device, dtype=torch.int32)   # no triangle ids in `loc`: never read
+    return InversePlan(winner, None, None, None, None, None, None, dummy, loc, h, w, H, W, h * w + 4, 1, "nearest")
+
+
 def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
     """Plan for interpolating EVERY pixel of an H x W canvas from an arbitrary site set (Interp2D, interp2d.py:37-91):
     no pixel carries a node (winner = -1 everywhere); `table_rows` is the index of the NaN row of the value table."""

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 3
+#define FOVEA_ABI_VERSION 4
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -194,6 +194,19 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
 int fovea_inverse_fill(const int32_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
                        int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
+
+/* rev_deform_interp = 'nearest' (the mode config/deform.yaml:17 ships): fillMissingValues_tensor(..., 'nearest'),
+ * models/models.py:213-250, 259-272 = getPixelsForInterp_NB + scipy NearestNDInterpolator on the host.  Produces the
+ * same per-pixel source map as fovea_locate_pixels, every entry a direct table row:
+ *   loc[b,y,x] = -(n+1)   n = the node the pixel received (winner >= 0), else the node of the NEAREST interpolation site
+ *                         (exact integer Euclidean distance; equidistant sites: smaller |dx|, then left, then upper);
+ *                         n = h*w when the image has no site at all (NaN row).
+ * Sites: filled pixels with an unfilled pixel directly above/below (on the nearest-downscaled mask when
+ * max(nchan,H,W) > 512, models.py:222-232); no forced corners.  Feed `loc` to fovea_inverse_fill (trirec is not read).
+ *   workspace: fovea_nearest_workspace_bytes(B,H,W) bytes;  H, W < 32767. */
+int64_t fovea_nearest_workspace_bytes(int B, int H, int W);
+int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, int H, int W, int nchan, void* workspace,
+                         int32_t* loc, fovea_stream_t stream);
 
 /* Diagnostic (bench.py): the store pattern of fovea_inverse_fill with no computation -- same tiling, one 128-bit
  * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout.

@@ -317,13 +317,59 @@ def fill_missing_values_tensor(t: torch.Tensor, copy: bool = False) -> torch.Ten
     return t
 
 
+def _dilate_cv2_chw(mask_u8: np.ndarray) -> np.ndarray:
+    """cv2.dilate(img[C,H,W], cross3x3, BORDER_CONSTANT 0) as getPixelsForInterp_NB calls it (models/models.py:229, 236):
+    OpenCV reads a 3-D array as (rows, cols, channels) = (C, H, W), so the cross spans the CLASS and ROW axes -- never
+    the column axis.  Restated in NumPy (cv2 is used when importable; tests assert the two agree)."""
+    try:
+        import cv2
+        k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3))
+        if mask_u8.shape[2] <= 512:                                             # CV_CN_MAX
+            return cv2.dilate(np.ascontiguousarray(mask_u8), k, borderType=cv2.BORDER_CONSTANT, borderValue=int(0))
+    except ImportError:
+        pass
+    o = mask_u8.copy()
+    o[1:] |= mask_u8[:-1]; o[:-1] |= mask_u8[1:]
+    o[:, 1:] |= mask_u8[:, :-1]; o[:, :-1] |= mask_u8[:, 1:]
+    return o
+
+
+def pixels_for_interp_nb(t: torch.Tensor):
+    """models/models.py:213-242 (getPixelsForInterp_NB) -> (mask_for_interp[C,H,W] bool ndarray, invalid ndarray)."""
+    invalid = np.isnan(t.cpu().numpy())
+    if max(invalid.shape) > 512:                                               # :222-232
+        dr = max(invalid.shape) / 512
+        shape_ori = (invalid.shape[-2], int(invalid.shape[-1]))
+        shape_scaled = (int(invalid.shape[-2] / dr), int(invalid.shape[-1] / dr))
+        scaled = F.interpolate(torch.tensor(invalid.astype("float")).unsqueeze(0), shape_scaled, mode="nearest").squeeze(0)
+        dil_s = _dilate_cv2_chw(scaled.numpy().astype("bool").astype("uint8"))
+        dil = F.interpolate(torch.tensor(dil_s.astype("float")).unsqueeze(0), shape_ori, mode="nearest").squeeze(0)
+        dilated = dil.numpy().astype("uint8")
+    else:                                                                      # :235-237
+        dilated = _dilate_cv2_chw(invalid.astype("uint8"))
+    return (dilated * ~invalid).astype("bool"), invalid                        # :240-242
+
+
+def fill_missing_values_nearest(t: torch.Tensor, copy: bool = False, return_sites: bool = False):
+    """models/models.py:159-286 with interp_mode='nearest': NearestNDInterpolator over the 3-D (class,row,col) voxels."""
+    import scipy.interpolate
+    if copy:
+        t = t.clone()
+    mask, invalid = pixels_for_interp_nb(t)
+    points = np.argwhere(mask)                                                 # :259
+    values = t[torch.from_numpy(mask)].cpu().numpy()                           # :261
+    interp = scipy.interpolate.NearestNDInterpolator(points, values)           # :245-247, :269
+    t[torch.from_numpy(invalid)] = torch.tensor(interp(np.argwhere(invalid))).float()   # :272
+    return (t, mask) if return_sites else t
+
+
 def inverse_path(pred: torch.Tensor, grid: torch.Tensor, segSize, zero_residual: bool = True,
-                 tie: str = "max") -> torch.Tensor:
+                 tie: str = "max", interp_mode: str = "tri") -> torch.Tensor:
     """A7 -> A8 -> A9 per sample (models/models.py:933-940; models_instance.py:883-893, 940)."""
     gi = grid_inverse(grid, segSize, tie=tie)
     ps = inverse_sample(pred, gi)
     for n in range(ps.shape[0]):
-        ps[n] = fill_missing_values_tensor(ps[n])
+        ps[n] = fill_missing_values_nearest(ps[n]) if interp_mode == "nearest" else fill_missing_values_tensor(ps[n])
     if zero_residual:
         ps[torch.isnan(ps)] = 0                                                # models_instance.py:940
     return ps

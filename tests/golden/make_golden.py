@@ -190,3 +190,20 @@ def case_module(name, upsample, H=256, W=256, B=2, seed=11):
 if __name__ == "__main__" and "--module" in sys.argv:
     case_module("module_256_lowres", upsample=False)
     case_module("module_256_upsample", upsample=True)
+
+
+def case_nearest(name, src_name):
+    """fillMissingValues_tensor(..., interp_mode='nearest') of the UNMODIFIED reference (models/models.py:213-272: cv2.dilate
+    site selection + SciPy NearestNDInterpolator on the host) on the NaN-masked tensors of an existing inverse fixture."""
+    src = np.load(os.path.join(HERE, src_name + ".npz"))
+    ps_nan = torch.from_numpy(src["pred_sampled_nan"])
+    out = ps_nan.clone()
+    for n in range(out.shape[0]):
+        out[n] = rm.fillMissingValues_tensor(out[n], interp_mode="nearest")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pred_sampled_nearest=out.numpy(), source=np.array(src_name))
+    print(name, out.shape, "nan left:", int(torch.isnan(out).sum()))
+
+
+if __name__ == "__main__" and "--nearest" in sys.argv:
+    case_nearest("nearest_80_to_128", "inverse_80_to_128")
+    case_nearest("nearest_80_to_520", "inverse_80_to_520")

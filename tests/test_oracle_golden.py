@@ -114,3 +114,32 @@ def test_a8_is_two_by_two_box_average():
     got = ps[0, :, ys, xs]
     want = box[0].reshape(3, -1)[:, win[ys, xs]]
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,src", [("nearest_80_to_128", "inverse_80_to_128"), ("nearest_80_to_520", "inverse_80_to_520")])
+def test_nearest_fill_matches_reference(golden_dir, name, src):
+    """interp_mode='nearest' (models/models.py:213-272) of the oracle == the unmodified reference, bit for bit."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    s = np.load(os.path.join(golden_dir, src + ".npz"))
+    want = torch.from_numpy(g["pred_sampled_nearest"])
+    for n in range(want.shape[0]):
+        got = rp.fill_missing_values_nearest(torch.from_numpy(s["pred_sampled_nan"][n]).clone())
+        assert torch.equal(got, want[n])
+
+
+def test_cv2_dilate_reads_chw_as_rows_cols_channels():
+    """The reading of getPixelsForInterp_NB that the 'nearest' kernels implement: cv2.dilate on a [C,H,W] array spans the
+    class and row axes, never the column axis (so with one NaN pattern in every class only vertical neighbours count)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(0)
+    a = (rng.rand(5, 40, 37) > 0.9).astype("uint8")
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3))
+    d = cv2.dilate(a, k, borderType=cv2.BORDER_CONSTANT, borderValue=int(0))
+    o = a.copy()
+    o[1:] |= a[:-1]; o[:-1] |= a[1:]
+    o[:, 1:] |= a[:, :-1]; o[:, :-1] |= a[:, 1:]
+    assert np.array_equal(d, o)
+    b = np.repeat(a[:1], 5, 0)
+    v = b.copy()
+    v[:, 1:] |= b[:, :-1]; v[:, :-1] |= b[:, 1:]
+    assert np.array_equal(cv2.dilate(b, k, borderType=cv2.BORDER_CONSTANT, borderValue=int(0)), v)

@@ -310,3 +310,77 @@ def test_inverse_fill_full_resolution_1024(ops):
     lin = 0.5 * scores + 2.0 * s2
     assert (s12 - lin).abs().max() <= 1e-5 * lin.abs().max()
     assert torch.equal(torch.argmax(scores, dim=1), mask)
+
+
+# ---------------------------------------------------------------------------------------------- 'nearest' mode
+def _check_nearest(ops, pred, grid, seg, C, want=None):
+    """Every unfilled pixel must carry the value of A nearest site (exact integer distance); where the nearest site is
+    unique the result must equal the reference's (its KD-tree picks arbitrarily among equidistant sites)."""
+    from scipy.spatial import cKDTree
+    B = grid.shape[0]
+    plan = ops.build_nearest_plan(grid.cuda(), seg, nchan=C)
+    scores, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=True, want_mask=True, zero_residual=False)
+    table = ops.box4_table(pred.cuda()).cpu()
+    win = plan.winner.cpu().numpy()
+    loc = plan.loc.cpu().numpy()
+    scores = scores.cpu()
+    ps_nan = rp.inverse_sample(pred, rp.grid_inverse(grid, seg, tie="max"))
+    n_tie = 0
+    for b in range(B):
+        sites_mask, invalid = rp.pixels_for_interp_nb(ps_nan[b])
+        sites = np.argwhere(sites_mask[0])
+        tree = cKDTree(sites)
+        q = np.argwhere(invalid[0])
+        dmin, _ = tree.query(q)
+        node = -(loc[b][invalid[0]]) - 1                       # chosen table row per unfilled pixel
+        assert (node >= 0).all() and (node < grid.shape[1] * grid.shape[2]).all()
+        # where does each node sit?  (the winner map is its inverse)
+        pos = np.full((grid.shape[1] * grid.shape[2], 2), -1, dtype=np.int64)
+        wy, wx = np.where(win[b] >= 0)
+        pos[win[b][wy, wx]] = np.stack([wy, wx], 1)
+        chosen = pos[node]
+        assert sites_mask[0][chosen[:, 0], chosen[:, 1]].all(), "chose a pixel that is not an interpolation site"
+        d2 = ((chosen - q) ** 2).sum(1)
+        assert np.array_equal(d2, np.rint(dmin ** 2).astype(np.int64)), "not a nearest site"
+        # values: the chosen node's table row, bit for bit; filled pixels keep their own
+        got = scores[b][:, torch.from_numpy(invalid[0])]
+        assert torch.equal(got, table[b, torch.from_numpy(node), :C].T)
+        keep = ~invalid[0]
+        assert torch.equal(scores[b][:, torch.from_numpy(keep)], table[b, torch.from_numpy(win[b][keep]), :C].T)
+        if want is not None:
+            diff = ((scores[b] - want[b]).abs() > 1e-5 * want[b].abs().max()).any(0).numpy()   # (A8 values: 1e-5 bar)
+            cnt = np.array([len(c) for c in tree.query_ball_point(q, dmin + 1e-9)])
+            tie_map = np.zeros_like(invalid[0])
+            tie_map[invalid[0]] = cnt > 1
+            assert not (diff & ~tie_map).any(), "differs from the reference away from equidistant sites"
+            n_tie += int(diff.sum())
+    assert torch.equal(torch.argmax(scores.cuda(), dim=1), mask)
+    return n_tie
+
+
+@pytest.mark.parametrize("name,src,grid_name,C", [("nearest_80_to_128", "inverse_80_to_128", "grid_80_R45", 5),
+                                                  ("nearest_80_to_520", "inverse_80_to_520", "grid_80_R45_seg520", 2)])
+def test_nearest_fill_matches_reference_golden(ops, golden_dir, name, src, grid_name, C):
+    g, s, gg = _load(golden_dir, name), _load(golden_dir, src), _load(golden_dir, grid_name)
+    grid, pred = torch.from_numpy(s["grid"]), torch.from_numpy(s["pred"])
+    seg = tuple(int(v) for v in gg["segSize"])
+    # exact check against the oracle with the documented A7 collision rule (largest node wins; the reference's own
+    # index_put leaves the winner of duplicate targets undefined) ...
+    want = rp.inverse_path(pred, grid, seg, zero_residual=False, tie="max", interp_mode="nearest")
+    n_tie = _check_nearest(ops, pred, grid, seg, C, want=want)
+    print(f"{name}: {n_tie} pixels differ from the oracle, all at equidistant sites")
+    # ... and against the unmodified reference's output: everything but equidistant-site ties and collision pixels
+    plan = ops.build_nearest_plan(grid.cuda(), seg, nchan=C)
+    scores, _ = ops.inverse_fill(plan, pred.cuda(), zero_residual=False)
+    ref = torch.from_numpy(g["pred_sampled_nearest"])
+    close = ((scores.cpu() - ref).abs() <= 1e-5 * ref.abs().max()).all(1).float().mean().item()
+    print(f"{name}: {close:.4f} of the pixels equal the reference's own output")
+    assert close > 0.8
+
+
+def test_nearest_fill_full_resolution_1024(ops):
+    B, C, H, W = 2, 51, 1024, 1024
+    xs, _ = rp.synthetic_saliency(B, seed=31)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    _check_nearest(ops, rp.synthetic_pred(B, C, seed=31), grid, (H, W), C)
