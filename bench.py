@@ -329,7 +329,7 @@ def main():
         return 4.0 * C * H * W * B / (min(times) * 1e-3) / 1e9
 
     store_ceiling = probe(None)
-    # the same stores preceded by a 4-byte-per-pixel read (what the fill kernel's `loc` map costs at the DRAM)
+    # the same stores preceded by the 2-byte-per-pixel read of the fill kernel's `loc` map (its cost at the DRAM)
     store_read_ceiling = probe(torch.zeros(B, H, W, device=dev, dtype=torch.int32))
 
     traffic = None
@@ -361,7 +361,7 @@ def main():
                          "timed_in": "the serial-schedule region (kernel alone on the GPU, events on its stream)",
                          "ms_per_launch_overlapped": fill_ms_overlapped,
                          "store_only_ceiling_gbs": store_ceiling,
-                         "store_plus_4B_per_px_read_ceiling_gbs": store_read_ceiling},
+                         "store_plus_loc_read_ceiling_gbs": store_read_ceiling},
         }
         if e2e:
             line["e2e"] = e2e

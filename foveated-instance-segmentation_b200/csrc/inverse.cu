@@ -236,6 +236,14 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__
 //   loc[b,y,x] = -(n+1)    : the pixel received low-res node n directly        (models/models.py:650-651);
 //                            n == h*w: no value (outside the triangulation)    -> the NaN row of the value table
 
+// `loc` is stored in 16 bits per pixel (the fill kernel's only per-pixel read stream: halving it is worth 6 % of the
+// store bandwidth, measured with fovea_probe_store_ceiling): bit 15 clear = triangle id (< 32768), bit 15 set = direct
+// table row n (< 32768).  In-kernel the signed form is used: t >= 0, or -(n+1).
+__device__ __forceinline__ uint16_t encode_loc(int v) {
+  return static_cast<uint16_t>(v >= 0 ? v : (0x8000 | (-v - 1)));
+}
+__device__ __forceinline__ int decode_loc(unsigned v) { return (v & 0x8000u) ? -static_cast<int>(v & 0x7FFFu) - 1 : static_cast<int>(v); }
+
 // ---- per-triangle setup records ------------------------------------------------------------------------------
 // Everything the walkers and the fill need about a triangle, derived once per triangle from (mesh, pts, src) instead
 // of once per visit: one 64-byte record = four independent 16-byte loads, no pts/src indirection.
@@ -353,7 +361,7 @@ __device__ __forceinline__ int floor_div_capped(int num, int den, int cap) {
 // the winners and written with coalesced 128-byte rows.
 __global__ void __launch_bounds__(kLocThreads)
 locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restrict__ trirec,
-                     const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints, int32_t* __restrict__ loc,
+                     const int32_t* __restrict__ ntri, const int32_t* __restrict__ hints, uint16_t* __restrict__ loc,
                      int hw, int H, int W, int tcap) {
   __shared__ int tile_all[kLocThreads / 32][32 * kLocStride];
   const int b = blockIdx.z;
@@ -445,7 +453,7 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restric
 #pragma unroll 8
   for (int l = 0; l < 32; ++l) {
     const int yy = wy0 + (l >> 2), xx = wx0 + (l & 3) * kLocRun + lane;
-    if (yy < H && xx < W) loc[img + static_cast<size_t>(yy) * W + xx] = tile[l * kLocStride + lane];
+    if (yy < H && xx < W) loc[img + static_cast<size_t>(yy) * W + xx] = encode_loc(tile[l * kLocStride + lane]);
   }
 }
 
@@ -506,7 +514,7 @@ __device__ __forceinline__ void ldg3_if<8>(Rows<8>& r, unsigned long long pa, un
 // (exact integer edge functions, stepped in registers while the triangle does not change), then stream all channels
 // with 128-bit stores.  Table rows are re-loaded only where they differ from the previous pixel's.
 template <bool kScores, bool kMask, int G>
-__device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const TriRec* __restrict__ trirec,
+__device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, const TriRec* __restrict__ trirec,
                                           const float* __restrict__ table, float* __restrict__ scores,
                                           long long* __restrict__ mask, const FillParams& p, int b, int x0, int y) {
   const int hw = p.h * p.w;
@@ -514,8 +522,8 @@ __device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const
   const size_t plane = static_cast<size_t>(p.H) * p.W;
   const TriRec* recs = trirec + static_cast<size_t>(b) * p.tcap;
 
-  const int4 l4 = __ldcs(reinterpret_cast<const int4*>(loc + static_cast<size_t>(b) * plane + pixoff));
-  const int lc[4] = {l4.x, l4.y, l4.z, l4.w};
+  const uint2 l2 = __ldcs(reinterpret_cast<const uint2*>(loc + static_cast<size_t>(b) * plane + pixoff));  // 4 x 16 bit
+  const int lc[4] = {decode_loc(l2.x & 0xFFFFu), decode_loc(l2.x >> 16), decode_loc(l2.y & 0xFFFFu), decode_loc(l2.y >> 16)};
   unsigned nd0[4], nd1[4], nd2[4];  // table rows (node ids) of the three vertices of each pixel
   float w0[4], w1[4], w2[4];        // barycentric weights ((1,0,0) for a pixel that received a node)
   unsigned nanmask = 0;             // pixels whose value is NaN in every channel
@@ -624,7 +632,7 @@ __device__ __forceinline__ void fill_tile(const int32_t* __restrict__ loc, const
 // there is no such reuse).
 template <bool kScores, bool kMask, int G>
 __global__ void __launch_bounds__(kFillThreads, (G == 8 ? 2 : 4) * 256 / kFillThreads)
-inverse_fill_kernel(const int32_t* __restrict__ loc, const TriRec* __restrict__ trirec, const float* __restrict__ table,
+inverse_fill_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__ trirec, const float* __restrict__ table,
                     float* __restrict__ scores, long long* __restrict__ mask, FillParams p) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -650,9 +658,9 @@ store_ceiling_kernel(float* __restrict__ scores, const int4* __restrict__ side_r
   const size_t pix = static_cast<size_t>(y) * W + x0;
   float* o = scores + static_cast<size_t>(b) * C * plane + pix;
   float f = static_cast<float>(lane);
-  if (side_read) {  // the 4-byte-per-pixel read stream the fill kernel carries (its `loc` map)
-    const int4 l = __ldcs(side_read + (static_cast<size_t>(b) * plane + pix) / 4);
-    f += static_cast<float>(l.x ^ l.y ^ l.z ^ l.w);
+  if (side_read) {  // the 2-byte-per-pixel read stream the fill kernel carries (its `loc` map)
+    const int2 l = __ldcs(reinterpret_cast<const int2*>(side_read) + (static_cast<size_t>(b) * plane + pix) / 4);
+    f += static_cast<float>(l.x ^ l.y);
   }
   for (int c = 0; c < C; ++c, o += plane) __stcs(reinterpret_cast<float4*>(o), make_float4(f, f + 1.f, f + 2.f, f + 3.f));
 }
@@ -763,11 +771,12 @@ extern "C" int fovea_triangle_setup(const int32_t* pts, const int32_t* src, cons
 }
 
 extern "C" int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t* ntri,
-                                   const int32_t* hints, int B, int h, int w, int H, int W, int tcap, int32_t* loc,
+                                   const int32_t* hints, int B, int h, int w, int H, int W, int tcap, uint16_t* loc,
                                    fovea_stream_t stream) {
   FOVEA_REQUIRE(winner && trirec && ntri && hints && loc, "fovea_locate_pixels: null pointer");
   FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1, "fovea_locate_pixels: bad sizes");
   FOVEA_REQUIRE(H <= 16384 && W <= 16384, "fovea_locate_pixels: canvas side must be <= 16384");
+  FOVEA_REQUIRE(tcap <= 32768 && h * w < 32767, "fovea_locate_pixels: triangle ids / table rows must fit 15 bits");
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kLocTileH) <= 65535, "fovea_locate_pixels: B or H too large for the grid");
   dim3 grid(ceil_div(W, kLocTileW), ceil_div(H, kLocTileH), B);
   locate_pixels_kernel<<<grid, kLocThreads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -784,7 +793,7 @@ static bool fill_wide_requested() {
 }
 
 template <int G>
-static int launch_fill(const int32_t* loc, const TriRec* recs, const float* table, float* scores, long long* mk,
+static int launch_fill(const uint16_t* loc, const TriRec* recs, const float* table, float* scores, long long* mk,
                        const FillParams& p, int B, cudaStream_t s) {
   dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH * kFillTilesY), B);
   if (scores && mk)
@@ -796,7 +805,7 @@ static int launch_fill(const int32_t* loc, const TriRec* recs, const float* tabl
   return check_launch("fovea_inverse_fill");
 }
 
-extern "C" int fovea_inverse_fill(const int32_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h,
+extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h,
                                   int w, int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask,
                                   fovea_stream_t stream) {
   FOVEA_REQUIRE(loc && trirec && table, "fovea_inverse_fill: null pointer");
@@ -806,8 +815,8 @@ extern "C" int fovea_inverse_fill(const int32_t* loc, const void* trirec, const 
   FOVEA_REQUIRE(W % 4 == 0, "fovea_inverse_fill: W=%d must be a multiple of 4 (128-bit stores)", W);
   FOVEA_REQUIRE(H <= 16384 && W <= 16384, "fovea_inverse_fill: canvas side must be <= 16384");
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_inverse_fill: B or H too large for the grid");
-  FOVEA_REQUIRE(static_cast<long long>(h) * w + 2 < 65536 && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
-                "fovea_inverse_fill: value table too large (rows must fit 16 bits, bytes 32 bits)");
+  FOVEA_REQUIRE(static_cast<long long>(h) * w + 2 <= 32768 && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
+                "fovea_inverse_fill: value table too large (rows must fit 15 bits, bytes 32 bits)");
   FillParams p{C, Cs, h, w, H, W, 0, tcap, zero_residual};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const TriRec* recs = static_cast<const TriRec*>(trirec);

@@ -62,7 +62,7 @@ nearest_columns_kernel(const int32_t* __restrict__ winner, short* __restrict__ g
 }
 
 __global__ void __launch_bounds__(256)
-nearest_rows_kernel(const int32_t* __restrict__ winner, const short* __restrict__ g, int32_t* __restrict__ loc,
+nearest_rows_kernel(const int32_t* __restrict__ winner, const short* __restrict__ g, uint16_t* __restrict__ loc,
                     int hw, int H, int W) {
   const int b = blockIdx.z, y = blockIdx.y;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,7 +70,7 @@ nearest_rows_kernel(const int32_t* __restrict__ winner, const short* __restrict_
   const size_t row = (static_cast<size_t>(b) * H + y) * W;
   const int n = winner[row + x];
   if (n >= 0) {  // a filled pixel keeps its own value
-    loc[row + x] = -(n + 1);
+    loc[row + x] = static_cast<uint16_t>(0x8000 | n);
     return;
   }
   const short* gr = g + row;
@@ -93,9 +93,9 @@ nearest_rows_kernel(const int32_t* __restrict__ winner, const short* __restrict_
       if (d < best) { best = d; bx = xr; bdy = dr; }
     }
   }
-  int out = -(hw + 1);  // no site anywhere: the NaN row of the value table
-  if (bx >= 0) out = -(winner[(static_cast<size_t>(b) * H + (y + bdy)) * W + bx] + 1);
-  loc[row + x] = out;
+  int out = hw;  // no site anywhere: the NaN row of the value table
+  if (bx >= 0) out = winner[(static_cast<size_t>(b) * H + (y + bdy)) * W + bx];
+  loc[row + x] = static_cast<uint16_t>(0x8000 | out);   // 16-bit source map: bit 15 = direct table row
 }
 
 }  // namespace fovea
@@ -107,10 +107,11 @@ extern "C" int64_t fovea_nearest_workspace_bytes(int B, int H, int W) {
 }
 
 extern "C" int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
-                                    void* workspace, int32_t* loc, fovea_stream_t stream) {
+                                    void* workspace, uint16_t* loc, fovea_stream_t stream) {
   FOVEA_REQUIRE(winner && workspace && loc, "fovea_nearest_locate: null pointer");
   FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "fovea_nearest_locate: bad sizes");
   FOVEA_REQUIRE(H < 32767 && W < 32767 && B <= 65535 && H <= 65535, "fovea_nearest_locate: canvas or batch too large");
+  FOVEA_REQUIRE(h * w < 32767, "fovea_nearest_locate: table rows must fit 15 bits (h*w=%d)", h * w);
   SelectParams p;
   if (int rc = make_select_params(p, h, w, H, W, nchan, 0, "fovea_nearest_locate")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

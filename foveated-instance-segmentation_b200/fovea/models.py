@@ -96,8 +96,8 @@ def _fill_nearest(t):
     n = int(valid.sum())
     if n == 0:
         return t                                  # no site: the reference's KD-tree would fail on an empty point set
-    if n + 2 >= 65536:
-        raise FoveaError(f"fillMissingValues_tensor('nearest'): {n} valid pixels exceed the value-table limit (65533)")
+    if n + 2 > 32768:
+        raise FoveaError(f"fillMissingValues_tensor('nearest'): {n} valid pixels exceed the value-table limit (32766)")
     winner = torch.full((1, H, W), -1, device=t.device, dtype=torch.int32)
     winner[0][valid] = torch.arange(n, device=t.device, dtype=torch.int32)
     Cs = (C + 7) // 8 * 8

@@ -207,7 +207,7 @@ class InversePlan:
     ntri: torch.Tensor     # [B] int32
     hints: torch.Tensor    # [B,ceil(H/8),ceil(W/32)] int32 walk-start triangles
     trirec: torch.Tensor   # [B,tcap,16] int32: 64-byte per-triangle setup records (edge functions, 1/area, rows)
-    loc: torch.Tensor      # [B,H,W] int32 per-pixel source: triangle id, or -(node+1)
+    loc: torch.Tensor      # [B,H,W] uint16 per-pixel source: triangle id, or 0x8000 | table row
     h: int
     w: int
     H: int
@@ -321,7 +321,7 @@ def _locate(winner, trirec, ntri, hints, h, w, tcap):
     B, H, W = winner.shape
     if W % 4:
         raise FoveaError(f"canvas width {W} must be a multiple of 4 (128-bit accesses)")
-    loc = torch.empty_like(winner)
+    loc = torch.empty(B, H, W, device=winner.device, dtype=torch.int16)    # uint16 bit patterns
     _lib.call("fovea_locate_pixels", _ptr(winner), _ptr(trirec), _ptr(ntri), _ptr(hints), B, h, w, H, W, tcap,
               _ptr(loc), _stream())
     return loc
@@ -334,7 +334,7 @@ def nearest_locate(winner, h, w, nchan):
     B, H, W = win.shape
     nbytes = int(_lib.load().fovea_nearest_workspace_bytes(B, H, W))
     ws = torch.empty((nbytes + 3) // 4, device=win.device, dtype=torch.int32)
-    loc = torch.empty_like(win)
+    loc = torch.empty(B, H, W, device=win.device, dtype=torch.int16)    # uint16 bit patterns
     _lib.call("fovea_nearest_locate", _ptr(win), B, int(h), int(w), H, W, int(nchan), _ptr(ws), _ptr(loc), _stream())
     return loc
 
@@ -410,7 +410,7 @@ def probe_store_ceiling(scores, side_read=None):
     s = _req(scores, torch.float32, "scores", 4)
     B, Cc, H, W = s.shape
     if side_read is not None:
-        side_read = _req(side_read, torch.int32, "side_read", 3)
+        side_read = _req(side_read, torch.int32, "side_read", 3)     # only its first 2*B*H*W bytes are read
     _lib.call("fovea_probe_store_ceiling", _ptr(s), _ptr(side_read), B, Cc, H, W, _stream())
 
 

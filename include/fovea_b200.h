@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 4
+#define FOVEA_ABI_VERSION 5
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -171,16 +171,16 @@ int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t*
 
 /* A9 point location, interp2d.py:58 (Delaunay.find_simplex over every pixel, spatial/qhull.pyx:2075-2163), merged
  * with the A7 winners into one per-pixel source map -- a function of the sampling grid only (not of the scores):
- *   loc[b,y,x] >= 0      id of the mesh triangle that owns pixel (y,x).  A pixel exactly on an edge belongs to
- *                        the triangle a top-left fill rule picks (csrc/mesh.cuh), so the map does not depend on
- *                        walk order;
- *   loc[b,y,x] = -(n+1)  the pixel received low-res node n directly (winner[b,y,x] = n);  n = h*w: the pixel has no
- *                        value (outside the triangulation / empty mesh) and reads the NaN row of the value table.
+ * 16 bits per pixel (this map is the fill kernel's only per-pixel read stream):
+ *   bit 15 clear: loc = id of the mesh triangle that owns pixel (y,x).  A pixel exactly on an edge belongs to the
+ *                 triangle a top-left fill rule picks (csrc/mesh.cuh), so the map does not depend on walk order;
+ *   bit 15 set:   loc & 0x7FFF = n: the pixel received low-res node n directly (winner[b,y,x] = n);  n = h*w: the
+ *                 pixel has no value (outside the triangulation / empty mesh) and reads the NaN row of the value table.
  *   winner [B,H,W] int32 from fovea_grid_inv_scatter (all -1 = interpolate every pixel, Interp2D);  trirec from
- *   fovea_triangle_setup;  hints from fovea_locate_hints;  loc [B,H,W] int32 (a separate buffer: must not alias
- *   winner);  H, W <= 16384. */
+ *   fovea_triangle_setup;  hints from fovea_locate_hints;  loc [B,H,W] uint16;  H, W <= 16384, tcap <= 32768,
+ *   h*w < 32767. */
 int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t* ntri, const int32_t* hints, int B,
-                        int h, int w, int H, int W, int tcap, int32_t* loc, fovea_stream_t stream);
+                        int h, int w, int H, int W, int tcap, uint16_t* loc, fovea_stream_t stream);
 
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
  * fillMissingValues_tensor(..., 'tri') = Interp2D barycentric gather (models/models.py:939-940,
@@ -188,30 +188,30 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
  * (models/models.py:1044), in ONE pass over the full-resolution canvas: the score tensor is written exactly once.
  *   loc    [B,H,W] from fovea_locate_pixels
  *   trirec [B,tcap,16] from fovea_triangle_setup
- *   table  [B, h*w+2, Cs] from fovea_box4_table   (h*w+2 < 65536)
+ *   table  [B, h*w+2, Cs] from fovea_box4_table   (h*w+2 <= 32768)
  *   scores [B,C,H,W] fp32   (NULL = do not materialise)
  *   mask   [B,H,W]  int64   (NULL = do not compute)
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
-int fovea_inverse_fill(const int32_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
+int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
                        int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
 
 /* rev_deform_interp = 'nearest' (the mode config/deform.yaml:17 ships): fillMissingValues_tensor(..., 'nearest'),
  * models/models.py:213-250, 259-272 = getPixelsForInterp_NB + scipy NearestNDInterpolator on the host.  Produces the
  * same per-pixel source map as fovea_locate_pixels, every entry a direct table row:
- *   loc[b,y,x] = -(n+1)   n = the node the pixel received (winner >= 0), else the node of the NEAREST interpolation site
- *                         (exact integer Euclidean distance; equidistant sites: smaller |dx|, then left, then upper);
- *                         n = h*w when the image has no site at all (NaN row).
+ *   loc[b,y,x] = 0x8000 | n   n = the node the pixel received (winner >= 0), else the node of the NEAREST interpolation
+ *                         site (exact integer Euclidean distance; equidistant sites: smaller |dx|, then left, then
+ *                         upper);  n = h*w when the image has no site at all (NaN row).
  * Sites: filled pixels with an unfilled pixel directly above/below (on the nearest-downscaled mask when
  * max(nchan,H,W) > 512, models.py:222-232); no forced corners.  Feed `loc` to fovea_inverse_fill (trirec is not read).
  *   workspace: fovea_nearest_workspace_bytes(B,H,W) bytes;  H, W < 32767. */
 int64_t fovea_nearest_workspace_bytes(int B, int H, int W);
 int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, int H, int W, int nchan, void* workspace,
-                         int32_t* loc, fovea_stream_t stream);
+                         uint16_t* loc, fovea_stream_t stream);
 
 /* Diagnostic (bench.py): the store pattern of fovea_inverse_fill with no computation -- same tiling, one 128-bit
  * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout.
- * side_read (may be NULL): a [B,H,W] int32 buffer read once, 16 bytes per thread, like the fill kernel's `loc` map --
- * shows what a 2 % read stream mixed into the write stream costs at the DRAM. */
+ * side_read (may be NULL): a buffer of >= 2*B*H*W bytes read once, 8 bytes per thread, like the fill kernel's 16-bit
+ * `loc` map -- shows what a 1 % read stream mixed into the write stream costs at the DRAM. */
 int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, int C, int H, int W,
                               fovea_stream_t stream);
 

@@ -322,7 +322,7 @@ def _check_nearest(ops, pred, grid, seg, C, want=None):
     scores, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=True, want_mask=True, zero_residual=False)
     table = ops.box4_table(pred.cuda()).cpu()
     win = plan.winner.cpu().numpy()
-    loc = plan.loc.cpu().numpy()
+    loc = plan.loc.cpu().numpy().view(np.uint16)
     scores = scores.cpu()
     ps_nan = rp.inverse_sample(pred, rp.grid_inverse(grid, seg, tie="max"))
     n_tie = 0
@@ -332,7 +332,8 @@ def _check_nearest(ops, pred, grid, seg, C, want=None):
         tree = cKDTree(sites)
         q = np.argwhere(invalid[0])
         dmin, _ = tree.query(q)
-        node = -(loc[b][invalid[0]]) - 1                       # chosen table row per unfilled pixel
+        assert (loc[b][invalid[0]].astype(np.int64) & 0x8000).all()        # every entry is a direct table row
+        node = loc[b][invalid[0]].astype(np.int64) & 0x7FFF    # chosen table row per unfilled pixel
         assert (node >= 0).all() and (node < grid.shape[1] * grid.shape[2]).all()
         # where does each node sit?  (the winner map is its inverse)
         pos = np.full((grid.shape[1] * grid.shape[2], 2), -1, dtype=np.int64)
