@@ -18,7 +18,7 @@ namespace fovea {
 // u = int(((gx+1)/2)*(W-1)), v = int(((gy+1)/2)*(H-1))  -- models/models.py:644-645, fp32 op for op.
 __device__ __forceinline__ int target_coord(float g, int size) {
   const float f = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), static_cast<float>(size - 1));
-  return __float2int_rz(f);
+  return f == f ? __float2int_rz(f) : -1;  // NaN (cvt.rzi gives 0): lands nowhere, like any out-of-range target
 }
 
 __global__ void grid_inv_scatter_kernel(const float2* __restrict__ grid, int32_t* __restrict__ winner, int B, int hw,
@@ -259,7 +259,7 @@ struct TriRec {
 
 __global__ void __launch_bounds__(256)
 triangle_setup_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__ src, const uint4* __restrict__ mesh,
-                      const int32_t* __restrict__ ntri, TriRec* __restrict__ recs, int cap, int tcap) {
+                      const int32_t* __restrict__ ntri, TriRec* __restrict__ recs, int cap, int tcap, int nan_row) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntri[b]) return;
@@ -273,6 +273,8 @@ triangle_setup_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict
   const int area2 = (c[1] - c[0]) * (r[2] - r[0]) - (r[1] - r[0]) * (c[2] - c[0]);  // orient(p0,p1,p2)
   const int s = area2 < 0 ? -1 : 1;
   const unsigned nb[3] = {n0, n1, n2};
+  const int s0 = __ldg(srcb + i0), s1 = __ldg(srcb + i1), s2 = __ldg(srcb + i2);
+  const bool nan_me = s0 == nan_row || s1 == nan_row || s2 == nan_row;  // a vertex without a value (unfilled corner)
   int A[3], Bc[3], Cc[3];
   unsigned m = 0;
 #pragma unroll
@@ -282,7 +284,17 @@ triangle_setup_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict
     A[i] = s * dc;
     Bc[i] = -s * dr;
     Cc[i] = s * (dr * ac - dc * ar);
-    const bool tie_owned = nb[i] == kNoTri || (dr != 0 ? (s * dr > 0) : (s * dc > 0));  // mesh.cuh edge_owned at e == 0
+    // Who owns a pixel lying EXACTLY on this edge?  Hull edge: this triangle.  One side has a vertex without a value
+    // and the other has not: the side that can produce a value (the reference's eps-tolerant walk accepts either;
+    // coming from the filled region it meets the finite one, e.g. the row of the last nodes above an unfilled image
+    // corner).  Otherwise the top-left rule of mesh.cuh (edge_owned at e == 0).
+    bool tie_owned = true;
+    if (nb[i] != kNoTri) {
+      const uint4 qn = __ldg(mesh + static_cast<size_t>(b) * tcap + nb[i]);
+      const bool nan_nb = __ldg(srcb + (qn.x & 0xFFFFu)) == nan_row || __ldg(srcb + (qn.x >> 16)) == nan_row ||
+                          __ldg(srcb + (qn.y & 0xFFFFu)) == nan_row;
+      tie_owned = nan_me != nan_nb ? !nan_me : (dr != 0 ? (s * dr > 0) : (s * dc > 0));
+    }
     if (!tie_owned) m |= 1u << i;
   }
   const int area = area2 < 0 ? -area2 : area2;
@@ -291,8 +303,8 @@ triangle_setup_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict
   R.q0 = make_uint4(A[0], Bc[0], Cc[0], A[1]);
   R.q1 = make_uint4(Bc[1], Cc[1], A[2], Bc[2]);
   R.q2 = make_uint4(Cc[2], n0 | (n1 << 16), n2 | (m << 16), area);
-  R.q3 = make_uint4(static_cast<unsigned>(__ldg(srcb + i0)) | (static_cast<unsigned>(__ldg(srcb + i1)) << 16),
-                    static_cast<unsigned>(__ldg(srcb + i2)), static_cast<unsigned>(__double2loint(inv)),
+  R.q3 = make_uint4(static_cast<unsigned>(s0) | (static_cast<unsigned>(s1) << 16), static_cast<unsigned>(s2),
+                    static_cast<unsigned>(__double2loint(inv)),
                     static_cast<unsigned>(__double2hiint(inv)));
   recs[static_cast<size_t>(b) * tcap + t] = R;
 }
@@ -759,14 +771,15 @@ extern "C" int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const
 }
 
 extern "C" int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t* mesh, const int32_t* ntri,
-                                    int B, int cap, int tcap, int max_coord, void* trirec, fovea_stream_t stream) {
+                                    int B, int cap, int tcap, int max_coord, int nan_row, void* trirec,
+                                    fovea_stream_t stream) {
   FOVEA_REQUIRE(pts && src && mesh && ntri && trirec && B > 0 && cap > 0 && tcap > 0, "fovea_triangle_setup: bad arguments");
   FOVEA_REQUIRE(max_coord > 0 && max_coord <= 16384,
                 "fovea_triangle_setup: coordinates must be < 16384 for exact int32 edge functions (got %d)", max_coord);
   FOVEA_REQUIRE(B <= 65535, "fovea_triangle_setup: B too large for the grid");
   dim3 grid(ceil_div(tcap, 256), B);
   triangle_setup_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      pts, src, reinterpret_cast<const uint4*>(mesh), ntri, static_cast<TriRec*>(trirec), cap, tcap);
+      pts, src, reinterpret_cast<const uint4*>(mesh), ntri, static_cast<TriRec*>(trirec), cap, tcap, nan_row);
   return check_launch("fovea_triangle_setup");
 }
 

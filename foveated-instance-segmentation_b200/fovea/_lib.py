@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class FoveaError(RuntimeError):
@@ -44,7 +44,7 @@ PROTOTYPES = {
     "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_locate_hints_workspace_bytes": (_i64, [_i, _i, _i]),
     "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_nearest_workspace_bytes": (_i64, [_i, _i, _i]),

@@ -276,7 +276,7 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
     hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
-    trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W))
+    trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), h * w)
     loc = _locate(winner, trirec, ntri, hints, h, w, tcap)
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, h, w, H, W, cap, tcap, triangulation)
 
@@ -307,12 +307,12 @@ def _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W):
     return hints
 
 
-def _triangle_setup(pts, src, mesh, ntri, cap, tcap, max_coord):
+def _triangle_setup(pts, src, mesh, ntri, cap, tcap, max_coord, nan_row):
     """Per-triangle setup records (edge functions, tie bits, 1/area, value rows) for the walkers and the fill."""
     B = pts.shape[0]
     trirec = torch.empty(B, tcap, 16, device=pts.device, dtype=torch.int32)
     _lib.call("fovea_triangle_setup", _ptr(pts), _ptr(src), _ptr(mesh), _ptr(ntri), B, cap, tcap, int(max_coord),
-              _ptr(trirec), _stream())
+              int(nan_row), _ptr(trirec), _stream())
     return trirec
 
 
@@ -357,7 +357,7 @@ def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
     tcap = mesh.shape[1]
     winner = torch.full((B, H, W), -1, device=pts.device, dtype=torch.int32)
     hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
-    trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W))
+    trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), table_rows)
     loc = _locate(winner, trirec, ntri, hints, table_rows, 1, tcap)
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, table_rows, 1, H, W, cap, tcap, "given")
 

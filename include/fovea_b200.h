@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 5
+#define FOVEA_ABI_VERSION 6
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -164,10 +164,12 @@ int fovea_locate_hints(const int32_t* pts, const int32_t* npts, const uint16_t* 
  * (exact int32), the tie-ownership bit of each edge (top-left rule, csrc/mesh.cuh), the neighbours, |area|, 1/area
  * (float64, as interp2d.py:58 / spatial/qhull.pyx:1210-1264 compute the barycentric transform) and the value-table rows
  * of the three vertices.  Layout: csrc/inverse.cu `struct TriRec` (64 bytes).
- *   trirec [B, tcap, 16] int32 (64-byte records);  max_coord = max(H, W) <= 16384. */
+ * Tie ownership: a pixel exactly on an edge goes to the triangle that can produce a value when exactly one of the two
+ * has a vertex without one (src == nan_row, an image corner no node landed on); else to the top-left rule.
+ *   trirec [B, tcap, 16] int32 (64-byte records);  max_coord = max(H, W) <= 16384;  nan_row = h*w (row of NaN). */
 #define FOVEA_TRIREC_BYTES 64
 int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t* mesh, const int32_t* ntri, int B,
-                         int cap, int tcap, int max_coord, void* trirec, fovea_stream_t stream);
+                         int cap, int tcap, int max_coord, int nan_row, void* trirec, fovea_stream_t stream);
 
 /* A9 point location, interp2d.py:58 (Delaunay.find_simplex over every pixel, spatial/qhull.pyx:2075-2163), merged
  * with the A7 winners into one per-pixel source map -- a function of the sampling grid only (not of the scores):

@@ -385,3 +385,83 @@ def test_nearest_fill_full_resolution_1024(ops):
     filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
     grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
     _check_nearest(ops, rp.synthetic_pred(B, C, seed=31), grid, (H, W), C)
+
+
+# ---------------------------------------------------------------------------------------------- edge cases
+def _grid_from(xs, task=(80, 80)):
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, task)
+    return grid
+
+
+@pytest.mark.parametrize("kind", ["uniform", "delta_corner", "delta_centre", "two_peaks"])
+@pytest.mark.parametrize("seg", [(200, 204), (64, 64), (1, 1)])
+def test_inverse_path_on_extreme_saliency_and_ragged_canvases(ops, kind, seg):
+    """Saliency maps the networks can produce at their extremes -- uniform (identity-like grid), all mass in ONE cell
+    (most of the 6400 nodes collide on a few pixels), two far peaks -- on canvases that are not multiples of any tile
+    size.  Parity mode (host Qhull) against the oracle; device Delaunay must yield a valid mesh and finite scores."""
+    if seg == (1, 1):
+        with pytest.raises(Exception):      # the C ABI rejects degenerate canvases loudly (H, W > 1)
+            ops.build_inverse_plan(torch.zeros(1, 80, 80, 2).cuda(), seg, nchan=3)
+        return
+    B, C = 2, 3
+    xs = torch.full((B, 1, 80, 80), 1e-12)
+    if kind == "uniform":
+        xs[:] = 1.0
+    elif kind == "delta_corner":
+        xs[:, :, 0, 0] = 1.0
+    elif kind == "delta_centre":
+        xs[:, :, 40, 37] = 1.0
+    else:
+        xs[:, :, 5, 70] = 1.0
+        xs[:, :, 72, 8] = 0.7
+    xs = xs / xs.sum(dim=(2, 3), keepdim=True)
+    grid = _grid_from(xs)
+    pred = rp.synthetic_pred(B, C, seed=3)
+    want = rp.inverse_path(pred, grid, seg, zero_residual=True, tie="max")
+    plan = ops.build_inverse_plan(grid.cuda(), seg, nchan=C, triangulation="host")
+    scores, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=True, want_mask=True)
+    exempt = _edge_exempt(scores.cpu(), want, plan)
+    bad = ((scores.cpu() - want).abs() > 1e-5 * max(1.0, float(want.abs().max()))).any(1) & ~exempt
+    assert bad.float().mean().item() < 1e-3, f"{int(bad.sum())} pixels differ from the oracle"
+    plan_d = ops.build_inverse_plan(grid.cuda(), seg, nchan=C, triangulation="device")
+    s_d, _ = ops.inverse_fill(plan_d, pred.cuda())
+    assert torch.isfinite(s_d).all()
+    # 'nearest' on the same inputs: finite, and filled pixels keep their node's value
+    plan_n = ops.build_nearest_plan(grid.cuda(), seg, nchan=C)
+    s_n, _ = ops.inverse_fill(plan_n, pred.cuda())
+    assert torch.isfinite(s_n).all()
+
+
+def test_nan_saliency_and_unaligned_width_fail_or_degrade_like_the_reference(ops):
+    """A NaN saliency gives NaN grid coordinates: no node lands anywhere (models/models.py:644-651 would index with
+    garbage; here the scatter ignores them) and the whole canvas is 'no value' -> NaN -> 0 (models_instance.py:940).
+    A canvas width that is not a multiple of 4 is refused (128-bit stores), not silently mis-handled."""
+    from fovea import FoveaError
+    grid = torch.full((1, 80, 80, 2), float("nan")).cuda()
+    pred = rp.synthetic_pred(1, 4, seed=1).cuda()
+    plan = ops.build_inverse_plan(grid, (96, 128), nchan=4, triangulation="device")
+    scores, mask = ops.inverse_fill(plan, pred, want_scores=True, want_mask=True, zero_residual=True)
+    assert (scores == 0).all() and (mask == 0).all()
+    scores, _ = ops.inverse_fill(plan, pred, zero_residual=False)
+    assert torch.isnan(scores).all()
+    with pytest.raises(FoveaError):
+        ops.build_inverse_plan(_grid_from(rp.synthetic_saliency(1, seed=1)[0]).cuda(), (96, 130), nchan=4)
+    with pytest.raises(FoveaError):
+        ops.inverse_fill(plan, rp.synthetic_pred(2, 4, seed=1).cuda())          # batch mismatch
+
+
+def test_batch_of_one_and_non_square_low_res_grid(ops):
+    """B = 1 (BASELINE configs[0]) and a non-square task size (grid 40x80 upsampled to 48x96)."""
+    xs, _ = rp.synthetic_saliency(1, 40, 80, seed=9)
+    filt, P = rp.gaussian_filter_weight(12, 24, 12), rp.p_basis(40, 80, 12, 24)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 12, 24), filt, P, 40, 80, (48, 96))
+    pred = rp.synthetic_pred(1, 6, 48, 96, seed=9)
+    seg = (192, 384)
+    want = rp.inverse_path(pred, grid, seg, zero_residual=True, tie="max")
+    plan = ops.build_inverse_plan(grid.cuda(), seg, nchan=6, triangulation="host")
+    scores, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=True, want_mask=True)
+    exempt = _edge_exempt(scores.cpu(), want, plan)
+    _check_masks(mask.cpu(), want, exempt)
+    bad = ((scores.cpu() - want).abs() > 1e-5 * float(want.abs().max())).any(1) & ~exempt
+    assert bad.float().mean().item() < 1e-3
