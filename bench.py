@@ -41,7 +41,7 @@ WORKLOADS = {
     "b16_4096": dict(B=16, H=4096, W=4096, C=51, g=80, R=45),
     "tiny": dict(B=4, H=256, W=256, C=51, g=80, R=45),
 }
-KERNELS_PER_STEP = 10  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay, locate_hints, triangle_setup, locate_pixels, box4_table, inverse_fill
+KERNELS_PER_STEP = 9  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay(+hints), triangle_setup, locate_pixels, box4_table, inverse_fill
 
 
 def peaks():
@@ -352,8 +352,7 @@ def main():
                        "l2": "output per step (4*C*H*W*B bytes) exceeds the 126 MB L2; no flush needed"},
             "serial_ms_per_step": serial_ms / args.steps,
             "path_hbm_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
-            "gpu_launches": KERNELS_PER_STEP * args.steps if args.triangulation == "device"
-            else (KERNELS_PER_STEP - 1) * args.steps,
+            "gpu_launches": KERNELS_PER_STEP * args.steps,   # (host triangulation: locate_hints replaces delaunay)
             "clocks": clocks.summary(),
             "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -143,7 +143,8 @@ __device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsi
 __global__ void __launch_bounds__(kDtThreads, 1)
 delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
                 uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
-                int max_rounds, int32_t* __restrict__ dbg, unsigned short* __restrict__ row_ws) {
+                int max_rounds, int32_t* __restrict__ dbg, unsigned short* __restrict__ row_ws,
+                int32_t* __restrict__ hints_out, int H, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int warp_sums[33];
   __shared__ int s_ntri;
@@ -196,6 +197,10 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   __syncthreads();
   if (n < 3 || R < 2) {  // nothing to triangulate (all points collinear in one row)
     if (tid == 0) { ntri_out[b] = 0; if (rounds_out) rounds_out[b] = 0; }
+    if (hints_out) {
+      const int nh = ceil_div(H, FOVEA_HINT_CELL_H) * ceil_div(W, FOVEA_HINT_CELL_W);
+      for (int i = tid; i < nh; i += kDtThreads) hints_out[static_cast<size_t>(b) * nh + i] = 0;
+    }
     return;
   }
 
@@ -563,6 +568,49 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     ntri_out[b] = T;
     if (rounds_out) rounds_out[b] = round;
   }
+
+  // ------------------------------------------------------------------ walk-start hints (fovea_locate_hints, fused)
+  // The mesh is still in shared memory: the three coarse-to-fine levels of locate_hints_kernel run here without
+  // re-staging it.  A hint only has to be NEAR its cell centre (fovea_locate_pixels walks from it), so the walk below
+  // stops at the first triangle with no negative edge function (no tie rule needed).  Scratch: the dead lock array.
+  if (hints_out) {
+    __syncthreads();
+    const int ch = ceil_div(H, FOVEA_HINT_CELL_H), cw = ceil_div(W, FOVEA_HINT_CELL_W);
+    const int mh = ceil_div(ch, 4);
+    int* coarse = reinterpret_cast<int*>(A.lock);  // [16*16]
+    int* mid = coarse + 256;                       // [mh*cw]   (the host checked that it fits)
+    int32_t* hb = hints_out + static_cast<size_t>(b) * ch * cw;
+    auto walk = [&](int qr, int qc, int t) {
+      for (int step = 0; step < T + 8; ++step) {
+        const int p0 = pts[A.v0[t]], p1 = pts[A.v1[t]], p2 = pts[A.v2[t]];
+        const int q = (qr << 16) | qc;
+        unsigned code;
+        if (orient_pts(p1, p2, q) < 0) code = A.n0[t];         // triangles are counter-clockwise: inside <=> all >= 0
+        else if (orient_pts(p2, p0, q) < 0) code = A.n1[t];
+        else if (orient_pts(p0, p1, q) < 0) code = A.n2[t];
+        else return t;
+        if (code >= kPendingCode) return t;                    // left the hull: the last triangle is the nearest known
+        t = static_cast<int>(code >> 2);
+      }
+      return t;
+    };
+    if (tid < 256) {
+      const int py = tid / 16, px = tid % 16;
+      coarse[tid] = walk(min(H - 1, (2 * py + 1) * H / 32), min(W - 1, (2 * px + 1) * W / 32), 0);
+    }
+    __syncthreads();
+    for (int i = tid; i < mh * cw; i += kDtThreads) {
+      const int cy = i / cw, cx = i - cy * cw;
+      const int qr = min(H - 1, cy * 32 + 16), qc = min(W - 1, cx * FOVEA_HINT_CELL_W + FOVEA_HINT_CELL_W / 2);
+      mid[i] = walk(qr, qc, coarse[min(15, qr * 16 / H) * 16 + min(15, qc * 16 / W)]);
+    }
+    __syncthreads();
+    for (int i = tid; i < ch * cw; i += kDtThreads) {
+      const int cy = i / cw, cx = i - cy * cw;
+      hb[i] = walk(min(H - 1, cy * FOVEA_HINT_CELL_H + FOVEA_HINT_CELL_H / 2),
+                   min(W - 1, cx * FOVEA_HINT_CELL_W + FOVEA_HINT_CELL_W / 2), mid[(cy / 4) * cw + cx]);
+    }
+  }
 }
 
 static size_t dt_smem_bytes(int cap, int tcap) {
@@ -580,24 +628,48 @@ extern "C" int64_t fovea_delaunay_workspace_bytes(int B, int cap) {
   return static_cast<int64_t>(B) * 4 * 9 + static_cast<int64_t>(B) * (cap + 2) * 2;
 }
 
-extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
-                              uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream) {
-  FOVEA_REQUIRE(pts && npts && mesh && ntri && workspace, "fovea_delaunay: null pointer");
-  FOVEA_REQUIRE(B > 0 && cap >= 4 && tcap >= 2 * cap, "fovea_delaunay: need tcap >= 2*cap (cap=%d tcap=%d)", cap, tcap);
+static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
+                           uint16_t* mesh, int32_t* ntri, void* workspace, int32_t* hints, int H, int W,
+                           cudaStream_t stream, const char* who) {
+  FOVEA_REQUIRE(pts && npts && mesh && ntri && workspace, "%s: null pointer", who);
+  FOVEA_REQUIRE(B > 0 && cap >= 4 && tcap >= 2 * cap, "%s: need tcap >= 2*cap (cap=%d tcap=%d)", who, cap, tcap);
   FOVEA_REQUIRE(max_coord > 0 && max_coord <= 8192,
-                "fovea_delaunay: coordinates must be < 8192 for the exact int64 in-circle test (got %d)", max_coord);
+                "%s: coordinates must be < 8192 for the exact int64 in-circle test (got %d)", who, max_coord);
   if (tcap > 16383 || cap > 8190) {
-    set_error("fovea_delaunay: tcap=%d exceeds the 16-bit mesh encoding (max 16383 triangles)", tcap);
+    set_error("%s: tcap=%d exceeds the 16-bit mesh encoding (max 16383 triangles)", who, tcap);
     return FOVEA_ERR_CAPACITY;
   }
   const size_t smem = dt_smem_bytes(cap, tcap);
   if (smem > 227 * 1024) {
-    set_error("fovea_delaunay: %zu B of shared memory needed for cap=%d (> 227 KB); use the host triangulation", smem, cap);
+    set_error("%s: %zu B of shared memory needed for cap=%d (> 227 KB); use the host triangulation", who, smem, cap);
     return FOVEA_ERR_CAPACITY;
   }
   FOVEA_CUDA(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  delaunay_kernel<<<B, kDtThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  delaunay_kernel<<<B, kDtThreads, smem, stream>>>(
       pts, npts, cap, tcap, mesh, ntri, static_cast<int32_t*>(workspace), 20000,
-      static_cast<int32_t*>(workspace) + B, reinterpret_cast<unsigned short*>(static_cast<int32_t*>(workspace) + 9 * B));
-  return check_launch("fovea_delaunay");
+      static_cast<int32_t*>(workspace) + B, reinterpret_cast<unsigned short*>(static_cast<int32_t*>(workspace) + 9 * B),
+      hints, H, W);
+  return check_launch(who);
+}
+
+extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
+                              uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream) {
+  return launch_delaunay(pts, npts, B, cap, tcap, max_coord, mesh, ntri, workspace, nullptr, 0, 0,
+                         static_cast<cudaStream_t>(stream), "fovea_delaunay");
+}
+
+extern "C" int fovea_delaunay_hints_fused(int tcap, int H, int W) {
+  // the two coarse levels live in the kernel's dead lock array (4*tcap bytes)
+  const long long ch = ceil_div(H, FOVEA_HINT_CELL_H), cw = ceil_div(W, FOVEA_HINT_CELL_W);
+  return (256 + ceil_div(static_cast<int>(ch), 4) * cw) * 4 <= 4ll * tcap ? 1 : 0;
+}
+
+extern "C" int fovea_delaunay_with_hints(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int H,
+                                         int W, uint16_t* mesh, int32_t* ntri, int32_t* hints, void* workspace,
+                                         fovea_stream_t stream) {
+  FOVEA_REQUIRE(hints && H > 1 && W > 1, "fovea_delaunay_with_hints: bad arguments");
+  FOVEA_REQUIRE(fovea_delaunay_hints_fused(tcap, H, W), "fovea_delaunay_with_hints: %dx%d hints do not fit the kernel's "
+                "scratch (tcap=%d); call fovea_delaunay + fovea_locate_hints", H, W, tcap);
+  return launch_delaunay(pts, npts, B, cap, tcap, H > W ? H : W, mesh, ntri, workspace, hints, H, W,
+                         static_cast<cudaStream_t>(stream), "fovea_delaunay_with_hints");
 }

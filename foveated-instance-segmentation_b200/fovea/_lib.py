@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class FoveaError(RuntimeError):
@@ -42,6 +42,8 @@ PROTOTYPES = {
     "fovea_select_points": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_delaunay_workspace_bytes": (_i64, [_i, _i]),
     "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fovea_delaunay_hints_fused": (_i, [_i, _i, _i]),
+    "fovea_delaunay_with_hints": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "fovea_locate_hints_workspace_bytes": (_i64, [_i, _i, _i]),
     "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

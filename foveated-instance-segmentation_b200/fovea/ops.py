@@ -269,13 +269,18 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
     npts = torch.empty(B, device=dev, dtype=torch.int32)
     _lib.call("fovea_select_points", _ptr(g), _ptr(winner), B, h, w, H, W, int(nchan), cap, _ptr(pts), _ptr(src),
               _ptr(npts), _stream())
+    hints = None
     if triangulation == "host":
         mesh, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
     elif triangulation == "device":
-        mesh, ntri, _ = delaunay_device(pts, npts, cap, tcap, max(H, W))
+        if _lib.load().fovea_delaunay_hints_fused(tcap, H, W):
+            mesh, ntri, hints = delaunay_device_with_hints(pts, npts, cap, tcap, H, W)
+        else:
+            mesh, ntri, _ = delaunay_device(pts, npts, cap, tcap, max(H, W))
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
-    hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
+    if hints is None:
+        hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
     trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), h * w)
     loc = _locate(winner, trirec, ntri, hints, h, w, tcap)
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, h, w, H, W, cap, tcap, triangulation)
@@ -294,6 +299,19 @@ def delaunay_device(pts, npts, cap, tcap, max_coord):
     _lib.call("fovea_delaunay", _ptr(pts), _ptr(npts), B, cap, tcap, int(max_coord), _ptr(mesh), _ptr(ntri),
               _ptr(ws), _stream())
     return mesh, ntri, ws
+
+
+def delaunay_device_with_hints(pts, npts, cap, tcap, H, W):
+    """delaunay_device + the walk-start hints in one launch (the mesh is still in the kernel's shared memory)."""
+    B, dev = pts.shape[0], pts.device
+    mesh = torch.empty(B, tcap, 8, device=dev, dtype=torch.uint16)
+    ntri = torch.empty(B, device=dev, dtype=torch.int32)
+    hints = torch.empty(B, -(-H // _lib.HINT_CELL_H), -(-W // _lib.HINT_CELL_W), device=dev, dtype=torch.int32)
+    nbytes = int(_lib.load().fovea_delaunay_workspace_bytes(B, cap))
+    ws = torch.zeros((nbytes + 3) // 4, device=dev, dtype=torch.int32)
+    _lib.call("fovea_delaunay_with_hints", _ptr(pts), _ptr(npts), B, cap, tcap, H, W, _ptr(mesh), _ptr(ntri),
+              _ptr(hints), _ptr(ws), _stream())
+    return mesh, ntri, hints
 
 
 def _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W):

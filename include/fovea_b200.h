@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 6
+#define FOVEA_ABI_VERSION 7
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -148,6 +148,14 @@ int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, 
 int64_t fovea_delaunay_workspace_bytes(int B, int cap);
 int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
                    uint16_t* mesh, int32_t* ntri, void* workspace, fovea_stream_t stream);
+
+/* fovea_delaunay + fovea_locate_hints in ONE launch: the hints are computed while the mesh is still in the kernel's
+ * shared memory (saves re-staging 230 KB per image).  Possible when fovea_delaunay_hints_fused(tcap,H,W) != 0 (the two
+ * coarse hint levels must fit the kernel's scratch: canvases up to ~3500^2 at the default tcap); otherwise call the
+ * two entry points separately.  hints as fovea_locate_hints; workspace as fovea_delaunay. */
+int fovea_delaunay_hints_fused(int tcap, int H, int W);
+int fovea_delaunay_with_hints(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int H, int W,
+                              uint16_t* mesh, int32_t* ntri, int32_t* hints, void* workspace, fovea_stream_t stream);
 
 /* Walk-start hints for fovea_locate_pixels: hints[b, cy, cx] = the triangle containing the centre of the
  * FOVEA_HINT_CELL_W x FOVEA_HINT_CELL_H pixel cell (one thread of the locate kernel walks one cell-wide row run).
