@@ -437,9 +437,16 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     bool deferred = false;
     if (lane < wpw && wbase + lane < nwords) {
       const unsigned w = A.dirty[wbase + lane];
-      const bool dense = __popc(w) > 8;
+#ifndef DT_THIN
+#define DT_THIN 4   // keep one dirty triangle in DT_THIN of a dense word per round (2, 4 or 8)
+#endif
+#ifndef DT_DENSE
+#define DT_DENSE 8  // a word is dense when more than this many of its 32 triangles are dirty
+#endif
+      const bool dense = __popc(w) > DT_DENSE;
       const unsigned h = hash32((wbase + lane) * 0x9E3779B9u + round * 0x85EBCA6Bu);
-      myword = dense ? (w & h & hash32(h)) : w;
+      const unsigned keep = DT_THIN == 2 ? h : (DT_THIN == 4 ? (h & hash32(h)) : (h & hash32(h) & hash32(h ^ 0x5bd1e995u)));
+      myword = dense ? (w & keep) : w;
       if (dense && myword == 0u) myword = w & (0u - w);  // keep at least one (lowest) bit so progress is guaranteed
       A.dirty[wbase + lane] = w & ~myword;
       deferred = (w & ~myword) != 0u;  // unselected dirty triangles: the loop must not terminate this round

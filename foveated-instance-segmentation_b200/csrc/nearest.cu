@@ -12,7 +12,9 @@
 //               as k^2 >= best -- O(distance to the nearest site) steps, every load coalesced      (one thread per pixel)
 // The result is the same per-pixel source map `loc` the 'tri' mode produces (every entry a direct table row), so
 // fovea_inverse_fill streams the scores unchanged.  Equidistant sites: the reference's KD-tree returns whichever it
-// meets first; here the smaller |dx| wins, then the left one, then (within a column) the upper one.
+// meets first; here the leftmost column wins, then (within a column) the upper site.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "select.cuh"
 
@@ -98,6 +100,99 @@ nearest_rows_kernel(const int32_t* __restrict__ winner, const short* __restrict_
   loc[row + x] = static_cast<uint16_t>(0x8000 | out);   // 16-bit source map: bit 15 = direct table row
 }
 
+// Row pass, exact and O(W log W) per row regardless of how sparse the sites are: for one image row the cost
+// c(x, x') = (x - x')^2 + g[y][x']^2 is a Monge array, so its leftmost row minima opt(x) are non-decreasing in x.
+// One warp resolves one row by divide and conquer over x: position 0 first, then the odd multiples of the stride
+// s = P/2, P/4, ..., 1; position x only scans candidates between the optima of its already-resolved neighbours
+// x - s and x + s.  While a level has fewer positions than lanes the warp scans each range cooperatively (strided
+// candidates + a shuffle arg-min); afterwards every lane resolves its own positions.  The per-level candidate count is
+// <= W + (number of positions), ~11 W evaluations per row in total.
+constexpr int kDcWarps = 8;
+
+__device__ __forceinline__ void argmin_merge(unsigned& d, int& i, unsigned d2, int i2) {
+  if (d2 < d || (d2 == d && i2 < i)) { d = d2; i = i2; }  // leftmost among equal distances
+}
+
+__global__ void __launch_bounds__(kDcWarps * 32)
+nearest_rows_dc_kernel(const int32_t* __restrict__ winner, const short* __restrict__ g, uint16_t* __restrict__ loc, int hw,
+                       int H, int W, int P /* smallest power of two >= W */) {
+  extern __shared__ unsigned dc_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, y = blockIdx.x * kDcWarps + warp;
+  if (y >= H) return;  // warp-uniform
+  unsigned* f = dc_smem + static_cast<size_t>(warp) * (W + (W + 1) / 2);   // [W] g^2, 0xffffffff = no site in the column
+  unsigned short* opt = reinterpret_cast<unsigned short*>(f + W);        // [W] leftmost nearest column
+  const size_t row = (static_cast<size_t>(b) * H + y) * W;
+  bool any = false;
+  for (int x = lane; x < W; x += 32) {
+    const int dy = g[row + x];
+    f[x] = dy == kNoSite ? 0xffffffffu : static_cast<unsigned>(dy * dy);
+    any |= dy != kNoSite;
+  }
+  any = __any_sync(0xffffffffu, any);
+  __syncwarp();
+  if (!any) {  // no site in this image: the NaN row of the value table (filled pixels keep their own value)
+    for (int x = lane; x < W; x += 32) {
+      const int n = winner[row + x];
+      loc[row + x] = static_cast<uint16_t>(0x8000 | (n >= 0 ? n : hw));
+    }
+    return;
+  }
+  auto cost = [&](int x, int c) {
+    const unsigned fc = f[c];
+    const int dx = x - c;
+    return fc == 0xffffffffu ? 0xffffffffu : fc + static_cast<unsigned>(dx * dx);   // < 2^31, see nearest_rows_kernel
+  };
+  // cooperative resolution of one position: all lanes scan [lo, hi] strided, then arg-min across the warp
+  auto resolve_coop = [&](int x, int lo, int hi) {
+    unsigned d = 0xffffffffu;
+    int i = lo;
+    for (int c = lo + lane; c <= hi; c += 32) argmin_merge(d, i, cost(x, c), c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      argmin_merge(d, i, d2, i2);
+    }
+    if (lane == 0) opt[x] = static_cast<unsigned short>(i);
+  };
+  resolve_coop(0, 0, W - 1);
+  __syncwarp();
+  for (int s = P >> 1; s >= 1; s >>= 1) {
+    const int npos = P / (2 * s);  // positions s, 3s, 5s, ... (those < W)
+    if (npos < 32) {
+      for (int k = 0; k < npos; ++k) {
+        const int x = (2 * k + 1) * s;
+        if (x >= W) break;
+        const int lo = opt[x - s], hi = x + s < W ? opt[x + s] : W - 1;
+        resolve_coop(x, lo, hi);
+      }
+    } else {
+      for (int k = lane; k < npos; k += 32) {
+        const int x = (2 * k + 1) * s;
+        if (x >= W) break;
+        const int lo = opt[x - s], hi = x + s < W ? opt[x + s] : W - 1;
+        unsigned d = 0xffffffffu;
+        int i = lo;
+        for (int c = lo; c <= hi; ++c) {
+          const unsigned dc = cost(x, c);
+          if (dc < d) { d = dc; i = c; }
+        }
+        opt[x] = static_cast<unsigned short>(i);
+      }
+    }
+    __syncwarp();
+  }
+  for (int x = lane; x < W; x += 32) {
+    int n = winner[row + x];
+    if (n < 0) {
+      const int c = opt[x];
+      n = winner[(static_cast<size_t>(b) * H + (y + g[row + c])) * W + c];
+    }
+    loc[row + x] = static_cast<uint16_t>(0x8000 | n);
+  }
+}
+
 }  // namespace fovea
 
 using namespace fovea;
@@ -118,6 +213,17 @@ extern "C" int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, 
   short* g = static_cast<short*>(workspace);
   nearest_columns_kernel<<<dim3(ceil_div(W, 128), B), 128, 0, s>>>(winner, g, p);
   if (int rc = check_launch("fovea_nearest_locate (columns)")) return rc;
-  nearest_rows_kernel<<<dim3(ceil_div(W, 256), H, B), 256, 0, s>>>(winner, g, loc, h * w, H, W);
+  // rows: the divide-and-conquer envelope needs 6 bytes of shared memory per pixel of a row and warp; rows too long for
+  // that (W > ~4800) fall back to the outward scan (exact too, but O(distance to the nearest site) per pixel)
+  const size_t smem = static_cast<size_t>(kDcWarps) * (W + (W + 1) / 2) * sizeof(unsigned);
+  static const bool force_scan = [] { const char* e = getenv("FOVEA_NEAREST_SCAN"); return e && e[0] == '1'; }();
+  if (smem <= 227 * 1024 && !force_scan) {
+    int P = 1;
+    while (P < W) P <<= 1;
+    FOVEA_CUDA(cudaFuncSetAttribute(nearest_rows_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    nearest_rows_dc_kernel<<<dim3(ceil_div(H, kDcWarps), B), kDcWarps * 32, smem, s>>>(winner, g, loc, h * w, H, W, P);
+  } else {
+    nearest_rows_kernel<<<dim3(ceil_div(W, 256), H, B), 256, 0, s>>>(winner, g, loc, h * w, H, W);
+  }
   return check_launch("fovea_nearest_locate (rows)");
 }

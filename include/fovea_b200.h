@@ -209,8 +209,8 @@ int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* tab
  * models/models.py:213-250, 259-272 = getPixelsForInterp_NB + scipy NearestNDInterpolator on the host.  Produces the
  * same per-pixel source map as fovea_locate_pixels, every entry a direct table row:
  *   loc[b,y,x] = 0x8000 | n   n = the node the pixel received (winner >= 0), else the node of the NEAREST interpolation
- *                         site (exact integer Euclidean distance; equidistant sites: smaller |dx|, then left, then
- *                         upper);  n = h*w when the image has no site at all (NaN row).
+ *                         site (exact integer Euclidean distance; equidistant sites: the leftmost column, then the
+ *                         upper site);  n = h*w when the image has no site at all (NaN row).
  * Sites: filled pixels with an unfilled pixel directly above/below (on the nearest-downscaled mask when
  * max(nchan,H,W) > 512, models.py:222-232); no forced corners.  Feed `loc` to fovea_inverse_fill (trirec is not read).
  *   workspace: fovea_nearest_workspace_bytes(B,H,W) bytes;  H, W < 32767. */
