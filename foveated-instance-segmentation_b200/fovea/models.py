@@ -224,6 +224,7 @@ class DeformSegmentationModule(SegmentationModuleBase):
                       (i - self.padding_size_x) / (self.grid_size_x - 1.0) + 0 * j])
         self.P_basis = torch.from_numpy(P.astype(np.float32))                   # plain attribute, as the reference
         self._factors = None
+        self._plan_stream = None
 
     # -- stage 1 -----------------------------------------------------------------------------------------------
     def _g1(self, device):
@@ -289,16 +290,44 @@ class DeformSegmentationModule(SegmentationModuleBase):
         if not (c.TRAIN.deform_joint_loss and c.TRAIN.opt_deform_LabelEdge_norm):
             raise NotImplementedError("only the joint-loss / normalised edge-loss configuration of deform.yaml")
 
-    def inverse_upsample(self, pred, grid, segSize, zero_residual, want_mask=False):
-        """grid_inv + F.grid_sample(pred, grid_inv) + NaN mask + per-sample 'tri' fill (models.py:933-940) fused."""
+    def _build_plan(self, grid, segSize, nchan):
         mode = self.cfg.MODEL.rev_deform_interp
         if mode == "nearest":                      # config/deform.yaml:17
-            plan = ops.build_nearest_plan(grid.detach(), segSize, nchan=pred.shape[1])
-        elif mode == "tri":
-            plan = ops.build_inverse_plan(grid.detach(), segSize, nchan=pred.shape[1], triangulation=self.triangulation)
+            return ops.build_nearest_plan(grid.detach(), segSize, nchan=nchan)
+        if mode == "tri":
+            return ops.build_inverse_plan(grid.detach(), segSize, nchan=nchan, triangulation=self.triangulation)
+        raise NotImplementedError("rev_deform_interp must be 'tri' or 'nearest' on the GPU path ('BI' is the host SciPy "
+                                  "LinearNDInterpolator: the same interpolant as 'tri')")
+
+    def plan_async(self, grid, segSize):
+        """Start the saliency-only half of stage 3 (A7 scatter, A9 point selection, Delaunay, point location) on a
+        high-priority side stream as soon as the grid exists, so that it overlaps the encoder/decoder; returns a handle
+        for `inverse_upsample(..., plan=handle)`.  Needs the class count before the decoder has run: taken from
+        cfg.DATASET.num_class (it only enters the >512-pixel rule of the point selection, models/models.py:183); when
+        the config has none, returns None and the plan is built after the decoder instead."""
+        nchan = getattr(getattr(self.cfg, "DATASET", None), "num_class", None)
+        if nchan is None:
+            return None
+        if self._plan_stream is None:
+            self._plan_stream = torch.cuda.Stream(grid.device, priority=-1)
+        side = self._plan_stream
+        side.wait_stream(torch.cuda.current_stream(grid.device))
+        with torch.cuda.stream(side):
+            plan = self._build_plan(grid, segSize, int(nchan))
+            done = torch.cuda.Event()
+            done.record(side)
+        grid.record_stream(side)
+        return plan, done, int(nchan)
+
+    def inverse_upsample(self, pred, grid, segSize, zero_residual, want_mask=False, plan=None):
+        """grid_inv + F.grid_sample(pred, grid_inv) + NaN mask + per-sample fill (models.py:933-940) fused."""
+        if plan is not None and plan[2] == pred.shape[1]:
+            plan, done, _ = plan
+            torch.cuda.current_stream(pred.device).wait_event(done)
+            for t in (plan.loc, plan.trirec, plan.winner):           # allocated on the side stream, consumed here
+                t.record_stream(torch.cuda.current_stream(pred.device))
         else:
-            raise NotImplementedError("rev_deform_interp must be 'tri' or 'nearest' on the GPU path ('BI' is the host "
-                                      "SciPy LinearNDInterpolator: the same interpolant as 'tri')")
+            plan = self._build_plan(grid, segSize, pred.shape[1])
         return ops.inverse_fill(plan, pred, want_scores=True, want_mask=want_mask, zero_residual=zero_residual)
 
     # -- forward ------------------------------------------------------------------------------------------------
@@ -321,9 +350,10 @@ class DeformSegmentationModule(SegmentationModuleBase):
         xs_n = (xs - xs.min()) / (xs.max() - xs.min())                          # :889-898
         xt_n = (xs_target - xs_target.min()) / (xs_target.max() - xs_target.min())
         edge_loss = 0.05 * self.crit_mse(xs_n, xt_n) * cfg.TRAIN.edge_loss_scale
+        upsample = cfg.MODEL.upsample
+        plan = self.plan_async(grid, (H_HS, W_HS)) if upsample else None        # overlaps the encoder/decoder
         x_sampled = ops.grid_sample(x, grid)                                    # :909
         pred = self.decoder(self.encoder(x_sampled, return_feature_maps=True))  # :926
-        upsample = cfg.MODEL.upsample
         seg_low = y_sampled.long()
         y_hs = feed_dict["seg_label"].squeeze(1)
         feed_dict["seg_label"] = seg_low                                        # :951 (the reference mutates it too)
@@ -333,7 +363,7 @@ class DeformSegmentationModule(SegmentationModuleBase):
         if not upsample:
             target, scored = ground_truth, pred
         else:                                                                   # :933-940, :971
-            scored, _ = self.inverse_upsample(pred, grid, (H_HS, W_HS), zero_residual=False)
+            scored, _ = self.inverse_upsample(pred, grid, (H_HS, W_HS), zero_residual=False, plan=plan)
             target = (y_hs * cls[:, :, None] + (1 - y_hs) * 50).long()
         acc = self.pixel_acc(scored, target)
         if not is_inference:
@@ -344,13 +374,14 @@ class DeformSegmentationModule(SegmentationModuleBase):
     def _forward_inference(self, feed_dict, x, xs, y, segSize):
         """models_instance.py:840-1121 with rev_deform_opt == 51 ('ours deformed case')."""
         grid, grid_y = self._grid_from_saliency(xs, segSize=segSize)            # :844-845
+        plan = None if getattr(self.cfg.VAL, "no_upsample", False) else self.plan_async(grid, segSize)
         x_sampled = ops.grid_sample(x, grid)                                    # :851-852
         if tuple(x_sampled.shape[-2:]) != tuple(self.input_size_net_infer):
             x_sampled = F.interpolate(x_sampled, self.input_size_net_infer, mode="bilinear")
         pred = self.decoder(self.encoder(x_sampled, return_feature_maps=True), segSize=tuple(self.input_size_net_infer))
         y4 = y.float() if y.dim() == 4 else y.float().unsqueeze(1)
         y_sampled = F.grid_sample(y4, grid_y, mode="nearest", align_corners=False).long().squeeze(1)   # :866 (stock)
-        pred_sampled, _ = self.inverse_upsample(pred, grid, segSize, zero_residual=True)   # :883-893, :940
         if getattr(self.cfg.VAL, "no_upsample", False):
             return pred, x_sampled, xs
+        pred_sampled, _ = self.inverse_upsample(pred, grid, segSize, zero_residual=True, plan=plan)   # :883-893, :940
         return pred_sampled, pred, y_sampled

@@ -212,3 +212,29 @@ def test_fill_missing_values_nearest_api(golden_dir):
     # proves pixel by pixel that every disagreement is such a tie
     close = ((got - want).abs() <= 1e-5 * want.abs().max()).all(0)
     assert close.float().mean().item() > 0.8
+
+
+def test_module_nearest_mode_and_async_plan():
+    """cfg.MODEL.rev_deform_interp='nearest' (config/deform.yaml:17) through the module's inference branch, and the
+    side-stream plan (overlapping the encoder) against the plan built after the decoder."""
+    from fovea import ops
+    from fovea.models import CompressNet, DeformSegmentationModule
+    from fovea.saliency_network import fov_simple
+    torch.manual_seed(3)
+    feed = {k: v.cuda() for k, v in synthetic_batch(2, 128, 160, 9).items()}
+    outs = {}
+    for mode in ("nearest", "tri"):
+        cfg = make_cfg(True)
+        cfg.MODEL.rev_deform_interp = mode
+        cfg.VAL.no_upsample = False
+        torch.manual_seed(3)
+        m = DeformSegmentationModule(TinyEncoder(), TinyDecoder(), fov_simple(cfg), CompressNet(cfg), None, cfg).cuda().eval()
+        with torch.no_grad():
+            ps_async, pred, _ = m(feed, segSize=(128, 160))
+            cfg.DATASET.num_class = None                      # no class count in the config -> plan after the decoder
+            ps_sync, pred2, _ = m(feed, segSize=(128, 160))
+        assert torch.equal(pred, pred2) and torch.equal(ps_async, ps_sync)
+        assert ps_async.shape == (2, 51, 128, 160) and not torch.isnan(ps_async).any()
+        outs[mode] = ps_async
+    # both modes leave the pixels that received a node untouched, and differ elsewhere (step function vs. linear)
+    assert not torch.equal(outs["nearest"], outs["tri"])
