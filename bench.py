@@ -113,10 +113,10 @@ def make_inputs(cfg, seed, device=None, pinned=False):
 class Path:
     """The product path as a user drives it (fovea.ops), with every output buffer allocated once."""
 
-    def __init__(self, cfg, device, triangulation):
+    def __init__(self, cfg, device, triangulation, interp="tri"):
         from fovea import ops
         from oracle.reference_port import gaussian_filter_weight  # constant construction only (models.py:510-515)
-        self.ops, self.cfg, self.dev, self.tri = ops, cfg, device, triangulation
+        self.ops, self.cfg, self.dev, self.tri, self.interp = ops, cfg, device, triangulation, interp
         R = cfg["R"]
         self.g1x, self.g1y = (t.to(device) for t in ops.separable_factors(gaussian_filter_weight(R, R, R)))
         B, C, H, W = cfg["B"], cfg["C"], cfg["H"], cfg["W"]
@@ -129,7 +129,10 @@ class Path:
         g, R = cfg["g"], cfg["R"]
         grid = ops.saliency_to_grid(xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
         x_sampled = ops.grid_sample(x, grid)
-        plan = ops.build_inverse_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"], triangulation=self.tri)
+        if self.interp == "nearest":
+            plan = ops.build_nearest_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"])
+        else:
+            plan = ops.build_inverse_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"], triangulation=self.tri)
         table_ready = None
         if time_fill:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -199,6 +202,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--triangulation", default=os.environ.get("FOVEA_TRIANGULATION", "device"),
                     choices=["host", "device"])
+    ap.add_argument("--interp", default="tri", choices=["tri", "nearest"],
+                    help="cfg.MODEL.rev_deform_interp: 'tri' (headline) or 'nearest' (what config/deform.yaml ships)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -227,7 +232,7 @@ def main():
 
     B, C, H, W = cfg["B"], cfg["C"], cfg["H"], cfg["W"]
     x, xs, pred = make_inputs(cfg, seed=rank, device=dev)
-    path = Path(cfg, dev, args.triangulation)
+    path = Path(cfg, dev, args.triangulation, args.interp)
 
     # ---------------- device-resident, serial schedule: one stream, every kernel of a step after the previous one.
     # The fill kernel is timed here (CUDA events on its stream), with nothing else on the GPU: this is the roofline.
@@ -248,7 +253,8 @@ def main():
     # saliency-only half of step i+1 (grid, A7, A9 selection, Delaunay, point location) on a high-priority stream
     # overlapping the HBM-bound fill of step i.  Every step's full work happens inside the timed region.
     from fovea.pipeline import DevicePipeline
-    dpipe = DevicePipeline(B, C, H, W, cfg["g"], cfg["R"], dev, args.triangulation, depth=2, scores=path.scores)
+    dpipe = DevicePipeline(B, C, H, W, cfg["g"], cfg["R"], dev, args.triangulation, depth=2, scores=path.scores,
+                           interp=args.interp)
     for _ in range(args.warmup):
         dpipe.submit(x, xs, pred)
     dpipe.fence()
@@ -272,7 +278,7 @@ def main():
 
     # ---------------- end to end from host buffers (`e2e`): the public ResamplePipeline, three streams
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.interp == "tri":
         from fovea.pipeline import ResamplePipeline
         del x
         torch.cuda.empty_cache()
@@ -346,7 +352,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, **cfg, "frames_per_gpu": B, "triangulation": args.triangulation,
-                       "stages": "grid+grid_sample+inverse_fill(tri), scores mode",
+                       "stages": f"grid+grid_sample+inverse_fill({args.interp}), scores mode",
                        "schedule": "fovea.pipeline.DevicePipeline: plan of step i+1 (high-priority stream) overlaps "
                                    "the fill of step i; serial_ms_per_step = the same steps on one stream",
                        "l2": "output per step (4*C*H*W*B bytes) exceeds the 126 MB L2; no flush needed"},
@@ -364,7 +370,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.interp == "tri":
             fps, secs = cpu_reference_time(cfg, frames=1, reps=2)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"1 frame of {H}x{W}, C={C} (best of 2, {secs:.2f} s)"}

@@ -126,12 +126,12 @@ class DevicePipeline:
     """
 
     def __init__(self, B, C, H, W, g=80, R=45, device=None, triangulation="device", depth=2, want_mask=False,
-                 filter_weight=None, scores=None):
+                 filter_weight=None, scores=None, interp="tri"):
         if not torch.cuda.is_available():
             raise FoveaError("DevicePipeline needs a CUDA device: there is no CPU fallback")
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.B, self.C, self.H, self.W, self.g, self.R = B, C, H, W, g, R
-        self.tri, self.depth = triangulation, max(1, depth)
+        self.tri, self.depth, self.interp = triangulation, max(1, depth), interp
         if filter_weight is None:
             from .models import makeGaussian
             filter_weight = torch.from_numpy(makeGaussian(2 * R + 1, fwhm=R)).float()
@@ -155,7 +155,10 @@ class DevicePipeline:
                 self.plan_stream.wait_event(self.live[0][1])
             grid = ops.saliency_to_grid(xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
             x_sampled = ops.grid_sample(x, grid)
-            plan = ops.build_inverse_plan(grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
+            if self.interp == "nearest":
+                plan = ops.build_nearest_plan(grid, (self.H, self.W), nchan=self.C)
+            else:
+                plan = ops.build_inverse_plan(grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
             planned = torch.cuda.Event()
             planned.record(self.plan_stream)
         with torch.cuda.stream(self.fill_stream):
