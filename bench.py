@@ -308,6 +308,30 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e[key] = world * B * k / (float(t.item()) * 1e-3)
             del pipe
+        # API options beyond the reference's dtypes (reported beside the headline, never as it): the image stays uint8
+        # until the sampler (ToTensor's /255 folded into the tap loads) and the masks are uint8
+        hx8 = [(h[0] * 255).to(torch.uint8).pin_memory() for h in host]
+        hmask8 = [torch.empty(B, H, W, dtype=torch.uint8, pin_memory=True) for _ in range(nbuf)]
+        pipe = ResamplePipeline(B, C, H, W, cfg["g"], cfg["R"], dev, args.triangulation, depth=2, image_on_host=False,
+                                image_dtype=torch.uint8, mask_dtype=torch.uint8)
+        pipe.scores = path.scores
+        for i in range(3):
+            pipe.submit(hx8[i % nbuf], host[i % nbuf][1], host[i % nbuf][2], hmask8[i % nbuf])
+        pipe.drain()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        pipe.start_after(s0)
+        for i in range(k):
+            pipe.submit(hx8[i % nbuf], host[i % nbuf][1], host[i % nbuf][2], hmask8[i % nbuf])
+        pipe.fence()
+        s1.record()
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_u8 = world * B * k / (float(t.item()) * 1e-3)
+        del pipe
         hx, hxs, hpred = host[0]
         small = hxs.numel() * 4 + hpred.numel() * 4
         taps = B * 3 * cfg["g"] * cfg["g"] * 4                # 4 bilinear taps per output pixel and channel
@@ -316,6 +340,10 @@ def main():
                "h2d_bytes_per_step": small + (taps * 32 if best == "gather" else hx.numel() * 4),
                "d2h_bytes_per_step": hmask[0].numel() * 8, "steps": k, "image_ingest": best,
                "copy_frames_s": e2e["copy"], "gather_frames_s": e2e["gather"],
+               "uint8_image_and_masks": {"value": e2e_u8, "unit": "frames/s",
+                                         "h2d_bytes_per_step": small + hx.numel(), "d2h_bytes_per_step": B * H * W,
+                                         "what": "same pipeline with image_dtype=mask_dtype=uint8 (API options, not "
+                                                 "the reference's dtypes)"},
                "what": "pinned host image+saliency+pred -> device -> path (scores + fused argmax) -> D2H int64 masks; "
                        "fovea.pipeline.ResamplePipeline, 3 streams x 2 slots; image_ingest=copy: bulk H2D of the "
                        "image (h2d bytes = tensor bytes); gather: grid_sample pulls its taps from the pinned host "

@@ -43,6 +43,38 @@ grid_sample_fwd_kernel(const float* __restrict__ in, const float2* __restrict__ 
   }
 }
 
+// The same gather from a uint8 image: the loader's ToTensor() (uint8 -> fp32 / 255) is
+// folded into the tap loads, so the full-resolution frame crosses PCIe and sits in HBM at 1 byte per sample.  The
+// division is the fp32 division ToTensor performs, so the result is bit-identical to sampling the converted image.
+__global__ void __launch_bounds__(256)
+grid_sample_fwd_u8_kernel(const unsigned char* __restrict__ in, const float2* __restrict__ grid, float* __restrict__ out,
+                          int B, int C, int H, int W, int hw_out, float divisor) {
+  const long long total = static_cast<long long>(B) * hw_out;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(idx / hw_out);
+    const int pix = static_cast<int>(idx - static_cast<long long>(b) * hw_out);
+    const float2 g = grid[idx];
+    const Taps t = make_taps(g.x, g.y, H, W);
+    const size_t plane = static_cast<size_t>(H) * W;
+    const unsigned char* src = in + static_cast<size_t>(b) * C * plane + static_cast<long long>(t.y0) * W + t.x0;
+    float* dst = out + static_cast<size_t>(b) * C * hw_out + pix;
+#pragma unroll 3
+    for (int c = 0; c < C; ++c) {
+      const unsigned char* s = src + c * plane;
+      const float v_nw = t.ok_nw ? __fdiv_rn(static_cast<float>(__ldg(s)), divisor) : 0.f;
+      const float v_ne = t.ok_ne ? __fdiv_rn(static_cast<float>(__ldg(s + 1)), divisor) : 0.f;
+      const float v_sw = t.ok_sw ? __fdiv_rn(static_cast<float>(__ldg(s + W)), divisor) : 0.f;
+      const float v_se = t.ok_se ? __fdiv_rn(static_cast<float>(__ldg(s + W + 1)), divisor) : 0.f;
+      float acc = v_nw * t.nw;
+      acc = fmaf(v_ne, t.ne, acc);
+      acc = fmaf(v_sw, t.sw, acc);
+      acc = fmaf(v_se, t.se, acc);
+      dst[static_cast<size_t>(c) * hw_out] = acc;
+    }
+  }
+}
+
 // Warp-aggregated atomic add: lanes of the warp that target the same address elect a leader that adds the
 // group's sum with ONE red.global.add.f32 (the stock kernel issues one atomic per lane and tap).
 __device__ __forceinline__ void warp_aggregated_add(float* addr, float val, bool active) {
@@ -139,6 +171,16 @@ extern "C" int fovea_grid_sample_fwd(const float* in, const float* grid, int B, 
   grid_sample_fwd_kernel<<<launch_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, reinterpret_cast<const float2*>(grid), out, B, C, H, W, h * w);
   return check_launch("fovea_grid_sample_fwd");
+}
+
+extern "C" int fovea_grid_sample_fwd_u8(const uint8_t* in, const float* grid, int B, int C, int H, int W, int h, int w,
+                                        float divisor, float* out, fovea_stream_t stream) {
+  FOVEA_REQUIRE(in && grid && out, "fovea_grid_sample_fwd_u8: null pointer");
+  FOVEA_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0 && divisor > 0.f, "fovea_grid_sample_fwd_u8: bad arguments");
+  const long long total = static_cast<long long>(B) * h * w;
+  grid_sample_fwd_u8_kernel<<<launch_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, reinterpret_cast<const float2*>(grid), out, B, C, H, W, h * w, divisor);
+  return check_launch("fovea_grid_sample_fwd_u8");
 }
 
 extern "C" int fovea_grid_sample_bwd(const float* grad_out, const float* in, const float* grid, int B, int C, int H,

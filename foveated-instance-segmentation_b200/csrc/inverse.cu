@@ -472,6 +472,7 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restric
 // ------------------------------------------------------------------------------------------------ A8+A9+A10
 struct FillParams {
   int C, Cs, h, w, H, W, cap, tcap, zero_residual;
+  int mask_u8;  // 1: the fused argmax is written as uint8 (C <= 256) instead of torch.argmax's int64
 };
 
 #ifndef FOVEA_FILL_THREADS
@@ -633,9 +634,14 @@ __device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, cons
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if ((nanmask >> k) & 1u) besti[k] = 0;
-    longlong2* mp = reinterpret_cast<longlong2*>(mask + static_cast<size_t>(b) * plane + pixoff);
-    mp[0] = make_longlong2(besti[0], besti[1]);
-    mp[1] = make_longlong2(besti[2], besti[3]);
+    if (p.mask_u8) {
+      *reinterpret_cast<uchar4*>(reinterpret_cast<unsigned char*>(mask) + static_cast<size_t>(b) * plane + pixoff) =
+          make_uchar4(besti[0], besti[1], besti[2], besti[3]);
+    } else {
+      longlong2* mp = reinterpret_cast<longlong2*>(mask + static_cast<size_t>(b) * plane + pixoff);
+      mp[0] = make_longlong2(besti[0], besti[1]);
+      mp[1] = make_longlong2(besti[2], besti[3]);
+    }
   }
 }
 
@@ -819,8 +825,8 @@ static int launch_fill(const uint16_t* loc, const TriRec* recs, const float* tab
 }
 
 extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h,
-                                  int w, int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask,
-                                  fovea_stream_t stream) {
+                                  int w, int H, int W, int tcap, int zero_residual, float* scores, void* mask,
+                                  int mask_u8, fovea_stream_t stream) {
   FOVEA_REQUIRE(loc && trirec && table, "fovea_inverse_fill: null pointer");
   FOVEA_REQUIRE(scores || mask, "fovea_inverse_fill: neither scores nor mask requested");
   FOVEA_REQUIRE(B > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && h > 0 && w > 0 && H > 1 && W > 1,
@@ -830,7 +836,8 @@ extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_inverse_fill: B or H too large for the grid");
   FOVEA_REQUIRE(static_cast<long long>(h) * w + 2 <= 32768 && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
                 "fovea_inverse_fill: value table too large (rows must fit 15 bits, bytes 32 bits)");
-  FillParams p{C, Cs, h, w, H, W, 0, tcap, zero_residual};
+  FOVEA_REQUIRE(!mask_u8 || C <= 256, "fovea_inverse_fill: uint8 masks need C <= 256 (C=%d)", C);
+  FillParams p{C, Cs, h, w, H, W, 0, tcap, zero_residual, mask_u8 ? 1 : 0};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const TriRec* recs = static_cast<const TriRec*>(trirec);
   long long* mk = reinterpret_cast<long long*>(mask);

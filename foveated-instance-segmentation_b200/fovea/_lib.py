@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class FoveaError(RuntimeError):
@@ -35,6 +35,7 @@ PROTOTYPES = {
     "fovea_grid_resize": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_grid_resize_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_grid_sample_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_grid_sample_fwd_u8": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, C.c_float, _p, _p]),
     "fovea_grid_sample_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_grid_inv_scatter": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_grid_inv_canvas": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
@@ -48,7 +49,7 @@ PROTOTYPES = {
     "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "fovea_nearest_workspace_bytes": (_i64, [_i, _i, _i]),
     "fovea_nearest_locate": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_probe_store_ceiling": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -129,14 +129,29 @@ def grid_resize(grid, out_size):
 
 # ------------------------------------------------------------------------------------------------ stage 2
 
-def _req_gather_source(t, name):
+def _req_gather_source(t, name, dtype=torch.float32):
     """The image a gather kernel reads: a CUDA tensor, or a PINNED host tensor (unified virtual addressing makes its
     data_ptr dereferenceable on the device: the kernel then pulls only the 32-byte sectors it touches over PCIe)."""
     if isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned():
-        if t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous():
-            raise FoveaError(f"{name}: a pinned host source must be a contiguous 4-D float32 tensor")
+        if t.dtype != dtype or t.dim() != 4 or not t.is_contiguous():
+            raise FoveaError(f"{name}: a pinned host source must be a contiguous 4-D {dtype} tensor")
         return t
-    return _req(t, torch.float32, name, 4)
+    return _req(t, dtype, name, 4)
+
+
+def grid_sample_u8(inp, grid, divisor=255.0):
+    """F.grid_sample(inp.float() / divisor, grid) for a uint8 image [B,C,H,W] (CUDA or pinned host): ToTensor() folded
+    into the tap loads; bit-identical to converting first.  Not differentiable w.r.t. the
+    image; use grid_sample() on the fp32 image when the grid needs a gradient."""
+    x = _req_gather_source(inp, "input", torch.uint8)
+    g = _req(grid.detach(), torch.float32, "grid", 4)
+    B, Cc, H, W = x.shape
+    if g.shape[0] != B or g.shape[3] != 2:
+        raise FoveaError(f"grid_sample_u8: grid {tuple(g.shape)} does not match input {tuple(x.shape)}")
+    h, w = g.shape[1], g.shape[2]
+    out = torch.empty(B, Cc, h, w, device=g.device, dtype=torch.float32)
+    _lib.call("fovea_grid_sample_fwd_u8", _ptr(x), _ptr(g), B, Cc, H, W, h, w, float(divisor), _ptr(out), _stream())
+    return out
 
 
 class _GridSampleFn(torch.autograd.Function):
@@ -388,9 +403,14 @@ def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=
 
 
 def _fill(plan, table, C, zero_residual, scores, mask):
+    mask_u8 = 0
+    if mask is not None:
+        if mask.dtype not in (torch.int64, torch.uint8) or not mask.is_cuda or not mask.is_contiguous():
+            raise FoveaError("inverse_fill: mask must be a contiguous CUDA int64 (torch.argmax's dtype) or uint8 tensor")
+        mask_u8 = 1 if mask.dtype == torch.uint8 else 0
     _lib.call("fovea_inverse_fill", _ptr(plan.loc), _ptr(plan.trirec), _ptr(table), plan.loc.shape[0], C,
               table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.tcap, 1 if zero_residual else 0, _ptr(scores),
-              _ptr(mask), _stream())
+              _ptr(mask), mask_u8, _stream())
 
 
 def box4_table(pred, Cs=None):

@@ -25,11 +25,11 @@ from ._lib import FoveaError
 
 
 class _Slot:
-    def __init__(self, B, C, H, W, g, device, image_on_host):
-        self.x = None if image_on_host else torch.empty(B, 3, H, W, device=device)
+    def __init__(self, B, C, H, W, g, device, image_on_host, image_dtype, mask_dtype):
+        self.x = None if image_on_host else torch.empty(B, 3, H, W, device=device, dtype=image_dtype)
         self.xs = torch.empty(B, 1, g, g, device=device)
         self.pred = torch.empty(B, C, g, g, device=device)
-        self.mask = torch.empty(B, H, W, device=device, dtype=torch.int64)
+        self.mask = torch.empty(B, H, W, device=device, dtype=mask_dtype)
         self.h2d_done = torch.cuda.Event()
         self.compute_done = torch.cuda.Event()
         self.d2h_done = torch.cuda.Event()
@@ -38,7 +38,10 @@ class _Slot:
 
 class ResamplePipeline:
     def __init__(self, B, C, H, W, g=80, R=45, device=None, triangulation="device", depth=2, want_scores=True,
-                 image_on_host=False, filter_weight=None):
+                 image_on_host=False, filter_weight=None, image_dtype=torch.float32, mask_dtype=torch.int64):
+        """image_dtype=torch.uint8: the image arrives as the decoder produced it and ToTensor()'s /255 is folded into the
+        sampler (a quarter of the PCIe bytes); mask_dtype=torch.uint8: narrower masks than torch.argmax's int64 (an
+        eighth of the D2H bytes).  Both are API options beyond the reference's dtypes; the defaults are the reference's."""
         if not torch.cuda.is_available():
             raise FoveaError("ResamplePipeline needs a CUDA device: there is no CPU fallback")
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -51,7 +54,8 @@ class ResamplePipeline:
         self.copy_in = torch.cuda.Stream(self.dev)
         self.compute = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
-        self.slots = [_Slot(B, C, H, W, g, self.dev, image_on_host) for _ in range(depth)]
+        self.image_dtype = image_dtype
+        self.slots = [_Slot(B, C, H, W, g, self.dev, image_on_host, image_dtype, mask_dtype) for _ in range(depth)]
         self.scores = torch.empty(B, C, H, W, device=self.dev) if want_scores else None   # compute stream only
         self.n = 0
 
@@ -72,7 +76,8 @@ class ResamplePipeline:
             s.xs.copy_(hxs, non_blocking=True)
             s.pred.copy_(hpred, non_blocking=True)
             s.grid = ops.saliency_to_grid(s.xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
-            s.x_sampled = ops.grid_sample(hx if self.image_on_host else s.x, s.grid)
+            src = hx if self.image_on_host else s.x
+            s.x_sampled = ops.grid_sample_u8(src, s.grid) if self.image_dtype == torch.uint8 else ops.grid_sample(src, s.grid)
             s.h2d_done.record(self.copy_in)
         with torch.cuda.stream(self.compute):                # inverse stage
             self.compute.wait_event(s.h2d_done)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 7
+#define FOVEA_ABI_VERSION 8
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -90,6 +90,13 @@ int fovea_grid_resize_bwd(const float* grad_out, int B, int ih, int iw, int oh, 
  * ------------------------------------------------------------------------------------------------ */
 int fovea_grid_sample_fwd(const float* in, const float* grid, int B, int C, int H, int W, int h, int w,
                           float* out, fovea_stream_t stream);
+
+/* The same forward gather from a uint8 image, with the data loader's ToTensor() (uint8 -> fp32 / divisor, divisor = 255;
+ * DynamicFocus/e_preprocess_scripts/dataset.py:133-137) folded into the tap loads: bit-identical to sampling the converted
+ * fp32 image, at a quarter of the PCIe / HBM bytes.  No backward (the image needs no grad).
+ *   in [B,C,H,W] uint8 */
+int fovea_grid_sample_fwd_u8(const uint8_t* in, const float* grid, int B, int C, int H, int W, int h, int w,
+                             float divisor, float* out, fovea_stream_t stream);
 
 /* Backward (aten grid_sampler_2d_backward).  grad_in may be NULL (input does not require grad: the image
  * and label); when given it must be ZERO-FILLED by the caller and receives a warp-aggregated scatter-add.
@@ -200,10 +207,11 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
  *   trirec [B,tcap,16] from fovea_triangle_setup
  *   table  [B, h*w+2, Cs] from fovea_box4_table   (h*w+2 <= 32768)
  *   scores [B,C,H,W] fp32   (NULL = do not materialise)
- *   mask   [B,H,W]  int64   (NULL = do not compute)
+ *   mask   [B,H,W]  int64 (torch.argmax's dtype), or uint8 when mask_u8 != 0 (C <= 256)   (NULL = do not compute)
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
 int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
-                       int H, int W, int tcap, int zero_residual, float* scores, int64_t* mask, fovea_stream_t stream);
+                       int H, int W, int tcap, int zero_residual, float* scores, void* mask, int mask_u8,
+                       fovea_stream_t stream);
 
 /* rev_deform_interp = 'nearest' (the mode config/deform.yaml:17 ships): fillMissingValues_tensor(..., 'nearest'),
  * models/models.py:213-250, 259-272 = getPixelsForInterp_NB + scipy NearestNDInterpolator on the host.  Produces the

@@ -465,3 +465,24 @@ def test_batch_of_one_and_non_square_low_res_grid(ops):
     _check_masks(mask.cpu(), want, exempt)
     bad = ((scores.cpu() - want).abs() > 1e-5 * float(want.abs().max())).any(1) & ~exempt
     assert bad.float().mean().item() < 1e-3
+
+
+def test_uint8_image_ingest_and_uint8_masks(ops):
+    """grid_sample_u8 == F.grid_sample(ToTensor(image)) bit for bit (CUDA and pinned-host sources); uint8 masks carry
+    the same values as the int64 ones."""
+    B, C, H, W = 2, 9, 300, 500
+    gen = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (B, 3, H, W), generator=gen, dtype=torch.uint8)
+    grid = (torch.rand(B, 80, 80, 2, generator=gen) * 2.2 - 1.1)
+    want = rp.grid_sample(img.float().div(255), grid)                       # ToTensor: uint8 -> fp32 / 255
+    got = ops.grid_sample_u8(img.cuda(), grid.cuda())
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(ops.grid_sample_u8(img.pin_memory(), grid.cuda()).cpu(), want)
+    xs, _ = rp.synthetic_saliency(B, seed=8)
+    g = _grid_from(xs)
+    pred = rp.synthetic_pred(B, C, seed=8).cuda()
+    plan = ops.build_inverse_plan(g.cuda(), (H, W), nchan=C, triangulation="device")
+    _, m64 = ops.inverse_fill(plan, pred, want_scores=False, want_mask=True)
+    m8 = torch.empty(B, H, W, device="cuda", dtype=torch.uint8)
+    ops.inverse_fill(plan, pred, want_scores=False, want_mask=True, mask_out=m8)
+    assert torch.equal(m8.long(), m64)
