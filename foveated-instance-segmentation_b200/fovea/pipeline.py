@@ -8,9 +8,10 @@
 Every batch is one pass of SURVEY.md section 8 rows A4-A10 (models/models.py:594-657, 909, 933-940, 1044): saliency ->
 grid, grid_sample(image, grid), inverse plan (A7 scatter, A9 point selection, Delaunay, point location) and the fused
 inverse fill writing the [B,C,H,W] score tensor and its argmax.  What this class adds is the plumbing around the
-kernels: three CUDA streams -- ingest (host->device copies + the two image-facing kernels: saliency -> grid and
-grid_sample), inverse (plan + fill), and device->host copies -- over `depth` input/output slots, so the PCIe traffic of
-batch i+1 and i-1 overlaps the HBM-bound fill of batch i.  All large buffers are allocated once.
+kernels: four CUDA streams -- ingest (host->device copies + the two image-facing kernels: saliency -> grid and
+grid_sample), plan (high priority: scatter, point selection, Delaunay, point location), fill (+ fused argmax), and
+device->host copies -- over `depth` input/output slots, so the PCIe traffic of batch i+1 and i-1 and the latency-bound
+plan of batch i+1 overlap the HBM-bound fill of batch i.  All large buffers are allocated once.
 
 `image_on_host=True` skips the bulk copy of the full-resolution image: the grid_sample kernel gathers its 4 taps per
 output pixel straight from the pinned host tensor over PCIe (the sampler touches < 1 % of a 1024^2 frame, so pulling
@@ -52,6 +53,7 @@ class ResamplePipeline:
             filter_weight = torch.from_numpy(makeGaussian(2 * R + 1, fwhm=R)).float()
         self.g1x, self.g1y = (t.to(self.dev) for t in ops.separable_factors(filter_weight))
         self.copy_in = torch.cuda.Stream(self.dev)
+        self.plan_stream = torch.cuda.Stream(self.dev, priority=-1)
         self.compute = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
         self.image_dtype = image_dtype
@@ -79,15 +81,23 @@ class ResamplePipeline:
             src = hx if self.image_on_host else s.x
             s.x_sampled = ops.grid_sample_u8(src, s.grid) if self.image_dtype == torch.uint8 else ops.grid_sample(src, s.grid)
             s.h2d_done.record(self.copy_in)
-        with torch.cuda.stream(self.compute):                # inverse stage
+        with torch.cuda.stream(self.plan_stream):            # saliency-only half of the inverse stage, high priority:
+            self.plan_stream.wait_event(s.h2d_done)          # it overlaps the HBM-bound fill of the previous batch
+            s.grid.record_stream(self.plan_stream)
+            plan = ops.build_inverse_plan(s.grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
+            planned = torch.cuda.Event()
+            planned.record(self.plan_stream)
+        with torch.cuda.stream(self.compute):                # fill (+ fused argmax)
             self.compute.wait_event(s.h2d_done)
+            self.compute.wait_event(planned)
             if s.used:
                 self.compute.wait_event(s.d2h_done)          # the slot's previous mask has left the device
-            s.grid.record_stream(self.compute)
-            plan = ops.build_inverse_plan(s.grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
+            for t in (plan.loc, plan.trirec):
+                t.record_stream(self.compute)
             ops.inverse_fill(plan, s.pred, want_scores=self.scores is not None, want_mask=True, zero_residual=True,
                              out=self.scores, mask_out=s.mask)
             s.compute_done.record(self.compute)
+        s.plan = plan                                        # keep the plan's buffers alive until the slot is reused
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(s.compute_done)
             hmask_out.copy_(s.mask, non_blocking=True)
@@ -104,11 +114,11 @@ class ResamplePipeline:
 
     def start_after(self, event):
         """Make all three pipeline streams wait for `event` (used to bracket a timed region)."""
-        for st in (self.copy_in, self.compute, self.copy_out):
+        for st in (self.copy_in, self.plan_stream, self.compute, self.copy_out):
             st.wait_event(event)
 
     def drain(self):
-        for st in (self.copy_in, self.compute, self.copy_out):
+        for st in (self.copy_in, self.plan_stream, self.compute, self.copy_out):
             st.synchronize()
 
 
