@@ -90,8 +90,24 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def synthetic_saliency(B, gh=80, gw=80, seed=0):
+    """xs = softmax(3*N(0,1) + 6*exp(-d^2/(2*8^2))) centred at a random gaze -- a peaked saliency
+    that reproduces the reference's collision / tap-spacing statistics.  (Same generator as the tests' oracle uses; kept
+    here so that the measured arm imports nothing from oracle/.)"""
+    g = torch.Generator().manual_seed(seed)
+    gaze = torch.rand(B, 2, generator=g) * 0.98
+    ii = torch.arange(gh, dtype=torch.float32)[None, :, None]
+    jj = torch.arange(gw, dtype=torch.float32)[None, None, :]
+    d2 = (ii - gaze[:, 0, None, None] * (gh - 1)) ** 2 + (jj - gaze[:, 1, None, None] * (gw - 1)) ** 2
+    logits = 3.0 * torch.randn(B, gh, gw, generator=g) + 6.0 * torch.exp(-d2 / (2 * 8.0 ** 2))
+    return torch.softmax(logits.view(B, -1), 1).view(B, 1, gh, gw), gaze
+
+
+def synthetic_pred(B, C=51, h=80, w=80, seed=0):
+    return torch.randn(B, C, h, w, generator=torch.Generator().manual_seed(seed + 1000))
+
+
 def make_inputs(cfg, seed, device=None, pinned=False):
-    from oracle.reference_port import synthetic_saliency, synthetic_pred  # input generators only
     B, H, W, C, g = cfg["B"], cfg["H"], cfg["W"], cfg["C"], cfg["g"]
     gen = torch.Generator().manual_seed(seed)
     xs, gaze = synthetic_saliency(B, g, g, seed=seed)
@@ -115,10 +131,11 @@ class Path:
 
     def __init__(self, cfg, device, triangulation, interp="tri"):
         from fovea import ops
-        from oracle.reference_port import gaussian_filter_weight  # constant construction only (models.py:510-515)
+        from fovea.models import makeGaussian   # the filter constant of models/models.py:510-515 (fwhm = radius)
         self.ops, self.cfg, self.dev, self.tri, self.interp = ops, cfg, device, triangulation, interp
         R = cfg["R"]
-        self.g1x, self.g1y = (t.to(device) for t in ops.separable_factors(gaussian_filter_weight(R, R, R)))
+        filt = torch.from_numpy(makeGaussian(2 * R + 1, fwhm=R)).float()
+        self.g1x, self.g1y = (t.to(device) for t in ops.separable_factors(filt))
         B, C, H, W = cfg["B"], cfg["C"], cfg["H"], cfg["W"]
         self.scores = torch.empty(B, C, H, W, device=device)
         self.mask = torch.empty(B, H, W, device=device, dtype=torch.int64)
