@@ -107,26 +107,26 @@ nearest_rows_kernel(const int32_t* __restrict__ winner, const short* __restrict_
 // x - s and x + s.  While a level has fewer positions than lanes the warp scans each range cooperatively (strided
 // candidates + a shuffle arg-min); afterwards every lane resolves its own positions.  The per-level candidate count is
 // <= W + (number of positions), ~11 W evaluations per row in total.
-constexpr int kDcWarps = 8;
+constexpr int kDcMaxWarps = 8;
 
 __device__ __forceinline__ void argmin_merge(unsigned& d, int& i, unsigned d2, int i2) {
   if (d2 < d || (d2 == d && i2 < i)) { d = d2; i = i2; }  // leftmost among equal distances
 }
 
-__global__ void __launch_bounds__(kDcWarps * 32)
+__global__ void __launch_bounds__(kDcMaxWarps * 32)
 nearest_rows_dc_kernel(const int32_t* __restrict__ winner, const short* __restrict__ g, uint16_t* __restrict__ loc, int hw,
                        int H, int W, int P /* smallest power of two >= W */) {
-  extern __shared__ unsigned dc_smem[];
+  extern __shared__ unsigned short dc_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y, y = blockIdx.x * kDcWarps + warp;
+  const int b = blockIdx.y, y = blockIdx.x * (blockDim.x >> 5) + warp;
   if (y >= H) return;  // warp-uniform
-  unsigned* f = dc_smem + static_cast<size_t>(warp) * (W + (W + 1) / 2);   // [W] g^2, 0xffffffff = no site in the column
-  unsigned short* opt = reinterpret_cast<unsigned short*>(f + W);        // [W] leftmost nearest column
+  unsigned short* f = dc_smem + static_cast<size_t>(warp) * 2 * W;   // [W] |g| (0xffff = no site in the column)
+  unsigned short* opt = f + W;                                        // [W] leftmost nearest column
   const size_t row = (static_cast<size_t>(b) * H + y) * W;
   bool any = false;
   for (int x = lane; x < W; x += 32) {
     const int dy = g[row + x];
-    f[x] = dy == kNoSite ? 0xffffffffu : static_cast<unsigned>(dy * dy);
+    f[x] = dy == kNoSite ? 0xffffu : static_cast<unsigned short>(dy < 0 ? -dy : dy);
     any |= dy != kNoSite;
   }
   any = __any_sync(0xffffffffu, any);
@@ -141,7 +141,7 @@ nearest_rows_dc_kernel(const int32_t* __restrict__ winner, const short* __restri
   auto cost = [&](int x, int c) {
     const unsigned fc = f[c];
     const int dx = x - c;
-    return fc == 0xffffffffu ? 0xffffffffu : fc + static_cast<unsigned>(dx * dx);   // < 2^31, see nearest_rows_kernel
+    return fc == 0xffffu ? 0xffffffffu : fc * fc + static_cast<unsigned>(dx * dx);   // < 2^31, see nearest_rows_kernel
   };
   // cooperative resolution of one position: all lanes scan [lo, hi] strided, then arg-min across the warp
   auto resolve_coop = [&](int x, int lo, int hi) {
@@ -213,15 +213,18 @@ extern "C" int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, 
   short* g = static_cast<short*>(workspace);
   nearest_columns_kernel<<<dim3(ceil_div(W, 128), B), 128, 0, s>>>(winner, g, p);
   if (int rc = check_launch("fovea_nearest_locate (columns)")) return rc;
-  // rows: the divide-and-conquer envelope needs 6 bytes of shared memory per pixel of a row and warp; rows too long for
-  // that (W > ~4800) fall back to the outward scan (exact too, but O(distance to the nearest site) per pixel)
-  const size_t smem = static_cast<size_t>(kDcWarps) * (W + (W + 1) / 2) * sizeof(unsigned);
+  // rows: the divide-and-conquer envelope keeps a row in shared memory; rows too long for that (W > ~14000) fall back to
+  // the outward scan (exact too, but O(distance to the nearest site) per pixel)
+  // (4 bytes of shared memory per pixel of a row and warp; long rows run with fewer warps per CTA so that several CTAs
+  // still fit an SM)
+  const int nw = W > 2048 ? 4 : kDcMaxWarps;
+  const size_t smem = static_cast<size_t>(nw) * 2 * W * sizeof(unsigned short);
   static const bool force_scan = [] { const char* e = getenv("FOVEA_NEAREST_SCAN"); return e && e[0] == '1'; }();
   if (smem <= 227 * 1024 && !force_scan) {
     int P = 1;
     while (P < W) P <<= 1;
     FOVEA_CUDA(cudaFuncSetAttribute(nearest_rows_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    nearest_rows_dc_kernel<<<dim3(ceil_div(H, kDcWarps), B), kDcWarps * 32, smem, s>>>(winner, g, loc, h * w, H, W, P);
+    nearest_rows_dc_kernel<<<dim3(ceil_div(H, nw), B), nw * 32, smem, s>>>(winner, g, loc, h * w, H, W, P);
   } else {
     nearest_rows_kernel<<<dim3(ceil_div(W, 256), H, B), 256, 0, s>>>(winner, g, loc, h * w, H, W);
   }
