@@ -140,7 +140,10 @@ __device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsi
   if (code < kPendingCode) nb_slot(A, code >> 2, code & 3) = static_cast<unsigned short>(me);
 }
 
-__global__ void __launch_bounds__(kDtThreads, 1)
+#ifndef DT_MAXNREG
+#define DT_MAXNREG 48   // 1024 threads x 48 registers leave 16 K registers per SM: one inverse_fill CTA (256 x 64) can
+#endif                  // co-reside and use the issue slots this barrier-bound kernel leaves idle (pipelined schedule)
+__global__ void __maxnreg__(DT_MAXNREG)
 delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
                 uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
                 int max_rounds, int32_t* __restrict__ dbg, unsigned short* __restrict__ row_ws,

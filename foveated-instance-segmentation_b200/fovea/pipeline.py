@@ -26,8 +26,8 @@ from ._lib import FoveaError
 
 
 class _Slot:
-    def __init__(self, B, C, H, W, g, device, image_on_host, image_dtype, mask_dtype):
-        self.x = None if image_on_host else torch.empty(B, 3, H, W, device=device, dtype=image_dtype)
+    def __init__(self, B, C, H, W, g, device, n_copy, image_dtype, mask_dtype):
+        self.x = torch.empty(n_copy, 3, H, W, device=device, dtype=image_dtype) if n_copy else None
         self.xs = torch.empty(B, 1, g, g, device=device)
         self.pred = torch.empty(B, C, g, g, device=device)
         self.mask = torch.empty(B, H, W, device=device, dtype=mask_dtype)
@@ -47,7 +47,7 @@ class ResamplePipeline:
             raise FoveaError("ResamplePipeline needs a CUDA device: there is no CPU fallback")
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.B, self.C, self.H, self.W, self.g, self.R = B, C, H, W, g, R
-        self.tri, self.image_on_host = triangulation, image_on_host
+        self.tri = triangulation
         if filter_weight is None:
             from .models import makeGaussian       # models/models.py:510-515: fwhm = gaussian_radius
             filter_weight = torch.from_numpy(makeGaussian(2 * R + 1, fwhm=R)).float()
@@ -57,7 +57,12 @@ class ResamplePipeline:
         self.compute = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
         self.image_dtype = image_dtype
-        self.slots = [_Slot(B, C, H, W, g, self.dev, image_on_host, image_dtype, mask_dtype) for _ in range(depth)]
+        # image_on_host may be a fraction: that share of the frames (the LAST ones of the batch) is gathered over PCIe by
+        # the sampler, the rest is bulk-copied.  (Measured on the bench workload: 0 -> 3.4 k, 0.25 -> 3.9 k, 1 -> 4.3 k
+        # frames/s: gathering everything wins.)
+        frac = float(image_on_host)
+        self.n_copy = B - int(round(B * min(max(frac, 0.0), 1.0)))
+        self.slots = [_Slot(B, C, H, W, g, self.dev, self.n_copy, image_dtype, mask_dtype) for _ in range(depth)]
         self.scores = torch.empty(B, C, H, W, device=self.dev) if want_scores else None   # compute stream only
         self.n = 0
 
@@ -73,13 +78,18 @@ class ResamplePipeline:
         with torch.cuda.stream(self.copy_in):                # ingest stage: copies + the two image-facing kernels
             if s.used:
                 self.copy_in.wait_event(s.compute_done)      # the slot's previous batch has consumed its inputs
-            if not self.image_on_host:
-                s.x.copy_(hx, non_blocking=True)
+            nc = self.n_copy
             s.xs.copy_(hxs, non_blocking=True)
             s.pred.copy_(hpred, non_blocking=True)
             s.grid = ops.saliency_to_grid(s.xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
-            src = hx if self.image_on_host else s.x
-            s.x_sampled = ops.grid_sample_u8(src, s.grid) if self.image_dtype == torch.uint8 else ops.grid_sample(src, s.grid)
+            sample = ops.grid_sample_u8 if self.image_dtype == torch.uint8 else ops.grid_sample
+            parts = []
+            if nc < self.B:                                  # gathered straight from the pinned host frames
+                parts.append(sample(hx[nc:], s.grid[nc:]))
+            if nc:
+                s.x.copy_(hx[:nc], non_blocking=True)
+                parts.insert(0, sample(s.x, s.grid[:nc]))
+            s.x_sampled = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
             s.h2d_done.record(self.copy_in)
         with torch.cuda.stream(self.plan_stream):            # saliency-only half of the inverse stage, high priority:
             self.plan_stream.wait_event(s.h2d_done)          # it overlaps the HBM-bound fill of the previous batch

@@ -183,7 +183,7 @@ def test_resample_pipeline_matches_direct_path():
         plan = ops.build_inverse_plan(grid, (H, W), nchan=C, triangulation="device")
         _, mask = ops.inverse_fill(plan, pred.cuda(), want_scores=False, want_mask=True)
         want.append((ops.grid_sample(x.cuda(), grid).cpu(), mask.cpu()))
-    for on_host in (False, True):
+    for on_host in (False, True, 0.34):
         pipe = ResamplePipeline(B, C, H, W, g, R, torch.device("cuda", 0), "device", depth=2, image_on_host=on_host)
         outs = [torch.empty(B, H, W, dtype=torch.int64).pin_memory() for _ in batches]
         sampled = [pipe.submit(*bt, out) for bt, out in zip(batches, outs)]
