@@ -141,8 +141,8 @@ __device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsi
 }
 
 #ifndef DT_MAXNREG
-#define DT_MAXNREG 48   // 1024 threads x 48 registers leave 16 K registers per SM: one inverse_fill CTA (256 x 64) can
-#endif                  // co-reside and use the issue slots this barrier-bound kernel leaves idle (pipelined schedule)
+#define DT_MAXNREG 64   // (48 would let one inverse_fill CTA co-reside per SM under the pipelined schedule: measured, no gain)
+#endif
 __global__ void __maxnreg__(DT_MAXNREG)
 delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
                 uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
@@ -483,16 +483,19 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       const int t = rank < total ? (wbase + jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
       if (t < 0) continue;
       const int pa = pts[DT_V(t, 0)], pb = pts[DT_V(t, 1)], pc = pts[DT_V(t, 2)];
+      // all three neighbours are fetched and tested together (no early exit): the round's critical path is this
+      // dependent chain, and three independent chains cost one latency instead of up to three
+      unsigned code3[3];
+      int d3[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) code3[k] = DT_N(t, k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d3[k] = code3[k] < kPendingCode ? pts[DT_V(code3[k] >> 2, code3[k] & 3)] : 0;
       int found = -1;
       unsigned ucode = 0;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (found >= 0) break;
-        const unsigned code = DT_N(t, k);
-        if (code >= kPendingCode) continue;
-        const int d = pts[DT_V(code >> 2, code & 3)];
-        if (incircle_pts(pa, pb, pc, d) > 0) { found = k; ucode = code; }
-      }
+      for (int k = 2; k >= 0; --k)
+        if (code3[k] < kPendingCode && incircle_pts(pa, pb, pc, d3[k]) > 0) { found = k; ucode = code3[k]; }
       if (found < 0) continue;
       any = true;
       cand |= static_cast<unsigned>(found + 1) << (2 * it);
