@@ -532,20 +532,19 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       if (!sel) continue;
       const int k = sel - 1;
       const unsigned pri = tag | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0xFFFu) << 14) | static_cast<unsigned>(t);
-      // Check the claims in dependency order: a triangle whose lock is not mine may be rewritten by its owner
-      // right now, so nothing is read from it (its neighbour codes could be mid-update or a hull marker).
-      if (A.lock[t] != pri) continue;
+      // The claims are checked in dependency order, but the loads are issued eagerly (three dependent levels instead
+      // of five): a triangle whose lock is not mine may be rewritten by its owner right now, so what is read from it
+      // may be mid-update -- such values are only used as (always in-range: 14-bit) indices of further loads and
+      // discarded with the claim.
+      const unsigned lt = A.lock[t];
       const unsigned ucode = DT_N(t, k);
-      const int u = ucode >> 2, ku = ucode & 3;
-      if (A.lock[u] != pri) continue;
       const unsigned n_ca = DT_N(t, (k + 1) % 3), n_ab = DT_N(t, (k + 2) % 3);
+      const int u = ucode < kPendingCode ? static_cast<int>(ucode >> 2) : t, ku = ucode & 3;  // (a hull marker is no index)
+      const unsigned lu = A.lock[u];
       const unsigned n_bd = DT_N(u, (ku + 1) % 3), n_dc = DT_N(u, (ku + 2) % 3);
-      bool win = true;
-      if (n_ca < kPendingCode) win = win && A.lock[n_ca >> 2] == pri;
-      if (n_ab < kPendingCode) win = win && A.lock[n_ab >> 2] == pri;
-      if (n_bd < kPendingCode) win = win && A.lock[n_bd >> 2] == pri;
-      if (n_dc < kPendingCode) win = win && A.lock[n_dc >> 2] == pri;
-      if (!win) continue;
+      const unsigned l1 = n_ca < kPendingCode ? A.lock[n_ca >> 2] : pri, l2 = n_ab < kPendingCode ? A.lock[n_ab >> 2] : pri;
+      const unsigned l3 = n_bd < kPendingCode ? A.lock[n_bd >> 2] : pri, l4 = n_dc < kPendingCode ? A.lock[n_dc >> 2] : pri;
+      if (lt != pri || ucode >= kPendingCode || lu != pri || l1 != pri || l2 != pri || l3 != pri || l4 != pri) continue;
       const unsigned short a = DT_V(t, k), bq = DT_V(t, (k + 1) % 3), c = DT_V(t, (k + 2) % 3);
       const unsigned short d = DT_V(u, ku);
       // t <- (a,b,d), u <- (a,d,c); the new diagonal (a,d) is opposite v1 in t and opposite v2 in u
