@@ -227,13 +227,14 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__
 
 // ------------------------------------------------------------------------------------------------ A9 location
 // Stage 3 is split in two kernels.  locate_pixels (below) resolves, for every full-resolution pixel, which low-res
-// node or which triangle of the mesh produces its value -- 4 B per pixel, a function of the sampling grid only.
+// node or which triangle of the mesh produces its value -- 2 B per pixel, a function of the sampling grid only.
 // inverse_fill then streams the C channels of every pixel from that map with no walks and no divergent loops, so
 // the store-bound kernel runs at a register count / occupancy chosen for streaming, and the location work can
 // overlap the encoder on a side stream (it does not depend on `pred`).
 //
 //   loc[b,y,x] >= 0        : id of the triangle that owns pixel (y,x)          (interp2d.py:58 find_simplex)
-//   loc[b,y,x] = -(n+1)    : the pixel received low-res node n directly        (models/models.py:650-651);
+//   loc[b,y,x] = -(n+1)    : the pixel received low-res node n directly        (models/models.py:650-651);   [signed,
+//                            in-kernel form; stored as 16 bits, see encode_loc]
 //                            n == h*w: no value (outside the triangulation)    -> the NaN row of the value table
 
 // `loc` is stored in 16 bits per pixel (the fill kernel's only per-pixel read stream: halving it is worth 6 % of the

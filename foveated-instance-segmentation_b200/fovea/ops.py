@@ -444,7 +444,7 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
 
 def probe_store_ceiling(scores, side_read=None):
     """Diagnostic: overwrite `scores` [B,C,H,W] with the store pattern of fovea_inverse_fill and no computation;
-    `side_read` [B,H,W] int32 adds the fill kernel's 4-byte-per-pixel read stream."""
+    `side_read` (any int32 buffer of >= B*H*W/2 elements) adds the fill kernel's 2-byte-per-pixel `loc` read stream."""
     s = _req(scores, torch.float32, "scores", 4)
     B, Cc, H, W = s.shape
     if side_read is not None:
