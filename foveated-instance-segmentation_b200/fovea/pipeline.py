@@ -184,12 +184,13 @@ class DevicePipeline:
                 plan = ops.build_nearest_plan(grid, (self.H, self.W), nchan=self.C)
             else:
                 plan = ops.build_inverse_plan(grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
-            planned = torch.cuda.Event()
+            table = ops.box4_table(pred)                     # A8 at the nodes: also off the fill stream, which then
+            planned = torch.cuda.Event()                     # carries nothing but back-to-back fills
             planned.record(self.plan_stream)
         with torch.cuda.stream(self.fill_stream):
-            self.fill_stream.wait_event(ready)
-            table = ops.box4_table(pred)
             self.fill_stream.wait_event(planned)
+            for t in (table, plan.loc, plan.trirec):
+                t.record_stream(self.fill_stream)
             if time_fill:
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 t0.record(self.fill_stream)
