@@ -484,7 +484,10 @@ constexpr int kFillThreads = FOVEA_FILL_THREADS;
 #define FOVEA_FILL_TILES_Y 1
 #endif
 constexpr int kFillTilesY = FOVEA_FILL_TILES_Y;  // vertically adjacent tiles streamed by one CTA
-constexpr int kFillTileW = 128, kFillTileH = kFillThreads / 32;  // 4 warps across, each 32 x 4 pixels  // CTA tile; one warp covers 32 x 4 pixels (8 lanes x 4 px, 4 rows)
+// CTA tile = WX warps across x (8 / WX) down, one warp = 32 x 4 pixels.  Measured (64 frames of 1024^2): WX = 8
+// (256 x 4 tile) 2.50 ms, WX = 4 (128 x 8) 2.54, WX = 2 (64 x 16) 2.56, WX = 1 (32 x 32) 2.64: long row segments per
+// CTA are kinder to the DRAM than square tiles are to the L1.  Narrow canvases use WX = 4.
+constexpr int kFillTileW = 128, kFillTileH = kFillThreads / 32;  // the WX = 4 tile (also the store-ceiling probe's)
 
 // The table rows of the three vertices of one pixel, G channels each.
 template <int G>
@@ -649,16 +652,17 @@ __device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, cons
 // One CTA streams kFillTilesY vertically adjacent 128 x 8 tiles: neighbouring tiles share most of their triangles, so
 // the table rows fetched for one tile are L1 hits for the next (CTAs are handed to SMs round-robin, so ACROSS CTAs
 // there is no such reuse).
-template <bool kScores, bool kMask, int G>
+template <bool kScores, bool kMask, int G, int WX>
 __global__ void __launch_bounds__(kFillThreads, (G == 8 ? 2 : 4) * 256 / kFillThreads)
 inverse_fill_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__ trirec, const float* __restrict__ table,
                     float* __restrict__ scores, long long* __restrict__ mask, FillParams p) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
+  constexpr int kTileH = 4 * (kFillThreads / 32 / WX);
+  const int x0 = blockIdx.x * (32 * WX) + (warp % WX) * 32 + (lane & 7) * 4;
   if (x0 >= p.W) return;
   for (int ty = 0; ty < kFillTilesY; ++ty) {
-    const int y = (blockIdx.y * kFillTilesY + ty) * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
+    const int y = (blockIdx.y * kFillTilesY + ty) * kTileH + (warp / WX) * 4 + (lane >> 3);
     if (y >= p.H) return;
     fill_tile<kScores, kMask, G>(loc, trirec, table, scores, mask, p, b, x0, y);
   }
@@ -812,16 +816,17 @@ static bool fill_wide_requested() {
   return v;
 }
 
-template <int G>
+template <int G, int WX>
 static int launch_fill(const uint16_t* loc, const TriRec* recs, const float* table, float* scores, long long* mk,
                        const FillParams& p, int B, cudaStream_t s) {
-  dim3 grid(ceil_div(p.W, kFillTileW), ceil_div(p.H, kFillTileH * kFillTilesY), B);
+  constexpr int kTileH = 4 * (kFillThreads / 32 / WX);
+  dim3 grid(ceil_div(p.W, 32 * WX), ceil_div(p.H, kTileH * kFillTilesY), B);
   if (scores && mk)
-    inverse_fill_kernel<true, true, G><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
+    inverse_fill_kernel<true, true, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   else if (scores)
-    inverse_fill_kernel<true, false, G><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
+    inverse_fill_kernel<true, false, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   else
-    inverse_fill_kernel<false, true, G><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
+    inverse_fill_kernel<false, true, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   return check_launch("fovea_inverse_fill");
 }
 
@@ -834,7 +839,7 @@ extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const
                 "fovea_inverse_fill: bad sizes");
   FOVEA_REQUIRE(W % 4 == 0, "fovea_inverse_fill: W=%d must be a multiple of 4 (128-bit stores)", W);
   FOVEA_REQUIRE(H <= 16384 && W <= 16384, "fovea_inverse_fill: canvas side must be <= 16384");
-  FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_inverse_fill: B or H too large for the grid");
+  FOVEA_REQUIRE(B <= 65535 && ceil_div(H, 4) <= 65535, "fovea_inverse_fill: B or H too large for the grid");
   FOVEA_REQUIRE(static_cast<long long>(h) * w + 2 <= 32768 && static_cast<long long>(h) * w * Cs * 4 < (1ll << 32),
                 "fovea_inverse_fill: value table too large (rows must fit 15 bits, bytes 32 bits)");
   FOVEA_REQUIRE(!mask_u8 || C <= 256, "fovea_inverse_fill: uint8 masks need C <= 256 (C=%d)", C);
@@ -844,7 +849,9 @@ extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const
   long long* mk = reinterpret_cast<long long*>(mask);
   // 8-channel groups (256-bit table loads) need 32-byte aligned rows: Cs % 8 == 0 and a 32-byte aligned table
   const bool wide = Cs % 8 == 0 && (reinterpret_cast<uintptr_t>(table) & 31u) == 0 && fill_wide_requested();
-  return wide ? launch_fill<8>(loc, recs, table, scores, mk, p, B, s) : launch_fill<4>(loc, recs, table, scores, mk, p, B, s);
+  if (wide) return launch_fill<8, 4>(loc, recs, table, scores, mk, p, B, s);
+  return W >= 256 ? launch_fill<4, 8>(loc, recs, table, scores, mk, p, B, s)
+                  : launch_fill<4, 4>(loc, recs, table, scores, mk, p, B, s);
 }
 
 extern "C" int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, int C, int H, int W,

@@ -93,7 +93,6 @@ class ResamplePipeline:
             s.h2d_done.record(self.copy_in)
         with torch.cuda.stream(self.plan_stream):            # saliency-only half of the inverse stage, high priority:
             self.plan_stream.wait_event(s.h2d_done)          # it overlaps the HBM-bound fill of the previous batch
-            s.grid.record_stream(self.plan_stream)
             plan = ops.build_inverse_plan(s.grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
             planned = torch.cuda.Event()
             planned.record(self.plan_stream)
@@ -102,8 +101,6 @@ class ResamplePipeline:
             self.compute.wait_event(planned)
             if s.used:
                 self.compute.wait_event(s.d2h_done)          # the slot's previous mask has left the device
-            for t in (plan.loc, plan.trirec):
-                t.record_stream(self.compute)
             ops.inverse_fill(plan, s.pred, want_scores=self.scores is not None, want_mask=True, zero_residual=True,
                              out=self.scores, mask_out=s.mask)
             s.compute_done.record(self.compute)
@@ -188,9 +185,9 @@ class DevicePipeline:
             planned = torch.cuda.Event()                     # carries nothing but back-to-back fills
             planned.record(self.plan_stream)
         with torch.cuda.stream(self.fill_stream):
-            self.fill_stream.wait_event(planned)
-            for t in (table, plan.loc, plan.trirec):
-                t.record_stream(self.fill_stream)
+            self.fill_stream.wait_event(planned)             # (plan / table buffers stay referenced in self.live until
+                                                             # `depth` batches later: no record_stream, whose deferred
+                                                             # frees make the caching allocator grow and cudaMalloc)
             if time_fill:
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 t0.record(self.fill_stream)
