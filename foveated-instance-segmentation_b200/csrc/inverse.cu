@@ -486,7 +486,8 @@ constexpr int kFillThreads = FOVEA_FILL_THREADS;
 constexpr int kFillTilesY = FOVEA_FILL_TILES_Y;  // vertically adjacent tiles streamed by one CTA
 // CTA tile = WX warps across x (8 / WX) down, one warp = 32 x 4 pixels.  Measured (64 frames of 1024^2): WX = 8
 // (256 x 4 tile) 2.50 ms, WX = 4 (128 x 8) 2.54, WX = 2 (64 x 16) 2.56, WX = 1 (32 x 32) 2.64: long row segments per
-// CTA are kinder to the DRAM than square tiles are to the L1.  Narrow canvases use WX = 4.
+// CTA are kinder to the DRAM than square tiles are to the L1 (512 x 4 with 16 warps: 2.50 too, but it shares SMs worse
+// under the pipelined schedule).  Narrow canvases use WX = 4.
 constexpr int kFillTileW = 128, kFillTileH = kFillThreads / 32;  // the WX = 4 tile (also the store-ceiling probe's)
 
 // The table rows of the three vertices of one pixel, G channels each.
