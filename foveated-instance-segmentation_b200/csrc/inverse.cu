@@ -484,11 +484,17 @@ constexpr int kFillThreads = FOVEA_FILL_THREADS;
 #define FOVEA_FILL_TILES_Y 1
 #endif
 constexpr int kFillTilesY = FOVEA_FILL_TILES_Y;  // vertically adjacent tiles streamed by one CTA
-// CTA tile = WX warps across x (8 / WX) down, one warp = 32 x 4 pixels.  Measured (64 frames of 1024^2): WX = 8
-// (256 x 4 tile) 2.50 ms, WX = 4 (128 x 8) 2.54, WX = 2 (64 x 16) 2.56, WX = 1 (32 x 32) 2.64: long row segments per
-// CTA are kinder to the DRAM than square tiles are to the L1 (512 x 4 with 16 warps: 2.50 too, but it shares SMs worse
-// under the pipelined schedule).  Narrow canvases use WX = 4.
-constexpr int kFillTileW = 128, kFillTileH = kFillThreads / 32;  // the WX = 4 tile (also the store-ceiling probe's)
+// Thread -> pixel mapping.  One thread = 4 consecutive pixels; one warp = WL lanes across x (32 / WL) rows; one CTA =
+// WX warps across x (8 / WX) down.  What matters is how few row segments one warp-wide store touches -- measured on
+// 64 frames of 1024^2 (ms per launch, fraction of the 6 542 GB/s peak):
+//   warp 16 px x 8 rows (WL 4): 2.52 (0.83)   32 x 4 (WL 8): 2.50-2.64 depending on the CTA tile (0.79-0.84)
+//   warp 64 px x 2 rows (WL 16): 2.28-2.29 (0.915-0.918) for CTA tiles 64x16, 128x8, 256x4    128 x 1 (WL 32): 2.29-2.36
+// i.e. two 256-byte segments per store instruction instead of four 128-byte ones is worth 9 %.  WL = 16 with a 128 x 8
+// CTA tile (WX = 2) is the default; canvases narrower than 128 pixels use WX = 1.
+#ifndef FOVEA_FILL_WL
+#define FOVEA_FILL_WL 16  // lanes of a warp across a row (x 4 pixels each); the warp covers 32 / WL rows
+#endif
+constexpr int kFillTileW = 128, kFillTileH = kFillThreads / 32;  // the default CTA tile (also the store-ceiling probe's)
 
 // The table rows of the three vertices of one pixel, G channels each.
 template <int G>
@@ -659,11 +665,12 @@ inverse_fill_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__
                     float* __restrict__ scores, long long* __restrict__ mask, FillParams p) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kTileH = 4 * (kFillThreads / 32 / WX);
-  const int x0 = blockIdx.x * (32 * WX) + (warp % WX) * 32 + (lane & 7) * 4;
+  constexpr int WL = FOVEA_FILL_WL, kWarpW = 4 * WL, kWarpH = 32 / WL;
+  constexpr int kTileH = kWarpH * (kFillThreads / 32 / WX);
+  const int x0 = blockIdx.x * (kWarpW * WX) + (warp % WX) * kWarpW + (lane % WL) * 4;
   if (x0 >= p.W) return;
   for (int ty = 0; ty < kFillTilesY; ++ty) {
-    const int y = (blockIdx.y * kFillTilesY + ty) * kTileH + (warp / WX) * 4 + (lane >> 3);
+    const int y = (blockIdx.y * kFillTilesY + ty) * kTileH + (warp / WX) * kWarpH + (lane / WL);
     if (y >= p.H) return;
     fill_tile<kScores, kMask, G>(loc, trirec, table, scores, mask, p, b, x0, y);
   }
@@ -675,8 +682,9 @@ __global__ void __launch_bounds__(kFillThreads)
 store_ceiling_kernel(float* __restrict__ scores, const int4* __restrict__ side_read, int C, int H, int W) {
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * kFillTileW + (warp & 3) * 32 + (lane & 7) * 4;
-  const int y = blockIdx.y * kFillTileH + (warp >> 2) * 4 + (lane >> 3);
+  constexpr int WL = FOVEA_FILL_WL, WX = 2;  // the default mapping of inverse_fill_kernel
+  const int x0 = blockIdx.x * kFillTileW + (warp % WX) * (4 * WL) + (lane % WL) * 4;
+  const int y = blockIdx.y * kFillTileH + (warp / WX) * (32 / WL) + (lane / WL);
   if (x0 >= W || y >= H) return;
   const size_t plane = static_cast<size_t>(H) * W;
   const size_t pix = static_cast<size_t>(y) * W + x0;
@@ -820,8 +828,8 @@ static bool fill_wide_requested() {
 template <int G, int WX>
 static int launch_fill(const uint16_t* loc, const TriRec* recs, const float* table, float* scores, long long* mk,
                        const FillParams& p, int B, cudaStream_t s) {
-  constexpr int kTileH = 4 * (kFillThreads / 32 / WX);
-  dim3 grid(ceil_div(p.W, 32 * WX), ceil_div(p.H, kTileH * kFillTilesY), B);
+  constexpr int kTileH = (32 / FOVEA_FILL_WL) * (kFillThreads / 32 / WX);
+  dim3 grid(ceil_div(p.W, 4 * FOVEA_FILL_WL * WX), ceil_div(p.H, kTileH * kFillTilesY), B);
   if (scores && mk)
     inverse_fill_kernel<true, true, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
   else if (scores)
@@ -850,9 +858,9 @@ extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const
   long long* mk = reinterpret_cast<long long*>(mask);
   // 8-channel groups (256-bit table loads) need 32-byte aligned rows: Cs % 8 == 0 and a 32-byte aligned table
   const bool wide = Cs % 8 == 0 && (reinterpret_cast<uintptr_t>(table) & 31u) == 0 && fill_wide_requested();
-  if (wide) return launch_fill<8, 4>(loc, recs, table, scores, mk, p, B, s);
-  return W >= 256 ? launch_fill<4, 8>(loc, recs, table, scores, mk, p, B, s)
-                  : launch_fill<4, 4>(loc, recs, table, scores, mk, p, B, s);
+  if (wide) return launch_fill<8, 2>(loc, recs, table, scores, mk, p, B, s);
+  return W >= 128 ? launch_fill<4, 2>(loc, recs, table, scores, mk, p, B, s)
+                  : launch_fill<4, 1>(loc, recs, table, scores, mk, p, B, s);
 }
 
 extern "C" int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, int C, int H, int W,
