@@ -683,6 +683,8 @@ store_ceiling_kernel(float* __restrict__ scores, const int4* __restrict__ side_r
   const int b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int WL = FOVEA_FILL_WL, WX = 2;  // the default mapping of inverse_fill_kernel
+  static_assert(4 * WL * WX == kFillTileW && (32 / WL) * (kFillThreads / 32 / WX) == kFillTileH,
+                "the probe's launch grid assumes the default 128 x 8 CTA tile");
   const int x0 = blockIdx.x * kFillTileW + (warp % WX) * (4 * WL) + (lane % WL) * 4;
   const int y = blockIdx.y * kFillTileH + (warp / WX) * (32 / WL) + (lane / WL);
   if (x0 >= W || y >= H) return;
