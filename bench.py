@@ -6,7 +6,8 @@
 One "step" = one pass of the hot path over one batch of synthetic frames:
     S1 saliency -> grid, S2 grid_sample(image, grid), S3 scatter + point selection + Delaunay + walk hints +
     value table + fused inverse fill writing the [B,C,H,W] score tensor (the reference's `pred_sampled`).
-`value`  : whole-job frames/s with inputs resident in HBM (device-timed, max over ranks).
+`value`  : whole-job frames/s with inputs resident in HBM (device-timed, max over ranks), through fovea.pipeline.
+           DevicePipeline (the plan of step i+1 overlaps the fill of step i); `serial_ms_per_step` = one stream.
 `e2e`    : the same path through the public API with HOST (pinned) buffers: H2D of image/saliency/pred every
            step, the path with the fused argmax, D2H of the int64 instance masks.
 `roofline`: the dominant kernel (inverse_fill): algorithmic bytes 4*C*H*W per frame / measured launch duration
@@ -293,7 +294,7 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
     del dpipe
 
-    # ---------------- end to end from host buffers (`e2e`): the public ResamplePipeline, three streams
+    # ---------------- end to end from host buffers (`e2e`): the public ResamplePipeline, four streams
     e2e = None
     if not args.no_e2e and args.interp == "tri":
         from fovea.pipeline import ResamplePipeline
