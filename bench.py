@@ -267,6 +267,24 @@ def main():
     serial_ms = e0.elapsed_time(e1)
     fill_ms = sum(a.elapsed_time(b) for a, b in path.fill_ms) / max(1, len(path.fill_ms))
 
+    # ---------------- mask mode: the same serial steps with the fused argmax only -- the score
+    # tensor is never materialised, stage 3 writes 8*H*W bytes per frame (int64, the reference's mask dtype) instead of
+    # 4*C*H*W.  Reported beside the headline (scores mode), not as `value`.
+    km = min(args.steps, 10)
+    for _ in range(2):
+        path.step(x, xs, pred, want_scores=False, want_mask=True)
+    barrier()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(km):
+        path.step(x, xs, pred, want_scores=False, want_mask=True)
+    m1.record()
+    barrier()
+    mask_ms = m0.elapsed_time(m1) / km
+    mask_mode = {"serial_ms_per_step": mask_ms, "frames_s_per_gpu": B / (mask_ms * 1e-3), "steps": km,
+                 "algorithmic_bytes_per_frame": 8 * H * W,
+                 "what": "grid + grid_sample + plan + inverse_fill with scores=NULL, mask=int64 (one stream)"}
+
     # ---------------- device-resident throughput (`value`): the product's DevicePipeline -- the same K steps, with the
     # saliency-only half of step i+1 (grid, A7, A9 selection, Delaunay, point location) on a high-priority stream
     # overlapping the HBM-bound fill of step i.  Every step's full work happens inside the timed region.
@@ -416,6 +434,7 @@ def main():
                          "store_only_ceiling_gbs": store_ceiling,
                          "store_plus_loc_read_ceiling_gbs": store_read_ceiling},
         }
+        line["mask_mode"] = mask_mode
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and args.interp == "tri":

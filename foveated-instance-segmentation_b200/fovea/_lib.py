@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class FoveaError(RuntimeError):
@@ -30,6 +30,9 @@ _i64 = C.c_int64
 PROTOTYPES = {
     "fovea_abi_version": (_i, []),
     "fovea_last_error": (C.c_char_p, []),
+    "fovea_saliency_input": (_i, [_p, _i, C.c_float, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_saliency_softmax": (_i, [_p, _i, _i, _p, _p]),
+    "fovea_saliency_softmax_bwd": (_i, [_p, _p, _i, _i, _p, _p]),
     "fovea_grid_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p]),
     "fovea_grid_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     "fovea_grid_resize": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),

@@ -265,21 +265,14 @@ class DeformSegmentationModule(SegmentationModuleBase):
                                     self.padding_size_y, mode, size)
         return grid, ops.grid_resize(grid, size_y)
 
-    # -- stage 0/1 glue (stock PyTorch) --------------------------------------------------------------------------
+    # -- stage 0: saliency branch (the network itself is stock PyTorch) -------------------------------------------
     def _saliency(self, x, focus_point):
-        HS, WS = self.input_size
-        max_dist = np.sqrt(HS ** 2 + WS ** 2)
-        hidx = focus_point[:, 0] * (HS - 1)                                     # :684-694
-        widx = focus_point[:, 1] * (WS - 1)
-        ii = torch.arange(HS, device=x.device)[None, :, None]
-        jj = torch.arange(WS, device=x.device)[None, None, :]
-        dist = torch.sqrt((ii - hidx[:, None, None]) ** 2 + (jj - widx[:, None, None]) ** 2)
-        focus = (dist / max_dist).unsqueeze(1) ** 2
-        x_low = b_imresize(x, self.input_size, interp="bilinear")               # :701-705
-        x_low = torch.cat((x_low, focus, focus), dim=1)
+        # :684-705: focus map + b_imresize + two cats in one launch (x may be fp32 or the loader's uint8 frame)
+        x_low = ops.saliency_input(x, focus_point.to(x.device), self.input_size)
         xs = self.net_compress(self.localization(x_low))                        # :711-713
-        xs = F.interpolate(xs, (self.grid_size_x, self.grid_size_y), mode="bilinear")
-        xs = torch.softmax(xs.view(-1, self.grid_size_x * self.grid_size_y), dim=1)  # :715-723
+        if tuple(xs.shape[-2:]) != (self.grid_size_x, self.grid_size_y):        # nn.Upsample, identity by default
+            xs = F.interpolate(xs, (self.grid_size_x, self.grid_size_y), mode="bilinear")
+        xs = ops.saliency_softmax(xs.reshape(-1, self.grid_size_x * self.grid_size_y))  # :715-723
         return xs.view(-1, 1, self.grid_size_x, self.grid_size_y)
 
     def _check_cfg(self):

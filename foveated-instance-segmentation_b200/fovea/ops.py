@@ -37,6 +37,54 @@ def _req(t, dtype, name, ndim=None):
     return t.contiguous()
 
 
+# ------------------------------------------------------------------------------------------------ stage 0
+
+def saliency_input(img, focus_point, input_size, divisor=255.0):
+    """models/models.py:684-705 in one launch: `cat(b_imresize(img, input_size, 'bilinear'), focus, focus)`.
+
+    img: [B,C,H,W] fp32 or uint8 (uint8: ToTensor's `/ divisor` is folded into the taps), on the GPU or in pinned
+    host memory; focus_point: [B,2] (h,w) in [0,1).  Returns x_low [B,C+2,HS,WS] fp32.  Not differentiable (neither
+    the image nor the gaze needs a gradient in the reference)."""
+    if not isinstance(img, torch.Tensor) or img.dtype not in (torch.float32, torch.uint8):
+        raise FoveaError("saliency_input: img must be a float32 or uint8 tensor")
+    x = _req_gather_source(img, "img", img.dtype)
+    dev = x.device if x.is_cuda else focus_point.device
+    fp = _req(focus_point.detach().to(torch.float32), torch.float32, "focus_point", 2)
+    B, Cc, H, W = x.shape
+    if fp.shape[0] != B or fp.shape[1] != 2:
+        raise FoveaError(f"saliency_input: focus_point {tuple(fp.shape)} does not match img {tuple(x.shape)}")
+    HS, WS = int(input_size[0]), int(input_size[1])
+    out = torch.empty(B, Cc + 2, HS, WS, device=dev, dtype=torch.float32)
+    _lib.call("fovea_saliency_input", _ptr(x), int(x.dtype == torch.uint8), float(divisor), _ptr(fp), B, Cc, H, W, HS,
+              WS, _ptr(out), _stream())
+    return out
+
+
+class _SaliencySoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits):
+        z = _req(logits, torch.float32, "logits", 2)
+        xs = torch.empty_like(z)
+        _lib.call("fovea_saliency_softmax", _ptr(z), z.shape[0], z.shape[1], _ptr(xs), _stream())
+        ctx.save_for_backward(xs)
+        return xs
+
+    @staticmethod
+    def backward(ctx, grad_xs):
+        xs, = ctx.saved_tensors
+        g = _req(grad_xs, torch.float32, "grad_xs", 2)
+        out = torch.empty_like(xs)
+        _lib.call("fovea_saliency_softmax_bwd", _ptr(xs), _ptr(g), xs.shape[0], xs.shape[1], _ptr(out), _stream())
+        return out
+
+
+def saliency_softmax(logits):
+    """nn.Softmax over each frame's saliency logits, models/models.py:715-723.  logits: [B,...] -> same shape, every
+    frame sums to 1; differentiable."""
+    shape = logits.shape
+    return _SaliencySoftmaxFn.apply(logits.reshape(shape[0], -1)).view(shape)
+
+
 # ------------------------------------------------------------------------------------------------ stage 1
 
 def separable_factors(filter_weight: torch.Tensor, rtol: float = 1e-5):

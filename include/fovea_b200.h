@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 8
+#define FOVEA_ABI_VERSION 9
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -48,6 +48,28 @@ typedef void* fovea_stream_t; /* cudaStream_t */
 int fovea_abi_version(void);
 /* thread-local, NUL-terminated description of the last failure in this thread ("" if none) */
 const char* fovea_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 0 -- either side of the (stock) saliency network.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* A0, models/models.py:684-705: the saliency network's input in one launch --
+ *   out[b, 0:C]  = b_imresize(img, (HS,WS), 'bilinear')      (F.interpolate, align_corners=False: 4 taps / pixel)
+ *   out[b, C]    = out[b, C+1] = ((i - hidx)^2 + (j - widx)^2) / (HS^2 + WS^2),  hidx = focus_point[b,0]*(HS-1),
+ *                  widx = focus_point[b,1]*(WS-1)            (focus map, concatenated twice as the reference does)
+ *   img [B,C,H,W] fp32, or uint8 when img_u8 != 0 (ToTensor's uint8 -> fp32 / divisor folded into the taps,
+ *                 DynamicFocus/e_preprocess_scripts/dataset.py:133-137); may be PINNED HOST memory (only 4*HS*WS
+ *                 samples per channel are touched)
+ *   focus_point [B,2] fp32 (h,w) in [0,1)     out [B,C+2,HS,WS] fp32 */
+int fovea_saliency_input(const void* img, int img_u8, float divisor, const float* focus_point, int B, int C, int H,
+                         int W, int HS, int WS, float* out, fovea_stream_t stream);
+
+/* A2, models/models.py:715-723: nn.Softmax over the n = gh*gw saliency logits of each frame (logits, xs: [B,n]);
+ * a NaN logit makes the whole frame NaN as in torch (the reference's assert, a host sync, becomes the caller's choice).
+ * Backward: grad_logits = xs * (grad_xs - sum(grad_xs * xs)). */
+int fovea_saliency_softmax(const float* logits, int B, int n, float* xs, fovea_stream_t stream);
+int fovea_saliency_softmax_bwd(const float* xs, const float* grad_xs, int B, int n, float* grad_logits,
+                               fovea_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- saliency -> sampling grid.      Replaces models/models.py:594-637 (create_grid, forward

@@ -143,3 +143,14 @@ def test_cv2_dilate_reads_chw_as_rows_cols_channels():
     v = b.copy()
     v[:, 1:] |= b[:, :-1]; v[:, :-1] |= b[:, 1:]
     assert np.array_equal(cv2.dilate(b, k, borderType=cv2.BORDER_CONSTANT, borderValue=int(0)), v)
+
+
+@pytest.mark.parametrize("name", ["module_256_lowres", "module_256_upsample"])
+def test_saliency_input_matches_reference_module(golden_dir, name):
+    """A0 (models/models.py:684-705): the oracle's focus map + x_low against the tensor the UNMODIFIED reference module
+    handed to its saliency network (captured by make_golden.py --module with a forward pre-hook)."""
+    from tiny_nets import synthetic_batch
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    feed = synthetic_batch(int(g["B"]), int(g["H"]), int(g["W"]), int(g["seed"]))
+    got = rp.saliency_input(feed["img_data"], feed["focus_point"], (80, 80))
+    np.testing.assert_allclose(got.numpy(), g["x_low"], rtol=0, atol=1e-7)

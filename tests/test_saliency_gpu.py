@@ -1,0 +1,106 @@
+"""Stage-0 kernels (8f row 3) through the C ABI against the reference's own output
+(`x_low` captured at the saliency network's input by tests/golden/make_golden.py --module) and the CPU oracle.
+
+Tolerances: x_low and the focus map 5e-6 absolute on values in [0,1].  The bilinear weights come from `real - floor(real)`
+with `real = scale*(dst+0.5)-0.5` in fp32: the cancellation leaves them ~1.5e-6 from their exact value, and whether the
+compiler contracts that expression into an FMA (nvcc does, the CPU build of torch does not) moves them by as much, so two
+correct fp32 evaluations differ by up to ~3e-6 (both are that far from the fp64 result).  Softmax 1e-6 relative to the frame's largest probability forward,
+1e-5 relative backward.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as rp
+from tiny_nets import synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (run on the B200 box with -m gpu)")
+    from fovea import ops as _ops
+    _ops._lib.load()
+    return _ops
+
+
+@pytest.mark.parametrize("name", ["module_256_lowres", "module_256_upsample"])
+def test_saliency_input_matches_reference_module(ops, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    feed = synthetic_batch(int(g["B"]), int(g["H"]), int(g["W"]), int(g["seed"]))
+    got = ops.saliency_input(feed["img_data"].cuda(), feed["focus_point"].cuda(), (80, 80))
+    np.testing.assert_allclose(got.cpu().numpy(), g["x_low"], rtol=0, atol=5e-6)
+    assert torch.equal(got[:, 3], got[:, 4])
+
+
+@pytest.mark.parametrize("B,C,H,W,HS,WS", [(3, 3, 1024, 1024, 80, 80), (2, 4, 333, 517, 40, 64), (1, 1, 64, 48, 80, 80)])
+def test_saliency_input_matches_oracle(ops, B, C, H, W, HS, WS):
+    """Down- and up-scaling, non-square frames, RGBA; the pinned-host source gives the same bits as the device one."""
+    gen = torch.Generator().manual_seed(H + W)
+    x = torch.rand(B, C, H, W, generator=gen)
+    fp = torch.rand(B, 2, generator=gen) * 0.98
+    want = rp.saliency_input(x, fp, (HS, WS))
+    got = ops.saliency_input(x.cuda(), fp.cuda(), (HS, WS))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=5e-6)
+    got_host = ops.saliency_input(x.pin_memory(), fp.cuda(), (HS, WS))
+    assert torch.equal(got_host, got)
+
+
+def test_saliency_input_uint8_folds_totensor(ops):
+    gen = torch.Generator().manual_seed(11)
+    x8 = torch.randint(0, 256, (2, 3, 512, 640), dtype=torch.uint8, generator=gen)
+    fp = torch.rand(2, 2, generator=gen)
+    got = ops.saliency_input(x8.cuda(), fp.cuda(), (80, 80))
+    # bit-identical to converting first (ToTensor: uint8 -> fp32 / 255), which is what the fp32 kernel sees
+    ref = ops.saliency_input((x8.float() / 255.0).cuda(), fp.cuda(), (80, 80))
+    assert torch.equal(got, ref)
+    np.testing.assert_allclose(got.cpu().numpy(), rp.saliency_input(x8.float() / 255.0, fp, (80, 80)).numpy(), rtol=0,
+                               atol=5e-6)
+
+
+def test_saliency_input_rejects_cpu_and_bad_shapes(ops):
+    from fovea import FoveaError
+    with pytest.raises(FoveaError):
+        ops.saliency_input(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2).cuda(), (4, 4))        # pageable host image
+    with pytest.raises(FoveaError):
+        ops.saliency_input(torch.zeros(1, 3, 8, 8).cuda(), torch.zeros(2, 2).cuda(), (4, 4))  # batch mismatch
+    with pytest.raises(FoveaError):
+        ops.saliency_input(torch.zeros(1, 3, 8, 8).double().cuda(), torch.zeros(1, 2).cuda(), (4, 4))
+
+
+@pytest.mark.parametrize("B,n", [(64, 6400), (3, 1000), (2, 7), (1, 40 * 80)])
+def test_saliency_softmax_forward_backward(ops, B, n):
+    gen = torch.Generator().manual_seed(n)
+    z = (torch.randn(B, n, generator=gen) * 4).double()
+    gout = torch.randn(B, n, generator=gen).double()
+    zr = z.clone().requires_grad_(True)
+    want = torch.softmax(zr, dim=1)
+    want.backward(gout)
+    zd = z.float().cuda().requires_grad_(True)
+    got = ops.saliency_softmax(zd)
+    got.backward(gout.float().cuda())
+    scale = want.detach().max(dim=1, keepdim=True).values
+    assert ((got.detach().cpu().double() - want.detach()).abs() / scale).max().item() <= 1e-6
+    assert (got.detach().sum(1).cpu() - 1).abs().max().item() <= 1e-5
+    gscale = zr.grad.abs().max().item()
+    assert (zd.grad.cpu().double() - zr.grad).abs().max().item() <= 1e-5 * gscale
+    # against the oracle's A2 restatement (torch CPU fp32) as well
+    xs = rp.saliency_normalise(z.float().view(B, 1, 1, n), 1, n).view(B, n)
+    assert ((got.detach().cpu() - xs).abs() / scale.float()).max().item() <= 1e-6
+
+
+def test_saliency_softmax_shapes_and_nan(ops):
+    z = torch.randn(4, 1, 80, 80).cuda()
+    xs = ops.saliency_softmax(z)
+    assert xs.shape == z.shape
+    z[2, 0, 17, 3] = float("nan")
+    xs = ops.saliency_softmax(z)
+    assert torch.isnan(xs[2]).all() and torch.isfinite(xs[[0, 1, 3]]).all()     # torch: one NaN poisons its frame only
+    z = torch.full((2, 50), -1e30).cuda()
+    z[0, 3] = 80.0
+    xs = ops.saliency_softmax(z)
+    assert xs[0, 3].item() == 1.0 and torch.allclose(xs[1], torch.full((50,), 0.02).cuda())
