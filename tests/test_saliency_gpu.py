@@ -88,10 +88,10 @@ def test_saliency_softmax_forward_backward(ops, B, n):
     assert (got.detach().sum(1).cpu() - 1).abs().max().item() <= 1e-5
     gscale = zr.grad.abs().max().item()
     assert (zd.grad.cpu().double() - zr.grad).abs().max().item() <= 1e-5 * gscale
-    # against the oracle's A2 restatement (torch CPU fp32) as well: two fp32 evaluations, each within 1e-6 of the fp64 one
+    # against the oracle's A2 restatement (torch CPU fp32) as well: that fp32 evaluation is itself up to ~1.2e-6 from the
+    # fp64 one on 6400 logits (measured), the kernel <= 1e-6 (asserted above)
     xs = rp.saliency_normalise(z.float().view(B, 1, 1, n), 1, n).view(B, n)
-    assert ((xs.double() - want.detach()).abs() / scale).max().item() <= 1e-6
-    assert ((got.detach().cpu() - xs).abs() / scale.float()).max().item() <= 2e-6
+    assert ((got.detach().cpu() - xs).abs() / scale.float()).max().item() <= 3e-6
 
 
 def test_saliency_softmax_shapes_and_nan(ops):
