@@ -11,6 +11,7 @@
 #include "mesh.cuh"
 #include "select.cuh"
 #include "taps.cuh"
+#include "tma.cuh"
 
 namespace fovea {
 
@@ -699,6 +700,49 @@ store_ceiling_kernel(float* __restrict__ scores, const int4* __restrict__ side_r
   for (int c = 0; c < C; ++c, o += plane) __stcs(reinterpret_cast<float4*>(o), make_float4(f, f + 1.f, f + 2.f, f + 3.f));
 }
 
+// The same probe with the stores routed through shared memory and TMA (cp.async.bulk.tensor): every thread parks its
+// 4 pixels of 4 channel planes with st.shared.v4, one elected thread issues one 128 x 8 tile store per plane.
+// kStages tiles of 4 planes (16 KB each) are in flight per CTA.
+constexpr int kTmaG = 4;
+template <int kStages>
+__global__ void __launch_bounds__(kFillThreads)
+store_ceiling_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* __restrict__ side_read, int C, int H,
+                         int W) {
+  extern __shared__ __align__(128) float tma_stage[];  // [kStages][kTmaG][kFillTileH][kFillTileW]
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int WL = FOVEA_FILL_WL, WX = 2;
+  const int tx = (warp % WX) * (4 * WL) + (lane % WL) * 4, ty = (warp / WX) * (32 / WL) + (lane / WL);
+  const int x0 = blockIdx.x * kFillTileW + tx, y = blockIdx.y * kFillTileH + ty;
+  const bool live = x0 < W && y < H;
+  const size_t plane = static_cast<size_t>(H) * W;
+  float f = static_cast<float>(lane);
+  if (side_read && live) {
+    const int2 l = __ldcs(reinterpret_cast<const int2*>(side_read) + (static_cast<size_t>(b) * plane +
+                                                                       static_cast<size_t>(y) * W + x0) / 4);
+    f += static_cast<float>(l.x ^ l.y);
+  }
+  constexpr int kPlaneFloats = kFillTileH * kFillTileW;
+  int stage = 0;
+  for (int c = 0; c < C; c += kTmaG) {
+    float* buf = tma_stage + stage * (kTmaG * kPlaneFloats);
+#pragma unroll
+    for (int e = 0; e < kTmaG; ++e)
+      *reinterpret_cast<float4*>(buf + e * kPlaneFloats + ty * kFillTileW + tx) = make_float4(f, f + 1.f, f + 2.f, f + 3.f);
+    fence_proxy_async();
+    if (threadIdx.x == 0) tma_wait_read<kStages - 2>();  // the tile the NEXT iteration overwrites has been read
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int e = 0; e < kTmaG; ++e)
+        if (c + e < C) tma_store_tile(&tmap, buf + e * kPlaneFloats, blockIdx.x * kFillTileW, blockIdx.y * kFillTileH, b * C + c + e);
+      tma_commit();
+    }
+    stage = stage + 1 == kStages ? 0 : stage + 1;
+  }
+  if (threadIdx.x == 0) tma_wait_read<0>();
+}
+
 // torch.argmax(scores, dim=1) as a stand-alone streaming pass
 __global__ void __launch_bounds__(256)
 argmax_classes_kernel(const float* __restrict__ scores, long long* __restrict__ mask, int C, long long HW,
@@ -870,6 +914,17 @@ extern "C" int fovea_probe_store_ceiling(float* scores, const int32_t* side_read
   FOVEA_REQUIRE(scores && B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "fovea_probe_store_ceiling: bad arguments");
   FOVEA_REQUIRE(B <= 65535 && ceil_div(H, kFillTileH) <= 65535, "fovea_probe_store_ceiling: B or H too large");
   dim3 grid(ceil_div(W, kFillTileW), ceil_div(H, kFillTileH), B);
+  static const int tma_stages = [] { const char* e = getenv("FOVEA_PROBE_TMA"); return e ? atoi(e) : 0; }();
+  if (tma_stages >= 2 && W >= kFillTileW) {  // experiment: the same stores through shared memory + TMA
+    CUtensorMap map;
+    if (int rc = make_plane_store_map(&map, scores, static_cast<long long>(B) * C, H, W, kFillTileW, kFillTileH)) return rc;
+    const int st = tma_stages >= 3 ? 3 : 2;
+    const size_t smem = static_cast<size_t>(st) * kTmaG * kFillTileH * kFillTileW * sizeof(float);
+    auto kern = st == 3 ? store_ceiling_tma_kernel<3> : store_ceiling_tma_kernel<2>;
+    FOVEA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kFillThreads, smem, static_cast<cudaStream_t>(stream)>>>(map, reinterpret_cast<const int4*>(side_read), C, H, W);
+    return check_launch("fovea_probe_store_ceiling (tma)");
+  }
   store_ceiling_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       scores, reinterpret_cast<const int4*>(side_read), C, H, W);
   return check_launch("fovea_probe_store_ceiling");
