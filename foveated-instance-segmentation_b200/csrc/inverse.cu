@@ -743,6 +743,22 @@ store_ceiling_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int4* _
   if (threadIdx.x == 0) tma_wait_read<0>();
 }
 
+// mask[b,p] = lut[b][labels[b,p]]: widens the uint8 output of a reduced-channel fill (fovea.ops.inverse_mask_c1) to the
+// reference's int64 class ids.  4 pixels per thread: one 32-bit load, two 128-bit streaming stores.
+__global__ void __launch_bounds__(256)
+relabel_mask_kernel(const uchar4* __restrict__ labels, const long long* __restrict__ lut, long long quads, int nl,
+                    longlong2* __restrict__ mask) {
+  const int b = blockIdx.y;
+  const long long* l = lut + static_cast<size_t>(b) * nl;
+  const uchar4* in = labels + static_cast<size_t>(b) * quads;
+  longlong2* out = mask + static_cast<size_t>(b) * quads * 2;
+  for (long long q = blockIdx.x * 256ll + threadIdx.x; q < quads; q += 256ll * gridDim.x) {
+    const uchar4 v = __ldcs(in + q);
+    __stcs(out + 2 * q, make_longlong2(__ldg(l + min(static_cast<int>(v.x), nl - 1)), __ldg(l + min(static_cast<int>(v.y), nl - 1))));
+    __stcs(out + 2 * q + 1, make_longlong2(__ldg(l + min(static_cast<int>(v.z), nl - 1)), __ldg(l + min(static_cast<int>(v.w), nl - 1))));
+  }
+}
+
 // torch.argmax(scores, dim=1) as a stand-alone streaming pass
 __global__ void __launch_bounds__(256)
 argmax_classes_kernel(const float* __restrict__ scores, long long* __restrict__ mask, int C, long long HW,
@@ -928,6 +944,18 @@ extern "C" int fovea_probe_store_ceiling(float* scores, const int32_t* side_read
   store_ceiling_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       scores, reinterpret_cast<const int4*>(side_read), C, H, W);
   return check_launch("fovea_probe_store_ceiling");
+}
+
+extern "C" int fovea_relabel_mask(const uint8_t* labels, const int64_t* lut, int B, int64_t HW, int nl, int64_t* mask,
+                                  fovea_stream_t stream) {
+  FOVEA_REQUIRE(labels && lut && mask && B > 0 && HW > 0 && nl > 0 && nl <= 256, "fovea_relabel_mask: bad arguments");
+  FOVEA_REQUIRE(HW % 4 == 0 && B <= 65535, "fovea_relabel_mask: H*W must be a multiple of 4 and B <= 65535");
+  const long long quads = HW / 4;
+  const int bx = static_cast<int>(quads < 256ll * kNumSMs * 8 ? (quads + 255) / 256 : kNumSMs * 8);
+  relabel_mask_kernel<<<dim3(bx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uchar4*>(labels), reinterpret_cast<const long long*>(lut), quads, nl,
+      reinterpret_cast<longlong2*>(mask));
+  return check_launch("fovea_relabel_mask");
 }
 
 extern "C" int fovea_argmax_classes(const float* scores, int B, int C, int64_t HW, int64_t* mask,

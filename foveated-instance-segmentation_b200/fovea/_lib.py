@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class FoveaError(RuntimeError):
@@ -56,6 +56,7 @@ PROTOTYPES = {
     "fovea_nearest_workspace_bytes": (_i64, [_i, _i, _i]),
     "fovea_nearest_locate": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_probe_store_ceiling": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "fovea_relabel_mask": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "fovea_argmax_classes": (_i, [_p, _i, _i, _i64, _p, _p]),
 }
 

@@ -490,6 +490,48 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
     return scores, mask
 
 
+def c1_tail_pred(cls_pred, x):
+    """The C1 decoder's tail as the reference materialises it (models/model_utils.py:298-309): class logits broadcast
+    over the map, the last one multiplied by the mask logit x = sigmoid(.) - 0.5.  -> pred [B,K,h,w]."""
+    B, K = cls_pred.shape
+    pred = cls_pred[:, :, None, None].expand(B, K, x.shape[-2], x.shape[-1]).clone()
+    pred[:, -1:] = cls_pred[:, -1:, None, None] * x
+    return pred
+
+
+def inverse_mask_c1(plan: InversePlan, cls_pred, x, mask_out=None):
+    """Instance mask of the C1 decoder without materialising its [B,K,h,w] prediction or the [B,K,H,W] scores
+    (SURVEY.md section 8f row 4): `argmax(inverse_fill(plan, c1_tail_pred(cls_pred, x)))`.
+
+    cls_pred [B,K] class logits, x [B,1,h,w] mask logit.  Only ONE of the K channels varies over the map; the first
+    K-1 are per-frame constants c_k, and the whole inverse path is linear with non-negative weights, so their
+    full-resolution scores are c_k * s(p) with one common s(p) > 0: their arg-max is the same class k* at every pixel
+    (first maximum, as torch.argmax).  Stage 3 therefore runs on three channels -- a sentinel, k*, and the varying
+    channel -- writing 1 byte per pixel, and fovea_relabel_mask widens {0,1,2} to the reference's int64 ids {0, k*,
+    K-1} (0 = a pixel the reference leaves NaN / sets to zero in every channel: torch.argmax gives class 0 there).
+    Stage-3 traffic drops from 4*K*H*W to 9*H*W bytes.  Differs from the general path only at exact ties."""
+    cp = _req(cls_pred.detach(), torch.float32, "cls_pred", 2)
+    xm = _req(x.detach(), torch.float32, "x", 4)
+    B, K = cp.shape
+    if K < 2 or xm.shape[0] != B or xm.shape[1] != 1 or tuple(xm.shape[-2:]) != (plan.h, plan.w):
+        raise FoveaError(f"inverse_mask_c1: cls_pred {tuple(cp.shape)} / x {tuple(xm.shape)} do not match the plan "
+                         f"({plan.winner.shape[0]}x{plan.h}x{plan.w})")
+    kstar = torch.argmax(cp[:, :K - 1], dim=1)
+    pred3 = torch.empty(B, 3, plan.h, plan.w, device=cp.device, dtype=torch.float32)
+    pred3[:, 0] = -1e30                                            # sentinel: never the maximum of a valid pixel
+    pred3[:, 1] = cp.gather(1, kstar[:, None])[:, :, None]
+    pred3[:, 2] = cp[:, K - 1, None, None] * xm[:, 0]
+    table = box4_table(pred3, Cs=4)
+    labels = torch.empty(B, plan.H, plan.W, device=cp.device, dtype=torch.uint8)
+    _fill(plan, table, 3, True, None, labels)
+    lut = torch.stack([torch.zeros_like(kstar), kstar, torch.full_like(kstar, K - 1)], dim=1).contiguous()
+    mask = mask_out if mask_out is not None else torch.empty(B, plan.H, plan.W, device=cp.device, dtype=torch.int64)
+    if mask.dtype != torch.int64 or not mask.is_cuda or not mask.is_contiguous():
+        raise FoveaError("inverse_mask_c1: mask_out must be a contiguous CUDA int64 tensor")
+    _lib.call("fovea_relabel_mask", _ptr(labels), _ptr(lut), B, plan.H * plan.W, 3, _ptr(mask), _stream())
+    return mask
+
+
 def probe_store_ceiling(scores, side_read=None):
     """Diagnostic: overwrite `scores` [B,C,H,W] with the store pattern of fovea_inverse_fill and no computation;
     `side_read` (any int32 buffer of >= B*H*W/2 elements) adds the fill kernel's 2-byte-per-pixel `loc` read stream."""

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 9
+#define FOVEA_ABI_VERSION 10
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -258,6 +258,12 @@ int fovea_probe_store_ceiling(float* scores, const int32_t* side_read, int B, in
 /* torch.argmax(scores, dim=1) as a stand-alone pass (models/models.py:1044): first maximum wins, NaN is
  * treated as the maximum (torch semantics).  scores [B,C,H,W] -> mask [B,H,W] int64 */
 int fovea_argmax_classes(const float* scores, int B, int C, int64_t HW, int64_t* mask, fovea_stream_t stream);
+
+/* SURVEY.md section 8f row 4 (C1 decoder tail, models/model_utils.py:277-309): widen the uint8 labels of a
+ * reduced-channel fill to the reference's int64 class ids, mask[b,p] = lut[b][labels[b,p]].
+ *   labels [B,HW] uint8   lut [B,nl] int64   mask [B,HW] int64   (HW % 4 == 0, nl <= 256; labels >= nl clamp to nl-1) */
+int fovea_relabel_mask(const uint8_t* labels, const int64_t* lut, int B, int64_t HW, int nl, int64_t* mask,
+                       fovea_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -105,3 +105,35 @@ def test_saliency_softmax_shapes_and_nan(ops):
     z[0, 3] = 80.0
     xs = ops.saliency_softmax(z)
     assert xs[0, 3].item() == 1.0 and torch.allclose(xs[1], torch.full((50,), 0.02).cuda())
+
+
+# ---------------------------------------------------------------------------------------------- C1 decoder tail (8f row 4)
+
+@pytest.mark.parametrize("mode", ["tri", "nearest"])
+@pytest.mark.parametrize("H,W", [(256, 256), (520, 392)])
+def test_inverse_mask_c1_equals_general_path(ops, mode, H, W):
+    """The three-channel C1 fast path gives the mask of the general 51-channel path on a C1-structured prediction
+    (models/model_utils.py:298-309), bit for bit except where the general path's two best scores tie to 1e-6."""
+    B, K = 3, 51
+    gen = torch.Generator().manual_seed(H)
+    xs, _ = rp.synthetic_saliency(B, seed=H)
+    g1x, g1y = (t.cuda() for t in ops.separable_factors(rp.gaussian_filter_weight(45, 45, 45)))
+    grid = ops.saliency_to_grid(xs.cuda(), g1x, g1y, 80, 80, 45, 45, "replication", (80, 80))
+    cls_pred = torch.randn(B, K, generator=gen).cuda()
+    cls_pred[1, :K - 1] = -cls_pred[1, :K - 1].abs() - 0.1           # a frame whose constant channels are all negative
+    cls_pred[2, 7] = cls_pred[2, 3] = cls_pred[2, :K - 1].max() + 1  # tied constant maxima: the FIRST one must win
+    x = (torch.sigmoid(3 * torch.randn(B, 1, 80, 80, generator=gen)) - 0.5).cuda()
+    plan = (ops.build_nearest_plan(grid, (H, W), nchan=K) if mode == "nearest"
+            else ops.build_inverse_plan(grid, (H, W), nchan=K, triangulation="device"))
+    scores, want = ops.inverse_fill(plan, ops.c1_tail_pred(cls_pred, x), want_scores=True, want_mask=True)
+    got = ops.inverse_mask_c1(plan, cls_pred, x)
+    assert got.dtype == torch.int64 and got.shape == want.shape
+    top2 = scores.topk(2, dim=1).values
+    near_tie = (top2[:, 0] - top2[:, 1]).abs() <= 1e-6 * scores.abs().amax(dim=1).clamp_min(1e-30)
+    all_zero = scores.abs().amax(dim=1) == 0                          # residual-NaN pixels: every channel 0 -> class 0
+    assert torch.equal(got[all_zero], torch.zeros_like(got[all_zero]))
+    differs = (got != want) & ~near_tie
+    assert int(differs.sum()) == 0, f"{int(differs.sum())} pixels differ away from ties"
+    assert near_tie.float().mean().item() < 0.02 or all_zero.float().mean().item() > 0
+    assert set(got.unique().tolist()) <= {0, K - 1} | set(torch.argmax(cls_pred[:, :K - 1], 1).tolist())
+    assert (got[2] != 7).all()                                        # first maximum among tied constants (3, not 7)
