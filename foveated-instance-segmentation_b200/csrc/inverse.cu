@@ -22,6 +22,18 @@ __device__ __forceinline__ int target_coord(float g, int size) {
   return f == f ? __float2int_rz(f) : -1;  // NaN (cvt.rzi gives 0): lands nowhere, like any out-of-range target
 }
 
+// The same scatter for targets that are already integer pixel coordinates (DynamicFocus int_rount_scale_grid +
+// deformed_unsampler, nn_B0_deformed_sampler.py:83-137): coords [B,2,h,w] int64, channel 0 = row, 1 = column.
+__global__ void scatter_nodes_kernel(const long long* __restrict__ coords, int32_t* __restrict__ winner, int B, int hw,
+                                     int H, int W) {
+  const int total = B * hw;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / hw, node = idx - b * hw;
+    const long long v = coords[static_cast<size_t>(b) * 2 * hw + node], u = coords[static_cast<size_t>(b) * 2 * hw + hw + node];
+    if (u >= 0 && u < W && v >= 0 && v < H) atomicMax(winner + (static_cast<size_t>(b) * H + v) * W + u, node);
+  }
+}
+
 __global__ void grid_inv_scatter_kernel(const float2* __restrict__ grid, int32_t* __restrict__ winner, int B, int hw,
                                         int H, int W) {
   const int total = B * hw;
@@ -59,6 +71,9 @@ __global__ void grid_inv_canvas_kernel(const int32_t* __restrict__ winner, float
 constexpr int kTabNodes = 32;
 constexpr int kTabThreads = 256;
 
+// kBox = false: the plain transpose table[b][node][c] = pred[b][c][node] (DynamicFocus deformed_unsampler scatters the
+// low-resolution labels themselves, nn_B0_deformed_sampler.py:137)
+template <bool kBox>
 __global__ void __launch_bounds__(kTabThreads)
 box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int C, int Cs, int h, int w) {
   __shared__ float tile[kTabNodes][65];  // [node][channel chunk of 64] (+1: bank-conflict-free transpose)
@@ -83,7 +98,9 @@ box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int
     for (int cc = warp; cc < 64; cc += 8) {
       const int c = c0 + cc;
       float acc = 0.f;
-      if (valid && c < C) {
+      if (!kBox) {
+        if (valid && c < C) acc = __ldg(pb + static_cast<size_t>(c) * hw + node);
+      } else if (valid && c < C) {
         const float* s = pb + static_cast<size_t>(c) * hw + t.y0 * w + t.x0;
         const float v_nw = t.ok_nw ? __ldg(s) : 0.f;
         const float v_ne = t.ok_ne ? __ldg(s + 1) : 0.f;
@@ -810,8 +827,28 @@ extern "C" int fovea_box4_table(const float* pred, int B, int C, int h, int w, i
   FOVEA_REQUIRE(pred && table && B > 0 && C > 0 && h > 0 && w > 0, "fovea_box4_table: bad arguments");
   FOVEA_REQUIRE(Cs >= C && Cs % 4 == 0, "fovea_box4_table: Cs=%d must be a multiple of 4 and >= C=%d", Cs, C);
   dim3 grid(ceil_div(h * w, kTabNodes), B);
-  box4_table_kernel<<<grid, kTabThreads, 0, static_cast<cudaStream_t>(stream)>>>(pred, table, C, Cs, h, w);
+  box4_table_kernel<true><<<grid, kTabThreads, 0, static_cast<cudaStream_t>(stream)>>>(pred, table, C, Cs, h, w);
   return check_launch("fovea_box4_table");
+}
+
+extern "C" int fovea_node_table(const float* values, int B, int C, int h, int w, int Cs, float* table,
+                                fovea_stream_t stream) {
+  FOVEA_REQUIRE(values && table && B > 0 && C > 0 && h > 0 && w > 0, "fovea_node_table: bad arguments");
+  FOVEA_REQUIRE(Cs >= C && Cs % 4 == 0, "fovea_node_table: Cs=%d must be a multiple of 4 and >= C=%d", Cs, C);
+  dim3 grid(ceil_div(h * w, kTabNodes), B);
+  box4_table_kernel<false><<<grid, kTabThreads, 0, static_cast<cudaStream_t>(stream)>>>(values, table, C, Cs, h, w);
+  return check_launch("fovea_node_table");
+}
+
+extern "C" int fovea_scatter_nodes(const int64_t* coords, int B, int h, int w, int H, int W, int32_t* winner,
+                                   fovea_stream_t stream) {
+  FOVEA_REQUIRE(coords && winner && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "fovea_scatter_nodes: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FOVEA_CUDA(cudaMemsetAsync(winner, 0xFF, sizeof(int32_t) * static_cast<size_t>(B) * H * W, s));
+  const int total = B * h * w;
+  scatter_nodes_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(
+      reinterpret_cast<const long long*>(coords), winner, B, h * w, H, W);
+  return check_launch("fovea_scatter_nodes");
 }
 
 extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W,

@@ -22,6 +22,9 @@ namespace fovea {
 
 constexpr short kNoSite = 32767;
 
+// kAllSites: every filled pixel is a site (DynamicFocus deformed_unsampler: an exact Euclidean distance transform of the
+// scattered labels, nn_B0_deformed_sampler.py:139-149) instead of the reference's dilation rule.
+template <bool kAllSites>
 __global__ void __launch_bounds__(128)
 nearest_columns_kernel(const int32_t* __restrict__ winner, short* __restrict__ g, SelectParams p) {
   const int b = blockIdx.y;
@@ -42,7 +45,7 @@ nearest_columns_kernel(const int32_t* __restrict__ winner, short* __restrict__ g
     for (int k = 0; k < U; ++k) {
       const int y = y0 + k;
       if (y >= p.H) break;
-      if (wv[k] >= 0 && dilation_covers<true>(win, p, y, x)) last = y;
+      if (wv[k] >= 0 && (kAllSites || dilation_covers<true>(win, p, y, x))) last = y;
       gb[static_cast<size_t>(y) * p.W + x] = last >= 0 ? static_cast<short>(last - y) : kNoSite;
     }
   }
@@ -201,17 +204,20 @@ extern "C" int64_t fovea_nearest_workspace_bytes(int B, int H, int W) {
   return static_cast<int64_t>(B) * H * W * static_cast<int64_t>(sizeof(short));
 }
 
-extern "C" int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
-                                    void* workspace, uint16_t* loc, fovea_stream_t stream) {
-  FOVEA_REQUIRE(winner && workspace && loc, "fovea_nearest_locate: null pointer");
-  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "fovea_nearest_locate: bad sizes");
-  FOVEA_REQUIRE(H < 32767 && W < 32767 && B <= 65535 && H <= 65535, "fovea_nearest_locate: canvas or batch too large");
-  FOVEA_REQUIRE(h * w < 32767, "fovea_nearest_locate: table rows must fit 15 bits (h*w=%d)", h * w);
+static int nearest_locate_impl(const int32_t* winner, int B, int h, int w, int H, int W, int nchan, bool all_sites,
+                               void* workspace, uint16_t* loc, fovea_stream_t stream, const char* who) {
+  FOVEA_REQUIRE(winner && workspace && loc, "%s: null pointer", who);
+  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "%s: bad sizes", who);
+  FOVEA_REQUIRE(H < 32767 && W < 32767 && B <= 65535 && H <= 65535, "%s: canvas or batch too large", who);
+  FOVEA_REQUIRE(h * w < 32767, "%s: table rows must fit 15 bits (h*w=%d)", who, h * w);
   SelectParams p;
-  if (int rc = make_select_params(p, h, w, H, W, nchan, 0, "fovea_nearest_locate")) return rc;
+  if (int rc = make_select_params(p, h, w, H, W, nchan, 0, who)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   short* g = static_cast<short*>(workspace);
-  nearest_columns_kernel<<<dim3(ceil_div(W, 128), B), 128, 0, s>>>(winner, g, p);
+  if (all_sites)
+    nearest_columns_kernel<true><<<dim3(ceil_div(W, 128), B), 128, 0, s>>>(winner, g, p);
+  else
+    nearest_columns_kernel<false><<<dim3(ceil_div(W, 128), B), 128, 0, s>>>(winner, g, p);
   if (int rc = check_launch("fovea_nearest_locate (columns)")) return rc;
   // rows: the divide-and-conquer envelope keeps a row in shared memory; rows too long for that (W > ~14000) fall back to
   // the outward scan (exact too, but O(distance to the nearest site) per pixel)
@@ -229,4 +235,14 @@ extern "C" int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, 
     nearest_rows_kernel<<<dim3(ceil_div(W, 256), H, B), 256, 0, s>>>(winner, g, loc, h * w, H, W);
   }
   return check_launch("fovea_nearest_locate (rows)");
+}
+
+extern "C" int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
+                                    void* workspace, uint16_t* loc, fovea_stream_t stream) {
+  return nearest_locate_impl(winner, B, h, w, H, W, nchan, false, workspace, loc, stream, "fovea_nearest_locate");
+}
+
+extern "C" int fovea_nearest_locate_all(const int32_t* winner, int B, int h, int w, int H, int W, void* workspace,
+                                        uint16_t* loc, fovea_stream_t stream) {
+  return nearest_locate_impl(winner, B, h, w, H, W, 1, true, workspace, loc, stream, "fovea_nearest_locate_all");
 }

@@ -55,6 +55,9 @@ PROTOTYPES = {
     "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "fovea_nearest_workspace_bytes": (_i64, [_i, _i, _i]),
     "fovea_nearest_locate": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_scatter_nodes": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_nearest_locate_all": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_node_table": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_probe_store_ceiling": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "fovea_relabel_mask": (_i, [_p, _p, _i, _i64, _i, _p, _p]),
     "fovea_argmax_classes": (_i, [_p, _i, _i, _i64, _p, _p]),

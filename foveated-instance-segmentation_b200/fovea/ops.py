@@ -420,6 +420,41 @@ def nearest_locate(winner, h, w, nchan):
     return loc
 
 
+def scatter_nodes(coords, segSize):
+    """DynamicFocus deformed_unsampler's scatter (nn_B0_deformed_sampler.py:127-137): coords [B,2,h,w] int64 (row, column)
+    -> winner int32 [B,H,W]; the largest node index wins a shared pixel, targets outside the canvas are dropped."""
+    c = _req(coords, torch.int64, "coords", 4)
+    B, two, h, w = c.shape
+    if two != 2:
+        raise FoveaError(f"scatter_nodes: expected coords [B,2,h,w], got {tuple(c.shape)}")
+    H, W = int(segSize[0]), int(segSize[1])
+    winner = torch.empty(B, H, W, device=c.device, dtype=torch.int32)
+    _lib.call("fovea_scatter_nodes", _ptr(c), B, h, w, H, W, _ptr(winner), _stream())
+    return winner
+
+
+def nearest_locate_all(winner, h, w):
+    """Exact nearest-filled-pixel labelling (a Euclidean distance transform with indices, nn_B0_deformed_sampler.py:143-149):
+    like nearest_locate, but EVERY filled pixel is a site."""
+    win = _req(winner, torch.int32, "winner", 3)
+    B, H, W = win.shape
+    nbytes = int(_lib.load().fovea_nearest_workspace_bytes(B, H, W))
+    ws = torch.empty((nbytes + 3) // 4, device=win.device, dtype=torch.int32)
+    loc = torch.empty(B, H, W, device=win.device, dtype=torch.int16)
+    _lib.call("fovea_nearest_locate_all", _ptr(win), B, int(h), int(w), H, W, _ptr(ws), _ptr(loc), _stream())
+    return loc
+
+
+def node_table(values, Cs=None):
+    """[B,C,h,w] -> channel-contiguous value table [B, h*w+2, Cs] of the nodes themselves (no 2x2 box mean)."""
+    v = _req(values.detach(), torch.float32, "values", 4)
+    B, Cc, h, w = v.shape
+    Cs = Cs or (Cc + 3) // 4 * 4
+    table = torch.empty(B, h * w + 2, Cs, device=v.device, dtype=torch.float32)
+    _lib.call("fovea_node_table", _ptr(v), B, Cc, h, w, Cs, _ptr(table), _stream())
+    return table
+
+
 def build_nearest_plan(grid, segSize, nchan) -> InversePlan:
     """A7 scatter + nearest-site labelling: the 'nearest' counterpart of build_inverse_plan (no triangulation)."""
     g = _req(grid.detach(), torch.float32, "grid", 4)

@@ -248,6 +248,21 @@ int64_t fovea_nearest_workspace_bytes(int B, int H, int W);
 int fovea_nearest_locate(const int32_t* winner, int B, int h, int w, int H, int W, int nchan, void* workspace,
                          uint16_t* loc, fovea_stream_t stream);
 
+/* DynamicFocus deformed_unsampler (DynamicFocus/d_model/nn_B0_deformed_sampler.py:115-153):
+ * scatter the low-resolution labels at integer pixel targets, then give every other pixel the value of its nearest
+ * scattered pixel (the reference: scipy.ndimage.distance_transform_edt(return_indices=True) on the HOST).
+ *   fovea_scatter_nodes      : coords [B,2,h,w] int64 (row, column; out-of-canvas targets are dropped) -> winner [B,H,W]
+ *                              (largest node index wins a shared pixel, -1 = none), :127-137
+ *   fovea_nearest_locate_all : fovea_nearest_locate with EVERY filled pixel a site (exact Euclidean nearest; ties: leftmost
+ *                              column, then upper site), :143-149;  same workspace, same `loc`
+ *   fovea_node_table         : table[b][n][c] = values[b][c][n] (+ the NaN and zero rows), the plain counterpart of
+ *                              fovea_box4_table;  feed loc + table to fovea_inverse_fill (scores mode) */
+int fovea_scatter_nodes(const int64_t* coords, int B, int h, int w, int H, int W, int32_t* winner,
+                        fovea_stream_t stream);
+int fovea_nearest_locate_all(const int32_t* winner, int B, int h, int w, int H, int W, void* workspace, uint16_t* loc,
+                             fovea_stream_t stream);
+int fovea_node_table(const float* values, int B, int C, int h, int w, int Cs, float* table, fovea_stream_t stream);
+
 /* Diagnostic (bench.py): the store pattern of fovea_inverse_fill with no computation -- same tiling, one 128-bit
  * streaming store per 4 pixels and channel plane.  Its GB/s is the practical write-only ceiling of this layout.
  * side_read (may be NULL): a buffer of >= 2*B*H*W bytes read once, 8 bytes per thread, like the fill kernel's 16-bit

@@ -385,6 +385,44 @@ def instance_mask(pred_sampled: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 
 
+# ----------------------------------------------------------------------------------------------
+# DynamicFocus deformed_unsampler          DynamicFocus/d_model/nn_B0_deformed_sampler.py:83-153
+# ----------------------------------------------------------------------------------------------
+
+
+def int_round_scale_grid(grid: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """nn_B0_deformed_sampler.py:83-102 (`int_rount_scale_grid`): [-1,1] -> clipped, truncated int64 canvas coordinates."""
+    g = 0.5 * (grid + 1.0)
+    g[:, 0] *= H - 1
+    g[:, 1] *= W - 1
+    g[:, 0] = torch.clip(g[:, 0], 0, H - 1)
+    g[:, 1] = torch.clip(g[:, 1], 0, W - 1)
+    return g.to(torch.int64)
+
+
+def deformed_unsampler(labels: torch.Tensor, coords: torch.Tensor, H: int, W: int, return_sites: bool = False):
+    """nn_B0_deformed_sampler.py:115-153: scatter labels [B,K,HS,WS] at coords [B,2,HS,WS] (row, col), then every
+    unscattered pixel copies its nearest scattered pixel (scipy distance_transform_edt, return_indices).  Nodes that
+    share a pixel: the last write wins (torch CPU index_put order = largest node index).
+    return_sites: also the node index each pixel received [B,H,W] and the EDT distances (for tie analysis in tests)."""
+    from scipy.ndimage import distance_transform_edt
+    B, K, HS, WS = labels.shape
+    out = np.zeros((B, K, H, W), np.float32)
+    owner = np.full((B, H, W), -1, np.int64)
+    dist = np.zeros((B, H, W), np.float64)
+    lab = labels.numpy().reshape(B, K, HS * WS)
+    for b in range(B):
+        r, c = coords[b, 0].numpy().ravel(), coords[b, 1].numpy().ravel()
+        node = np.full((H, W), -1, np.int64)
+        node[r, c] = np.arange(HS * WS)                          # :127-137, sequential: the last duplicate wins
+        d, idx = distance_transform_edt(node < 0, return_indices=True)        # :143
+        owner[b] = node[idx[0], idx[1]]                          # :147-149 (filled pixels index themselves)
+        dist[b] = d
+        out[b] = lab[b][:, owner[b]]
+    res = torch.from_numpy(out)
+    return (res, owner, dist) if return_sites else res
+
+
 def synthetic_saliency(B: int, gh: int = 80, gw: int = 80, seed: int = 0):
     """xs = softmax(3*N(0,1) + 6*exp(-d^2/(2*8^2))) centred at a random gaze; returns (xs[B,1,gh,gw], gaze[B,2])."""
     g = torch.Generator().manual_seed(seed)

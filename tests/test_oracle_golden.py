@@ -154,3 +154,16 @@ def test_saliency_input_matches_reference_module(golden_dir, name):
     feed = synthetic_batch(int(g["B"]), int(g["H"]), int(g["W"]), int(g["seed"]))
     got = rp.saliency_input(feed["img_data"], feed["focus_point"], (80, 80))
     np.testing.assert_allclose(got.numpy(), g["x_low"], rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["unsampler_24_to_96x128", "unsampler_40x64_to_520"])
+def test_deformed_unsampler_matches_reference(golden_dir, name):
+    """the oracle's restatement of DynamicFocus's deformed_unsampler against the output of the unmodified
+    reference functions (tests/golden/make_golden_dynamicfocus.py), bit for bit -- including the duplicate-target rule
+    (last write = largest node index) and SciPy's own choice among equidistant pixels."""
+    g = _load(golden_dir, name)
+    H, W = int(g["H"]), int(g["W"])
+    coords = rp.int_round_scale_grid(torch.from_numpy(g["grid"]).clone(), H, W)
+    assert np.array_equal(coords.numpy(), g["coords"])
+    out = rp.deformed_unsampler(torch.from_numpy(g["labels"]), coords, H, W)
+    assert np.array_equal(out.numpy(), g["out"])
