@@ -281,7 +281,35 @@ def main():
     m1.record()
     barrier()
     mask_ms = m0.elapsed_time(m1) / km
-    mask_mode = {"serial_ms_per_step": mask_ms, "frames_s_per_gpu": B / (mask_ms * 1e-3), "steps": km,
+    # the C1 decoder's tail: the same mask from 3 channels instead of C (ops.inverse_mask_c1), timed on
+    # one plan; and the general C-channel mask fill on the same plan beside it
+    c1 = None
+    if args.interp == "tri":
+        ops_ = path.ops
+        grid_ = ops_.saliency_to_grid(xs, path.g1x, path.g1y, cfg["g"], cfg["g"], cfg["R"], cfg["R"], "replication",
+                                      (cfg["g"], cfg["g"]))
+        plan_ = ops_.build_inverse_plan(grid_, (H, W), nchan=C, triangulation=args.triangulation)
+        cls_ = pred.mean(dim=(2, 3))
+        xm_ = torch.sigmoid(pred[:, -1:]) - 0.5
+        pred_c1 = ops_.c1_tail_pred(cls_, xm_)
+        tab_ = ops_.box4_table(pred_c1)
+
+        def timed(fn, n=5):
+            fn()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n
+        c1 = {"c1_tail_mask_ms": timed(lambda: ops_.inverse_mask_c1(plan_, cls_, xm_, mask_out=path.mask)),
+              "general_mask_fill_ms": timed(lambda: ops_._fill(plan_, tab_, C, True, None, path.mask)),
+              "what": "stage-3 fill only, on a prebuilt plan: 3-channel fill + relabel (9 B/pixel) vs the C-channel "
+                      "fused-argmax fill (8 B/pixel written, C channels interpolated)"}
+        del plan_, tab_, pred_c1
+    mask_mode = {"c1_tail": c1, "serial_ms_per_step": mask_ms, "frames_s_per_gpu": B / (mask_ms * 1e-3), "steps": km,
                  "algorithmic_bytes_per_frame": 8 * H * W,
                  "what": "grid + grid_sample + plan + inverse_fill with scores=NULL, mask=int64 (one stream)"}
 

@@ -33,3 +33,7 @@ def test_level2_stub_runs_and_matches_ops():
     torch.cuda.synchronize()
     assert torch.equal(mask, want_mask)
     assert torch.equal(scores, want_scores)
+    # the stage-0 stub further down the document, executed in the same namespace
+    exec(next(b for b in blocks if "def saliency_input" in b), ns)
+    fp = torch.rand(B, 2, generator=torch.Generator().manual_seed(6)).cuda()
+    assert torch.equal(ns["saliency_input"](x, fp), ops.saliency_input(x, fp, (80, 80)))
