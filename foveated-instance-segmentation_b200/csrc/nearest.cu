@@ -196,12 +196,222 @@ nearest_rows_dc_kernel(const int32_t* __restrict__ winner, const short* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiled exact nearest-site labelling (the default): at most h*w (~6.4 k) sites per frame, so almost every 32 x 32 pixel
+// tile can only be claimed by a handful of them.
+//   1. nearest_sites_kernel   : one CTA per tile scans its pixels of the winner map, applies the site rule and appends the
+//                               tile's sites (packed position + node) to the frame's site list: one contiguous BUCKET per
+//                               tile (one atomicAdd per CTA reserves the range).
+//   2. nearest_tiles_kernel   : one CTA per tile.  d0 = the distance from the tile centre c to SOME site s0 (the nearest one
+//                               found in a growing square of buckets around the tile).  With r = the tile's half diagonal,
+//                               a site that is nearest to ANY pixel p of the tile lies within d0 + 2r of c
+//                               (|s-p| <= |s0-p| <= d0 + r and |p-c| <= r), so
+//                               only the buckets meeting that disc are read; their sites inside the disc are compacted into
+//                               shared memory and every pixel takes the exact integer arg-min over them (ties: leftmost
+//                               column, then the upper site -- the rule of the scan kernels above).
+// Tiles without an unfilled pixel (the fovea core) skip the search entirely.  All distances are integers; the floating-point
+// disc test only has to be conservative (it is, by a one-pixel margin).
+constexpr int kNtTile = 32;           // tile edge in pixels
+constexpr int kNtThreads = 256;       // 4 pixels per thread
+constexpr int kNtCand = 3072;         // candidate slots in shared memory (a bucket holds at most 1024 sites)
+
+struct TileGeom { int H, W, nbx, nby, hw, cap; };
+
+template <bool kAllSites>
+__global__ void __launch_bounds__(kNtThreads)
+nearest_sites_kernel(const int32_t* __restrict__ winner, SelectParams p, TileGeom g, int2* __restrict__ sites,
+                     int2* __restrict__ buckets, int* __restrict__ counters) {
+  __shared__ int s_warp[kNtThreads / 32];
+  __shared__ int s_base;
+  const int b = blockIdx.z;
+  const int32_t* win = winner + static_cast<size_t>(b) * g.H * g.W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int y = blockIdx.y * kNtTile + (tid >> 3), x0 = blockIdx.x * kNtTile + (tid & 7) * 4;
+  int node[4];
+  unsigned mask = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x0 + k;
+    node[k] = (y < g.H && x < g.W) ? __ldg(win + static_cast<size_t>(y) * g.W + x) : -1;
+    if (node[k] >= 0 && (kAllSites || dilation_covers<true>(win, p, y, x))) mask |= 1u << k;
+  }
+  const int cnt = __popc(mask);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kNtThreads / 32; ++w) {
+    if (w < warp) before += s_warp[w];
+    total += s_warp[w];
+  }
+  if (tid == 0) {
+    s_base = total ? atomicAdd(counters + b, total) : 0;
+    buckets[(static_cast<size_t>(b) * g.nby + blockIdx.y) * g.nbx + blockIdx.x] = make_int2(s_base, total);
+  }
+  __syncthreads();
+  int pos = s_base + before + incl - cnt;
+  int2* out = sites + static_cast<size_t>(b) * g.cap;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if ((mask >> k) & 1u) out[pos++] = make_int2((y << 16) | (x0 + k), node[k]);
+}
+
+__global__ void __launch_bounds__(kNtThreads)
+nearest_tiles_kernel(const int32_t* __restrict__ winner, const int2* __restrict__ sites, const int2* __restrict__ buckets,
+                     const int* __restrict__ counters, TileGeom g, uint16_t* __restrict__ loc) {
+  __shared__ int2 cand[kNtCand];
+  __shared__ int s_count, s_scan[kNtThreads / 32];
+  __shared__ unsigned s_d0[kNtThreads / 32];
+  const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = blockIdx.y, tx = blockIdx.x;
+  const int y = ty * kNtTile + (tid >> 3), x0 = tx * kNtTile + (tid & 7) * 4;
+  const size_t fb = static_cast<size_t>(b) * g.H * g.W;
+  int node[4];
+  bool need = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool in = y < g.H && x0 + k < g.W;
+    node[k] = in ? __ldg(winner + fb + static_cast<size_t>(y) * g.W + x0 + k) : 0;
+    need |= in && node[k] < 0;
+  }
+  unsigned best[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  unsigned bkey[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};   // (x << 16 | y) of the best site: leftmost, then upper
+  int bnode[4] = {g.hw, g.hw, g.hw, g.hw};                                    // no site at all: the NaN row
+  if (__syncthreads_or(need) && counters[b] > 0) {   // (a frame without any site: the NaN row everywhere)
+    const int ntiles = g.nbx * g.nby;
+    const int2* bk = buckets + static_cast<size_t>(b) * ntiles;
+    const int2* sb = sites + static_cast<size_t>(b) * g.cap;
+    const float cy = ty * kNtTile + 0.5f * (kNtTile - 1), cx = tx * kNtTile + 0.5f * (kNtTile - 1);
+    // d0: an upper bound of the distance from the tile centre to its nearest site -- the nearest site found in a growing
+    // square of buckets around the tile (radius 1, 3, 7, ... buckets) -- as the bit pattern of a non-negative float
+    unsigned d0bits = 0x7f800000u;
+    for (int k = 1;; k = 2 * k + 1) {
+      const int qy0 = max(0, ty - k), qy1 = min(g.nby - 1, ty + k), qx0 = max(0, tx - k), qx1 = min(g.nbx - 1, tx + k);
+      const int qw = qx1 - qx0 + 1, nq = qw * (qy1 - qy0 + 1);
+      unsigned mind = 0x7f800000u;
+      for (int q = tid; q < nq; q += kNtThreads) {
+        const int2 e = __ldg(bk + (qy0 + q / qw) * g.nbx + qx0 + q % qw);
+        for (int i = 0; i < e.y; ++i) {
+          const int sv = __ldg(&sb[e.x + i].x);
+          const float dy = static_cast<float>(sv >> 16) - cy, dx = static_cast<float>(sv & 0xFFFF) - cx;
+          mind = min(mind, __float_as_uint(sqrtf(dy * dy + dx * dx)));
+        }
+      }
+      mind = __reduce_min_sync(0xffffffffu, mind);
+      __syncthreads();  // s_d0 of the previous round has been read
+      if (lane == 0) s_d0[warp] = mind;
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < kNtThreads / 32; ++w) d0bits = min(d0bits, s_d0[w]);
+      if (d0bits != 0x7f800000u || nq == ntiles) break;   // found, or the square already covers the whole frame
+    }
+    if (d0bits != 0x7f800000u) {
+      // disc radius in pixels: d0 + 2r (+1 margin); r = half diagonal of the tile = (T-1)/sqrt(2)
+      const float R = __uint_as_float(d0bits) + 2.f * 0.70710678f * (kNtTile - 1) + 1.f;
+      const float R2 = R * R;
+      const int by0 = max(0, static_cast<int>(floorf((cy - R) / kNtTile))), by1 = min(g.nby - 1, static_cast<int>(floorf((cy + R) / kNtTile)));
+      const int bx0 = max(0, static_cast<int>(floorf((cx - R) / kNtTile))), bx1 = min(g.nbx - 1, static_cast<int>(floorf((cx + R) / kNtTile)));
+      const int bw = bx1 - bx0 + 1, nb = bw * (by1 - by0 + 1);
+      // buckets are visited in chunks of 256 (one per thread); within a chunk, passes of at most kNtCand sites
+      for (int c0 = 0; c0 < nb; c0 += kNtThreads) {
+        int2 mine = make_int2(0, 0);
+        const int q = c0 + tid;
+        if (q < nb) {
+          const int by = by0 + q / bw, bx = bx0 + q % bw;
+          // distance from the centre to the bucket's pixel rectangle
+          const float ry = fmaxf(fmaxf(by * kNtTile - cy, cy - (by * kNtTile + kNtTile - 1)), 0.f);
+          const float rx = fmaxf(fmaxf(bx * kNtTile - cx, cx - (bx * kNtTile + kNtTile - 1)), 0.f);
+          if (ry * ry + rx * rx <= R2) mine = __ldg(bk + by * g.nbx + bx);
+        }
+        // exclusive block scan of the bucket sizes (upper bound of the candidates they contribute)
+        int incl = mine.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        __syncthreads();  // s_scan / cand of the previous chunk are no longer read
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kNtThreads / 32; ++w) {
+          if (w < warp) before += s_scan[w];
+          total += s_scan[w];
+        }
+        const int off = before + incl - mine.y;
+        constexpr int kWindow = kNtCand - 1024;  // a pass takes the buckets whose offset falls in one window: <= kNtCand sites
+        for (int w0 = 0; w0 < total; w0 += kWindow) {
+          if (tid == 0) s_count = 0;
+          __syncthreads();
+          // every lane walks its own bucket (buckets are small: a few sites on average)
+          if (mine.y > 0 && off >= w0 && off < w0 + kWindow) {
+            for (int i = 0; i < mine.y; ++i) {
+              const int2 sv = __ldg(sb + mine.x + i);
+              const float dy = static_cast<float>(sv.x >> 16) - cy, dx = static_cast<float>(sv.x & 0xFFFF) - cx;
+              if (dy * dy + dx * dx <= R2) cand[atomicAdd(&s_count, 1)] = sv;
+            }
+          }
+          __syncthreads();
+          const int nc = s_count;
+          if (need) {
+            for (int i = 0; i < nc; ++i) {
+              const int2 sv = cand[i];
+              const int sy = sv.x >> 16, sx = sv.x & 0xFFFF;
+              const int dy = sy - y;
+              const unsigned dy2 = static_cast<unsigned>(dy * dy);
+              const unsigned key = (static_cast<unsigned>(sx) << 16) | static_cast<unsigned>(sy);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int dx = sx - (x0 + k);
+                const unsigned d = dy2 + static_cast<unsigned>(dx * dx);   // < 2^31: coordinates < 32767
+                if (d < best[k] || (d == best[k] && key < bkey[k])) { best[k] = d; bkey[k] = key; bnode[k] = sv.y; }
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
+  if (y < g.H) {
+    uint16_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = static_cast<uint16_t>(0x8000 | (node[k] >= 0 ? node[k] : bnode[k]));
+    uint16_t* dst = loc + fb + static_cast<size_t>(y) * g.W + x0;
+    if ((g.W & 3) == 0 && x0 + 3 < g.W) {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(o[0] | (static_cast<unsigned>(o[1]) << 16), o[2] | (static_cast<unsigned>(o[3]) << 16));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x0 + k < g.W) dst[k] = o[k];
+    }
+  }
+}
+
 }  // namespace fovea
 
 using namespace fovea;
 
+// Workspace layout.  Scan path: [B][H][W] short.  Tiled path: per-frame counters [B] int (256-byte aligned block), site
+// lists [B][cap] int2, buckets [B][ntiles] int2; sized for cap = min(H*W, 32768) >= h*w sites.
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+static inline int nt_cap(int H, int W) {
+  const long long px = static_cast<long long>(H) * W;
+  return static_cast<int>(px < 32768 ? px : 32768);
+}
 extern "C" int64_t fovea_nearest_workspace_bytes(int B, int H, int W) {
-  return static_cast<int64_t>(B) * H * W * static_cast<int64_t>(sizeof(short));
+  const int64_t scan = static_cast<int64_t>(B) * H * W * static_cast<int64_t>(sizeof(short));
+  const int64_t ntiles = static_cast<int64_t>(ceil_div(H, kNtTile)) * ceil_div(W, kNtTile);
+  const int64_t tiled = align256(4ll * B) + align256(8ll * B * nt_cap(H, W)) + 8ll * B * ntiles;
+  return scan > tiled ? scan : tiled;
 }
 
 static int nearest_locate_impl(const int32_t* winner, int B, int h, int w, int H, int W, int nchan, bool all_sites,
@@ -213,6 +423,25 @@ static int nearest_locate_impl(const int32_t* winner, int B, int h, int w, int H
   SelectParams p;
   if (int rc = make_select_params(p, h, w, H, W, nchan, 0, who)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool force_old = [] { const char* e = getenv("FOVEA_NEAREST_TILES"); return e && e[0] == '0'; }();
+  const int cap = nt_cap(H, W) < h * w ? nt_cap(H, W) : h * w;   // every node lands on at most one pixel
+  if (!force_old && ceil_div(H, kNtTile) <= 65535) {
+    TileGeom tg{H, W, ceil_div(W, kNtTile), ceil_div(H, kNtTile), h * w, cap};
+    const int64_t ntiles = static_cast<int64_t>(tg.nbx) * tg.nby;
+    char* base = static_cast<char*>(workspace);
+    int* counters = reinterpret_cast<int*>(base);
+    int2* sites = reinterpret_cast<int2*>(base + align256(4ll * B));
+    int2* buckets = reinterpret_cast<int2*>(reinterpret_cast<char*>(sites) + align256(8ll * B * cap));
+    FOVEA_CUDA(cudaMemsetAsync(counters, 0, 4 * static_cast<size_t>(B), s));
+    dim3 tgrid(tg.nbx, tg.nby, B);
+    if (all_sites)
+      nearest_sites_kernel<true><<<tgrid, kNtThreads, 0, s>>>(winner, p, tg, sites, buckets, counters);
+    else
+      nearest_sites_kernel<false><<<tgrid, kNtThreads, 0, s>>>(winner, p, tg, sites, buckets, counters);
+    if (int rc = check_launch("fovea_nearest_locate (sites)")) return rc;
+    nearest_tiles_kernel<<<tgrid, kNtThreads, 0, s>>>(winner, sites, buckets, counters, tg, loc);
+    return check_launch("fovea_nearest_locate (tiles)");
+  }
   short* g = static_cast<short*>(workspace);
   if (all_sites)
     nearest_columns_kernel<true><<<dim3(ceil_div(W, 128), B), 128, 0, s>>>(winner, g, p);
