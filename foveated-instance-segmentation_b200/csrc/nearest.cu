@@ -198,7 +198,7 @@ nearest_rows_dc_kernel(const int32_t* __restrict__ winner, const short* __restri
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Tiled exact nearest-site labelling (the default): at most h*w (~6.4 k) sites per frame, so almost every 32 x 32 pixel
+// Tiled exact nearest-site labelling (chosen for sparse sites, see nearest_locate_impl): at most h*w (~6.4 k) sites per frame, so almost every 32 x 32 pixel
 // tile can only be claimed by a handful of them.
 //   1. nearest_sites_kernel   : one CTA per tile scans its pixels of the winner map, applies the site rule and appends the
 //                               tile's sites (packed position + node) to the frame's site list: one contiguous BUCKET per
@@ -423,9 +423,14 @@ static int nearest_locate_impl(const int32_t* winner, int B, int h, int w, int H
   SelectParams p;
   if (int rc = make_select_params(p, h, w, H, W, nchan, 0, who)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static const bool force_old = [] { const char* e = getenv("FOVEA_NEAREST_TILES"); return e && e[0] == '0'; }();
+  // Which exact algorithm: the tiled search wins when sites are sparse (few candidates per 32 x 32 tile), the column/row
+  // scans when they are dense.  Measured on B200, 80 x 80 nodes: 1024^2 (spacing ~13 px) tiled 3.2 ms vs scans 2.0 ms per
+  // 64 frames; 2048^2 (~26 px) tiled 1.3 ms vs scans 2.4 ms per 16 frames.  Threshold: expected spacing
+  // sqrt(H*W / (h*w)) >= 20 pixels.  FOVEA_NEAREST_TILES=0|1 forces one of them (A/B runs).
+  static const int force = [] { const char* e = getenv("FOVEA_NEAREST_TILES"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  const bool tiled = force >= 0 ? force == 1 : static_cast<double>(H) * W >= 400.0 * static_cast<double>(h) * w;
   const int cap = nt_cap(H, W) < h * w ? nt_cap(H, W) : h * w;   // every node lands on at most one pixel
-  if (!force_old && ceil_div(H, kNtTile) <= 65535) {
+  if (tiled && ceil_div(H, kNtTile) <= 65535) {
     TileGeom tg{H, W, ceil_div(W, kNtTile), ceil_div(H, kNtTile), h * w, cap};
     const int64_t ntiles = static_cast<int64_t>(tg.nbx) * tg.nby;
     char* base = static_cast<char*>(workspace);

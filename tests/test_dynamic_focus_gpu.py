@@ -83,6 +83,18 @@ def test_deformed_unsampler_full_size_properties(df):
     _check(df, labels, coords, H, W)
 
 
+def test_deformed_unsampler_sparse_lattice_tiled_search(df):
+    """A 20 x 24 lattice on a 400 x 520 canvas (>= 400 pixels per node): fovea_nearest_locate_all runs its tiled search."""
+    gen = torch.Generator().manual_seed(9)
+    B, K, HS, WS, H, W = 2, 2, 20, 24, 400, 520
+    coords = torch.stack([torch.randint(0, H, (B, HS, WS), generator=gen), torch.randint(0, W, (B, HS, WS), generator=gen)], 1)
+    coords[0, :, :4, :] = coords[0, :, :1, :1]                       # many nodes on one pixel; a cluster of neighbours
+    coords[1, 0] = (coords[1, 0] // 8).clamp(max=H - 1)              # everything in the top eighth: a far-away rest
+    labels = torch.randn(B, K, HS, WS, generator=gen)
+    assert H * W >= 400 * HS * WS
+    _check(df, labels, coords, H, W)
+
+
 def test_deformed_unsampler_edge_cases(df):
     # a single scattered pixel: the whole canvas takes its label; targets outside the canvas are dropped
     labels = torch.tensor([[[[3.0, 7.0]]]])

@@ -387,6 +387,18 @@ def test_nearest_fill_full_resolution_1024(ops):
     _check_nearest(ops, rp.synthetic_pred(B, C, seed=31), grid, (H, W), C)
 
 
+@pytest.mark.parametrize("H,W", [(2048, 2048), (1792, 2304)])
+def test_nearest_fill_sparse_sites_tiled_search(ops, H, W):
+    """Canvases where the 80 x 80 nodes are sparse (H*W >= 400 nodes' worth of pixels) take the TILED exact search
+    (csrc/nearest.cu: site buckets + disc culling) instead of the column/row scans: same exactness checks."""
+    B, C = 1, 3
+    xs, _ = rp.synthetic_saliency(B, seed=H)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    assert H * W >= 400 * 80 * 80
+    _check_nearest(ops, rp.synthetic_pred(B, C, seed=H), grid, (H, W), C)
+
+
 # ---------------------------------------------------------------------------------------------- edge cases
 def _grid_from(xs, task=(80, 80)):
     filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
