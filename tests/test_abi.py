@@ -44,6 +44,20 @@ def test_argument_errors_do_not_need_a_gpu():
         _lib.call("fovea_box4_table", None, 1, 3, 8, 8, 4, None, None)
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Stage-0, C1-tail and deformed_unsampler entry points: argument errors are reported before any CUDA call."""
+    from fovea import _lib
+    lib = _lib.load()
+    assert lib.fovea_saliency_input(None, 0, 255.0, None, 1, 3, 8, 8, 4, 4, None, None) == -1
+    assert b"null pointer" in lib.fovea_last_error()
+    assert lib.fovea_saliency_softmax(None, 1, 16, None, None) == -1
+    assert lib.fovea_relabel_mask(None, None, 1, 16, 3, None, None) == -1
+    assert lib.fovea_scatter_nodes(None, 1, 4, 4, 8, 8, None, None) == -1
+    assert lib.fovea_node_table(None, 1, 3, 4, 4, 4, None, None) == -1
+    assert lib.fovea_nearest_locate_all(None, 1, 4, 4, 8, 8, None, None, None) == -1
+    assert lib.fovea_nearest_workspace_bytes(2, 64, 64) >= 2 * 64 * 64 * 2      # covers the scan map and the site lists
+
+
 def test_ops_refuse_cpu_tensors():
     """No CPU fallback: handing a CPU tensor to the product path fails loudly."""
     import torch
@@ -52,6 +66,15 @@ def test_ops_refuse_cpu_tensors():
         ops.grid_sample(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 2, 2))
     with pytest.raises(FoveaError):
         ops.grid_inv_scatter(torch.zeros(1, 4, 4, 2), (8, 8))
+    with pytest.raises(FoveaError):
+        ops.saliency_input(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2), (4, 4))
+    with pytest.raises(FoveaError):
+        ops.saliency_softmax(torch.zeros(2, 16))
+    with pytest.raises(FoveaError):
+        ops.scatter_nodes(torch.zeros(1, 2, 4, 4, dtype=torch.int64), (8, 8))
+    from fovea import dynamic_focus
+    with pytest.raises(FoveaError):
+        dynamic_focus.deformed_unsampler(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2, dtype=torch.int64), 8, 8)
 
 
 def test_separable_factors_reject_non_gaussian():
