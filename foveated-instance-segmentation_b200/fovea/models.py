@@ -275,6 +275,16 @@ class DeformSegmentationModule(SegmentationModuleBase):
         xs = ops.saliency_softmax(xs.reshape(-1, self.grid_size_x * self.grid_size_y))  # :715-723
         return xs.view(-1, 1, self.grid_size_x, self.grid_size_y)
 
+    @staticmethod
+    def _sample_image(x, grid):
+        """F.grid_sample(x, grid) (:909); a uint8 frame (the loader's decode, before ToTensor) is sampled directly with the
+        /255 folded into the taps -- bit-identical to converting first, a quarter of the bytes."""
+        if x.dtype == torch.uint8:
+            if torch.is_grad_enabled() and grid.requires_grad:
+                raise NotImplementedError("a uint8 img_data cannot carry the grid gradient: pass the fp32 image when training")
+            return ops.grid_sample_u8(x, grid.detach())
+        return ops.grid_sample(x, grid)
+
     def _check_cfg(self):
         c = self.cfg
         if c.MODEL.uniform_sample != "" or getattr(c.MODEL, "gt_gradient", False) or \
@@ -345,7 +355,7 @@ class DeformSegmentationModule(SegmentationModuleBase):
         edge_loss = 0.05 * self.crit_mse(xs_n, xt_n) * cfg.TRAIN.edge_loss_scale
         upsample = cfg.MODEL.upsample
         plan = self.plan_async(grid, (H_HS, W_HS)) if upsample else None        # overlaps the encoder/decoder
-        x_sampled = ops.grid_sample(x, grid)                                    # :909
+        x_sampled = self._sample_image(x, grid)                                    # :909
         pred = self.decoder(self.encoder(x_sampled, return_feature_maps=True))  # :926
         seg_low = y_sampled.long()
         y_hs = feed_dict["seg_label"].squeeze(1)
@@ -368,7 +378,7 @@ class DeformSegmentationModule(SegmentationModuleBase):
         """models_instance.py:840-1121 with rev_deform_opt == 51 ('ours deformed case')."""
         grid, grid_y = self._grid_from_saliency(xs, segSize=segSize)            # :844-845
         plan = None if getattr(self.cfg.VAL, "no_upsample", False) else self.plan_async(grid, segSize)
-        x_sampled = ops.grid_sample(x, grid)                                    # :851-852
+        x_sampled = self._sample_image(x, grid)                                    # :851-852
         if tuple(x_sampled.shape[-2:]) != tuple(self.input_size_net_infer):
             x_sampled = F.interpolate(x_sampled, self.input_size_net_infer, mode="bilinear")
         pred = self.decoder(self.encoder(x_sampled, return_feature_maps=True), segSize=tuple(self.input_size_net_infer))

@@ -238,3 +238,26 @@ def test_module_nearest_mode_and_async_plan():
         outs[mode] = ps_async
     # both modes leave the pixels that received a node untouched, and differ elsewhere (step function vs. linear)
     assert not torch.equal(outs["nearest"], outs["tri"])
+
+
+def test_module_inference_accepts_uint8_frames():
+    """SURVEY 8f row 3 through the module: a uint8 img_data (the loader's decode, before ToTensor) gives bit for bit the
+    outputs of the converted fp32 image at inference; under autograd it is refused (the grid gradient needs fp32 taps)."""
+    from fovea.models import CompressNet, DeformSegmentationModule
+    from fovea.saliency_network import fov_simple
+    cfg = make_cfg(True)
+    cfg.VAL.no_upsample = False
+    torch.manual_seed(4)
+    m = DeformSegmentationModule(TinyEncoder(), TinyDecoder(), fov_simple(cfg), CompressNet(cfg), None, cfg).cuda().eval()
+    feed = {k: v.cuda() for k, v in synthetic_batch(2, 128, 160, 11).items()}
+    img8 = (feed["img_data"] * 255).round().to(torch.uint8)
+    feed32 = dict(feed, img_data=img8.float() / 255.0)
+    feed8 = dict(feed, img_data=img8)
+    with torch.no_grad():
+        a = m(dict(feed32), segSize=(128, 160))
+        b = m(dict(feed8), segSize=(128, 160))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(dict(feed8))
