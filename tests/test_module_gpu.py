@@ -251,7 +251,8 @@ def test_module_inference_accepts_uint8_frames():
     m = DeformSegmentationModule(TinyEncoder(), TinyDecoder(), fov_simple(cfg), CompressNet(cfg), None, cfg).cuda().eval()
     feed = {k: v.cuda() for k, v in synthetic_batch(2, 128, 160, 11).items()}
     img8 = (feed["img_data"] * 255).round().to(torch.uint8)
-    feed32 = dict(feed, img_data=img8.float() / 255.0)
+    # ToTensor divides on the CPU (a true fp32 division); torch's CUDA `/ 255.0` multiplies by the reciprocal instead
+    feed32 = dict(feed, img_data=(img8.cpu().float() / 255.0).cuda())
     feed8 = dict(feed, img_data=img8)
     with torch.no_grad():
         a = m(dict(feed32), segSize=(128, 160))
