@@ -253,14 +253,20 @@ nearest_sites_kernel(const int32_t* __restrict__ winner, SelectParams p, TileGeo
   }
   if (tid == 0) {
     s_base = total ? atomicAdd(counters + b, total) : 0;
-    buckets[(static_cast<size_t>(b) * g.nby + blockIdx.y) * g.nbx + blockIdx.x] = make_int2(s_base, total);
+    // a winner map from fovea_grid_inv_scatter / fovea_scatter_nodes holds every node at most once, so a frame has at most
+    // cap sites; a foreign map that breaks this contract loses the excess sites instead of writing past the list
+    const int room = max(0, g.cap - s_base);
+    buckets[(static_cast<size_t>(b) * g.nby + blockIdx.y) * g.nbx + blockIdx.x] = make_int2(s_base, min(total, room));
   }
   __syncthreads();
   int pos = s_base + before + incl - cnt;
   int2* out = sites + static_cast<size_t>(b) * g.cap;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
-    if ((mask >> k) & 1u) out[pos++] = make_int2((y << 16) | (x0 + k), node[k]);
+    if ((mask >> k) & 1u) {
+      if (pos < g.cap) out[pos] = make_int2((y << 16) | (x0 + k), node[k]);
+      ++pos;
+    }
 }
 
 __global__ void __launch_bounds__(kNtThreads)
