@@ -1,9 +1,5 @@
-"""Flip-round counts of the parallel Lawson phase for different initial triangulations (NumPy simulation with random
-priorities, as the kernel): x-merge zipper (what delaunay.cu builds) vs a greedy locally-Delaunay zipper per strip.
-Result: 177->141, 81->74, 89->92 rounds -- the cascade depth is a property of the 1-pixel row strips,
-not of how each strip is zipped."""
 import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools/prototypes')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tools', 'prototypes'))
 import numpy as np, torch
 from dt_proto import orient, incircle, build_adjacency, check_delaunay
 from oracle import reference_port as rp
@@ -73,14 +69,15 @@ def flip_rounds_random(pts, tris, nb, seed=0):
         total += int(win.sum()); rounds += 1
     return rounds, total, hist
 
-for (H, W, seed) in [(1024, 1024, 3), (1024, 1024, 7), (2048, 2048, 4)]:
-    xs, _ = rp.synthetic_saliency(1, seed=seed)
-    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
-    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
-    ps = rp.inverse_sample(rp.synthetic_pred(1, 1, seed=seed), rp.grid_inverse(grid, (H, W)))
-    mask, inv = rp.pixels_for_interp(ps[0]); rr, cc = torch.where(mask[0])
-    pts = np.stack([rr.numpy(), cc.numpy()], 1).astype(np.int64)
-    for greedy in (False, True):
-        t0 = time.time(); tris = zipper(pts, greedy); nb, _ = build_adjacency(tris)
-        r, tot, hist = flip_rounds_random(pts, tris.copy(), nb.copy())
-        print(f"{H}^2 seed {seed} greedy={greedy}: N={len(pts)} T={len(tris)} rounds={r} flips={tot} illegal edges per round (first 6) {hist[:6]} ... tail>{sum(1 for h in hist if h<=15)} rounds with <=15  ({time.time()-t0:.0f}s)", flush=True)
+if __name__ == "__main__":
+  for (H, W, seed) in [(1024, 1024, 3), (1024, 1024, 7), (2048, 2048, 4)]:
+      xs, _ = rp.synthetic_saliency(1, seed=seed)
+      filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+      grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+      ps = rp.inverse_sample(rp.synthetic_pred(1, 1, seed=seed), rp.grid_inverse(grid, (H, W)))
+      mask, inv = rp.pixels_for_interp(ps[0]); rr, cc = torch.where(mask[0])
+      pts = np.stack([rr.numpy(), cc.numpy()], 1).astype(np.int64)
+      for greedy in (False, True):
+          t0 = time.time(); tris = zipper(pts, greedy); nb, _ = build_adjacency(tris)
+          r, tot, hist = flip_rounds_random(pts, tris.copy(), nb.copy())
+          print(f"{H}^2 seed {seed} greedy={greedy}: N={len(pts)} T={len(tris)} rounds={r} flips={tot} illegal edges per round (first 6) {hist[:6]} ... tail>{sum(1 for h in hist if h<=15)} rounds with <=15  ({time.time()-t0:.0f}s)", flush=True)
