@@ -1,6 +1,9 @@
 """Delaunay kernel with and without the single-warp tail (DT_TAIL): time per 64 frames, flip rounds, and a checksum of the
 mesh (the tail runs the same rounds, so the meshes must be bit-identical).  Children load the library named by
-FOVEA_B200_LIB."""
+FOVEA_B200_LIB.  The comparison library is not built by the Makefile:
+    cd foveated-instance-segmentation_b200/csrc && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
+        -I../../include -DDT_TAIL=0 -c delaunay.cu -o /tmp/dt0.o && nvcc -gencode arch=compute_100a,code=sm_100a -shared \
+        -o ../../tools/_libfovea_notail.so common.o saliency.o grid.o grid_sample.o inverse.o nearest.o /tmp/dt0.o -lcudart"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -31,5 +34,8 @@ else:
     for name, lib in (("tail (default build)", None), ("no tail (-DDT_TAIL=0)", os.path.join(ROOT, "tools", "_libfovea_notail.so"))):
         print(name, flush=True)
         env = dict(os.environ)
+        if lib and not os.path.exists(lib):
+            print("  (not built: see the docstring)")
+            continue
         if lib: env["FOVEA_B200_LIB"] = lib
         subprocess.run([sys.executable, __file__, "child"], env=env)
