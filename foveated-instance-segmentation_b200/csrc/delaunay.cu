@@ -19,6 +19,8 @@
 // Exactness: coordinates < 8192 keep the 4th-order in-circle determinant inside int64 (checked on the host).
 // Co-circular point sets (ubiquitous on a pixel lattice) have no unique Delaunay triangulation; any locally
 // Delaunay result is accepted (in-circle == 0 is legal), exactly as Qhull's 'Qt' picks an arbitrary one.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fovea {
@@ -305,6 +307,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   // cprev[m]: bits 0..12 = previous alive chain vertex (kCNone = chain start), bit 13 DEAD, bit 14 SELECTED, bit 15 EAR
   constexpr unsigned kCIdx = 0x1FFFu, kCNone = 0x1FFFu, kCDead = 0x2000u, kCSel = 0x4000u, kCEar = 0x8000u;
   int ntri_run = nstrip_tris;  // triangles so far (identical in every thread)
+  bool converged = true;       // false: a safety bound ended a loop early (block-uniform) -> the frame reports no mesh
   for (int side = 0; side < 2; ++side) {
     auto cpt = [&](int m) { return side == 0 ? static_cast<int>(A.rowStart[m]) : static_cast<int>(A.rowStart[m + 1]) - 1; };
     auto cpri = [&](int m, int round) {
@@ -317,6 +320,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       if (side == 1 && m < nstrips) A.cown[m] = rown[m];
     }
     __syncthreads();
+    bool closed = false;
     for (int round = 0; round < 4 * R + 64; ++round) {
       if (dbg && tid == 0) dbg[b * 8 + 4 + side] = round;
       // phase 1: which alive interior chain vertices are ears (strictly convex towards the pocket)?
@@ -345,7 +349,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
         selected_any = true;
         A.cprev[m] = static_cast<unsigned short>(cp | kCSel);
       }
-      if (!__syncthreads_or(selected_any)) break;
+      if (!__syncthreads_or(selected_any)) { closed = true; break; }
       // phase 2b: clip the selected ears (their neighbours are not selected, so the list surgery is race-free).
       // Triangle ids come from a block scan over the selected ears, not from an atomic counter: the numbering -- and
       // with it the flip priorities and the final choice among co-circular alternatives -- is the same on every run.
@@ -390,6 +394,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       }
       __syncthreads();
     }
+    converged = converged && closed;
     __syncthreads();
   }
   const int T = ntri_run;
@@ -416,6 +421,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   const int wpw = (nwords + 31) / 32;  // dirty words per warp (<= 16 for tcap <= 16383)
   const int wbase = warp * wpw;
   int round = 0, tail_hold = 0;
+  bool flips_done = false;
   for (; round < max_rounds; ++round) {
     // Claims carry a 6-bit round tag that DEcreases every round, so this round's atomicMin always beats the stale
     // claims of earlier rounds and the lock array only needs a reset when the tag wraps (every 64 rounds).
@@ -512,7 +518,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       if (o3 < kPendingCode) atomicMin(&A.lock[o3 >> 2], pri);
       if (o4 < kPendingCode) atomicMin(&A.lock[o4 >> 2], pri);
     }
-    if (!__syncthreads_or(any)) break;
+    if (!__syncthreads_or(any)) { flips_done = true; break; }
     // P2: winners flip
     it = 0;
     for (int base = 0; base < total; base += 32, ++it) {
@@ -677,7 +683,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       const int rr = s_tail[0];
       const bool finished = s_tail[1] != 0;
       __syncthreads();           // s_tail may be rewritten by the next attempt
-      if (finished) { round = rr + 1; break; }
+      if (finished) { round = rr + 1; flips_done = true; break; }
       tail_hold = rr + 8;        // the set outgrew a warp (or never fitted): a few block-wide rounds before the next try
       round = rr;
     }
@@ -686,6 +692,18 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
 #undef DT_N
 
   if (dbg && tid == 0) dbg[b * 8 + 0] = (int)((clock64() - clk0) >> 4);
+  // A loop that ran into its safety bound (flips: max_rounds; pockets: 4R + 64 rounds) leaves a mesh that is not
+  // Delaunay.  Never observed; if it happens the frame reports NO mesh (ntri = 0: every unfilled pixel stays NaN) and
+  // rounds = -1, which fovea.ops.check_plan turns into an exception -- never a silently wrong interpolation.
+  converged = converged && flips_done;
+  if (!converged) {
+    if (tid == 0) { ntri_out[b] = 0; if (rounds_out) rounds_out[b] = -1; }
+    if (hints_out) {
+      const int nh = ceil_div(H, FOVEA_HINT_CELL_H) * ceil_div(W, FOVEA_HINT_CELL_W);
+      for (int i = tid; i < nh; i += kDtThreads) hints_out[static_cast<size_t>(b) * nh + i] = 0;
+    }
+    return;
+  }
   // ------------------------------------------------------------------ output: 16-byte records (v0,v1,v2,0,n0,n1,n2,0)
   for (int t = tid; t < T; t += kDtThreads) {
     const unsigned c0 = A.n0[t], c1 = A.n1[t], c2 = A.n2[t];
@@ -777,8 +795,12 @@ static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int c
     return FOVEA_ERR_CAPACITY;
   }
   FOVEA_CUDA(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // safety bound on the flip rounds (worst frame seen: ~310); FOVEA_DT_MAX_ROUNDS lowers it to exercise the
+  // non-convergence report in the tests
+  int max_rounds = 20000;
+  if (const char* e = getenv("FOVEA_DT_MAX_ROUNDS")) max_rounds = atoi(e) > 0 ? atoi(e) : max_rounds;
   delaunay_kernel<<<B, kDtThreads, smem, stream>>>(
-      pts, npts, cap, tcap, mesh, ntri, static_cast<int32_t*>(workspace), 20000,
+      pts, npts, cap, tcap, mesh, ntri, static_cast<int32_t*>(workspace), max_rounds,
       static_cast<int32_t*>(workspace) + B, reinterpret_cast<unsigned short*>(static_cast<int32_t*>(workspace) + 9 * B),
       hints, H, W);
   return check_launch(who);

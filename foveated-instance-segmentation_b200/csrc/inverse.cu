@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "mesh.cuh"
+#include "fill.cuh"
 #include "select.cuh"
 #include "taps.cuh"
 #include "tma.cuh"
@@ -131,8 +132,13 @@ box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int
 
 // ------------------------------------------------------------------------------------------------ A9 points
 constexpr int kSelThreads = 1024;
-constexpr int kSelMax = 8192;
+constexpr int kSelMax = 16384;  // keys of one frame (h*w + 4 <= 16384); shared memory is sized by the launch to the
+                                // next power of two >= cap (64 KB for the 80x80 lattice, 128 KB for 64x128)
 
+// kNB = false: the sites of 'tri' (getPixelsForInterp, models/models.py:169-211: 3x3-cross dilation, four forced corners)
+// kNB = true : the sites of 'nearest' / 'BI' (getPixelsForInterp_NB, :213-242: cv2.dilate on the [C,H,W] array = pixels
+//              directly above / below only; no forced corners)
+template <bool kNB>
 __global__ void __launch_bounds__(kSelThreads, 1)
 select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict__ winner, int32_t* __restrict__ pts,
                      int32_t* __restrict__ src, int32_t* __restrict__ npts, SelectParams p) {
@@ -150,12 +156,12 @@ select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict_
     if (u < 0 || u >= p.W || v < 0 || v >= p.H) continue;
     if (win[static_cast<size_t>(v) * p.W + u] != node) continue;  // lost a collision
     const bool corner = (v == 0 || v == p.H - 1) && (u == 0 || u == p.W - 1);
-    if (corner) continue;  // corners are appended below, exactly once
-    if (!dilation_covers<false>(win, p, v, u)) continue;
+    if (!kNB && corner) continue;  // corners are appended below, exactly once
+    if (!dilation_covers<kNB>(win, p, v, u)) continue;
     const int slot = atomicAdd(&count, 1);
     keys[slot] = (static_cast<unsigned long long>((v << 16) | u) << 32) | static_cast<unsigned>(node);
   }
-  if (tid < 4) {  // models/models.py:202-209: the four corners are always interpolation points
+  if (!kNB && tid < 4) {  // models/models.py:202-209: the four corners are always interpolation points
     const int v = (tid & 2) ? p.H - 1 : 0, u = (tid & 1) ? p.W - 1 : 0;
     // (degenerate 1-pixel-wide canvases would duplicate corners; the host rejects H,W < 2)
     const int n = win[static_cast<size_t>(v) * p.W + u];
@@ -254,27 +260,6 @@ locate_hints_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__
 //   loc[b,y,x] = -(n+1)    : the pixel received low-res node n directly        (models/models.py:650-651);   [signed,
 //                            in-kernel form; stored as 16 bits, see encode_loc]
 //                            n == h*w: no value (outside the triangulation)    -> the NaN row of the value table
-
-// `loc` is stored in 16 bits per pixel (the fill kernel's only per-pixel read stream: halving it is worth 6 % of the
-// store bandwidth, measured with fovea_probe_store_ceiling): bit 15 clear = triangle id (< 32768), bit 15 set = direct
-// table row n (< 32768).  In-kernel the signed form is used: t >= 0, or -(n+1).
-__device__ __forceinline__ uint16_t encode_loc(int v) {
-  return static_cast<uint16_t>(v >= 0 ? v : (0x8000 | (-v - 1)));
-}
-__device__ __forceinline__ int decode_loc(unsigned v) { return (v & 0x8000u) ? -static_cast<int>(v & 0x7FFFu) - 1 : static_cast<int>(v); }
-
-// ---- per-triangle setup records ------------------------------------------------------------------------------
-// Everything the walkers and the fill need about a triangle, derived once per triangle from (mesh, pts, src) instead
-// of once per visit: one 64-byte record = four independent 16-byte loads, no pts/src indirection.
-//   e_i(y,x) = A_i*y + B_i*x + C_i  is the orientation-normalised edge function of the edge OPPOSITE vertex i
-//   (> 0 inside; e_0/area, e_1/area are the barycentric coordinates of vertices 0 and 1).  All exact int32 for
-//   coordinates < 16384.  Pixel (y,x) belongs to the triangle iff e_i >= m_i for i = 0,1,2, where m_i = 0 if the
-//   tie rule of mesh.cuh gives an exactly-on-edge pixel to this triangle (or the edge is on the hull), else 1.
-//   q0 = (A0, B0, C0, A1)   q1 = (B1, C1, A2, B2)   q2 = (C2, n0 | n1 << 16, n2 | m << 16, area)
-//   q3 = (src0 | src1 << 16, src2, 1/area as a double)            area == 0: degenerate, owns nothing
-struct TriRec {
-  uint4 q0, q1, q2, q3;
-};
 
 __global__ void __launch_bounds__(256)
 triangle_setup_kernel(const int32_t* __restrict__ pts, const int32_t* __restrict__ src, const uint4* __restrict__ mesh,
@@ -489,11 +474,6 @@ locate_pixels_kernel(const int32_t* __restrict__ winner, const TriRec* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ A8+A9+A10
-struct FillParams {
-  int C, Cs, h, w, H, W, cap, tcap, zero_residual;
-  int mask_u8;  // 1: the fused argmax is written as uint8 (C <= 256) instead of torch.argmax's int64
-};
-
 #ifndef FOVEA_FILL_THREADS
 #define FOVEA_FILL_THREADS 256
 #endif
@@ -651,8 +631,9 @@ __device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, cons
         }
         if (kMask) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // torch.argmax: the first maximum wins
-            if (c + e == 0 || v[k][e] > best[k]) { best[k] = v[k][e]; besti[k] = c + e; }
+          for (int k = 0; k < 4; ++k) {  // torch.argmax: the first maximum wins, and NaN counts as the maximum:
+            // !(v <= best) is "greater or unordered"; once `best` is NaN nothing replaces it (best == best fails)
+            if (c + e == 0 || (!(v[k][e] <= best[k]) && best[k] == best[k])) { best[k] = v[k][e]; besti[k] = c + e; }
           }
         }
       }
@@ -851,22 +832,36 @@ extern "C" int fovea_scatter_nodes(const int64_t* coords, int B, int h, int w, i
   return check_launch("fovea_scatter_nodes");
 }
 
-extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W,
-                                   int nchan, int cap, int32_t* pts, int32_t* src, int32_t* npts,
-                                   fovea_stream_t stream) {
-  FOVEA_REQUIRE(grid && winner && pts && src && npts, "fovea_select_points: null pointer");
-  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "fovea_select_points: bad sizes");
+template <bool kNB>
+static int launch_select(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int nchan, int cap,
+                         int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream, const char* who) {
+  FOVEA_REQUIRE(grid && winner && pts && src && npts, "%s: null pointer", who);
+  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "%s: bad sizes", who);
   if (cap < h * w + 4 || cap > kSelMax) {
-    set_error("fovea_select_points: cap=%d must satisfy h*w+4=%d <= cap <= %d", cap, h * w + 4, kSelMax);
+    set_error("%s: cap=%d must satisfy h*w+4=%d <= cap <= %d", who, cap, h * w + 4, kSelMax);
     return FOVEA_ERR_CAPACITY;
   }
   SelectParams p;
-  if (int rc = make_select_params(p, h, w, H, W, nchan, cap, "fovea_select_points")) return rc;
-  const int smem = kSelMax * static_cast<int>(sizeof(unsigned long long));
-  FOVEA_CUDA(cudaFuncSetAttribute(select_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  select_points_kernel<<<B, kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  if (int rc = make_select_params(p, h, w, H, W, nchan, cap, who)) return rc;
+  int n2 = 1;
+  while (n2 < cap) n2 <<= 1;
+  const int smem = n2 * static_cast<int>(sizeof(unsigned long long));
+  FOVEA_CUDA(cudaFuncSetAttribute(select_points_kernel<kNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  select_points_kernel<kNB><<<B, kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float2*>(grid), winner, pts, src, npts, p);
-  return check_launch("fovea_select_points");
+  return check_launch(who);
+}
+
+extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W,
+                                   int nchan, int cap, int32_t* pts, int32_t* src, int32_t* npts,
+                                   fovea_stream_t stream) {
+  return launch_select<false>(grid, winner, B, h, w, H, W, nchan, cap, pts, src, npts, stream, "fovea_select_points");
+}
+
+extern "C" int fovea_select_points_nb(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W,
+                                      int nchan, int cap, int32_t* pts, int32_t* src, int32_t* npts,
+                                      fovea_stream_t stream) {
+  return launch_select<true>(grid, winner, B, h, w, H, W, nchan, cap, pts, src, npts, stream, "fovea_select_points_nb");
 }
 
 extern "C" int64_t fovea_locate_hints_workspace_bytes(int B, int H, int W) {

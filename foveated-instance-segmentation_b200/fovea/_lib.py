@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class FoveaError(RuntimeError):
@@ -44,6 +44,7 @@ PROTOTYPES = {
     "fovea_grid_inv_canvas": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_box4_table": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_select_points": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fovea_select_points_nb": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_delaunay_workspace_bytes": (_i64, [_i, _i]),
     "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_delaunay_hints_fused": (_i, [_i, _i, _i]),
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "fovea_inverse_fill_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_nearest_workspace_bytes": (_i64, [_i, _i, _i]),
     "fovea_nearest_locate": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_scatter_nodes": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),

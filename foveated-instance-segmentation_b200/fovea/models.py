@@ -13,7 +13,11 @@ Encoder / decoder / saliency networks are whatever `nn.Module`s the caller passe
 Dead work of the reference forward whose result is unobservable is skipped and listed in DESIGN.md (the per-sample
 PIL blur/edge loop models.py:776-800, the second/third create_grid calls :849-852, PNG dumps :973-1051, d(filter.weight)).
 Config branches the shipped `config/deform.yaml` never takes (uniform_sample, gt_gradient, deep supervision,
-loss_at_high_res, dynamic_task_input) raise NotImplementedError instead of silently running something else.
+dynamic_task_input) raise NotImplementedError instead of silently running something else.
+
+Triangulation of rev_deform_interp='tri': the reference runs Qhull on the host (interp2d.py:55).  The default here is the
+same ("host": bit-for-bit the reference's mesh); `triangulation="device"` (argument, or FOVEA_TRIANGULATION=device in
+the environment) selects the sm_100a Delaunay kernel, which differs from Qhull only inside co-circular lattice cells.
 """
 from __future__ import annotations
 
@@ -22,9 +26,19 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from . import ops
 from ._lib import FoveaError
 from .interp2d import Interp2D, interp2d_scores
+
+
+def default_triangulation():
+    """"host" (Qhull, the reference's own mesh) unless FOVEA_TRIANGULATION=device opts into the Delaunay kernel."""
+    mode = os.environ.get("FOVEA_TRIANGULATION", "host")
+    if mode not in ("host", "device"):
+        raise FoveaError(f"FOVEA_TRIANGULATION must be 'host' or 'device', got {mode!r}")
+    return mode
 
 
 def b_imresize(im, size, interp="bilinear"):
@@ -113,7 +127,7 @@ def _fill_nearest(t):
     return t
 
 
-def fillMissingValues_tensor(target_for_interp, copy=False, interp_mode="tri", triangulation="device"):
+def fillMissingValues_tensor(target_for_interp, copy=False, interp_mode="tri", triangulation=None):
     """models/models.py:159-286 for interp_mode='tri' | 'nearest' on a CUDA tensor [C,H,W]; in place unless `copy`.
 
     The NaN pattern is taken from channel 0 (the reference's own point extraction uses `mask_for_interp[0]`,
@@ -143,7 +157,7 @@ def fillMissingValues_tensor(target_for_interp, copy=False, interp_mode="tri", t
     mask[0, 0] = mask[0, -1] = mask[-1, 0] = mask[-1, -1] = True                # :202-209
     rr, cc = torch.where(mask)                                                  # :265-267
     values = t[:, rr, cc].T.contiguous()                                        # :268 (NaN at unfilled corners)
-    interp = interp2d_scores(torch.stack([rr, cc], 1), values, H, W, triangulation)
+    interp = interp2d_scores(torch.stack([rr, cc], 1), values, H, W, triangulation or default_triangulation())
     t[:, invalid] = interp[:, invalid]                                          # :280
     return t
 
@@ -191,13 +205,14 @@ class DeformSegmentationModule(SegmentationModuleBase):
     """models/models.py:476-1094 (training / eval-at-low-res forward) + models_instance.py:840-1121 (inference)."""
 
     def __init__(self, net_encoder, net_decoder, net_saliency, net_compress, crit, cfg, deep_sup_scale=None,
-                 triangulation="device"):
+                 triangulation=None):
         super().__init__()
         self.encoder, self.decoder = net_encoder, net_decoder
         self.localization, self.net_compress = net_saliency, net_compress
         self.crit = MulticlassDiceLoss()                                        # models.py:482 ignores `crit` too
         self.crit_mse = nn.MSELoss()
-        self.cfg, self.deep_sup_scale, self.triangulation = cfg, deep_sup_scale, triangulation
+        self.cfg, self.deep_sup_scale = cfg, deep_sup_scale
+        self.triangulation = triangulation or default_triangulation()
         if deep_sup_scale is not None:
             raise NotImplementedError("deep supervision is not part of the foveated path")
         sal = cfg.TRAIN.saliency_input_size
@@ -287,8 +302,7 @@ class DeformSegmentationModule(SegmentationModuleBase):
 
     def _check_cfg(self):
         c = self.cfg
-        if c.MODEL.uniform_sample != "" or getattr(c.MODEL, "gt_gradient", False) or \
-                getattr(c.MODEL, "loss_at_high_res", False) or c.TRAIN.dynamic_task_input[0] != 1:
+        if c.MODEL.uniform_sample != "" or getattr(c.MODEL, "gt_gradient", False) or c.TRAIN.dynamic_task_input[0] != 1:
             raise NotImplementedError("only the foveated (deform.yaml) configuration runs on the B200 path")
         if not (c.TRAIN.deform_joint_loss and c.TRAIN.opt_deform_LabelEdge_norm):
             raise NotImplementedError("only the joint-loss / normalised edge-loss configuration of deform.yaml")
@@ -299,8 +313,10 @@ class DeformSegmentationModule(SegmentationModuleBase):
             return ops.build_nearest_plan(grid.detach(), segSize, nchan=nchan)
         if mode == "tri":
             return ops.build_inverse_plan(grid.detach(), segSize, nchan=nchan, triangulation=self.triangulation)
-        raise NotImplementedError("rev_deform_interp must be 'tri' or 'nearest' on the GPU path ('BI' is the host SciPy "
-                                  "LinearNDInterpolator: the same interpolant as 'tri')")
+        if mode == "BI":                           # models/models.py:248-250 (see ops.build_inverse_plan, sites="nb")
+            return ops.build_inverse_plan(grid.detach(), segSize, nchan=nchan, triangulation=self.triangulation,
+                                          sites="nb")
+        raise NotImplementedError(f"rev_deform_interp={mode!r}: expected 'tri', 'nearest' or 'BI'")
 
     def plan_async(self, grid, segSize):
         """Start the saliency-only half of stage 3 (A7 scatter, A9 point selection, Delaunay, point location) on a
@@ -323,7 +339,11 @@ class DeformSegmentationModule(SegmentationModuleBase):
         return plan, done, int(nchan)
 
     def inverse_upsample(self, pred, grid, segSize, zero_residual, want_mask=False, plan=None):
-        """grid_inv + F.grid_sample(pred, grid_inv) + NaN mask + per-sample fill (models.py:933-940) fused."""
+        """grid_inv + F.grid_sample(pred, grid_inv) + NaN mask + per-sample fill (models.py:933-940) fused.
+        Differentiable w.r.t. `pred` (the reference's autograd graph through F.grid_sample + Interp2D)."""
+        if tuple(pred.shape[-2:]) != tuple(grid.shape[1:3]):
+            raise NotImplementedError(f"inverse upsampling needs the decoder output {tuple(pred.shape[-2:])} at the "
+                                      f"sampling-grid resolution {tuple(grid.shape[1:3])}")
         if plan is not None and plan[2] == pred.shape[1]:
             plan, done, _ = plan
             torch.cuda.current_stream(pred.device).wait_event(done)
@@ -331,7 +351,9 @@ class DeformSegmentationModule(SegmentationModuleBase):
                 t.record_stream(torch.cuda.current_stream(pred.device))
         else:
             plan = self._build_plan(grid, segSize, pred.shape[1])
-        return ops.inverse_fill(plan, pred, want_scores=True, want_mask=want_mask, zero_residual=zero_residual)
+        out = ops.inverse_fill(plan, pred, want_scores=True, want_mask=want_mask, zero_residual=zero_residual)
+        ops.check_plan(plan)     # (after the fill is enqueued: the one host sync reads a [B] status word)
+        return out
 
     # -- forward ------------------------------------------------------------------------------------------------
     def forward(self, feed_dict, *, writer=None, segSize=None, F_Xlr_acc_map=False, count=None, epoch=None,
@@ -343,7 +365,7 @@ class DeformSegmentationModule(SegmentationModuleBase):
         xs = self._saliency(x, feed_dict["focus_point"])
         y = feed_dict["seg_label"].clone()
         if segSize is not None:
-            return self._forward_inference(feed_dict, x, xs, y, segSize)
+            return self._forward_inference(feed_dict, x, xs, y, segSize, F_Xlr_acc_map)
 
         # ---- training / eval at low resolution (models/models.py:828-1094)
         xs_target = F.interpolate(y if y.dim() == 4 else y.unsqueeze(0), size=(self.grid_size_x, self.grid_size_y),
@@ -353,10 +375,22 @@ class DeformSegmentationModule(SegmentationModuleBase):
         xs_n = (xs - xs.min()) / (xs.max() - xs.min())                          # :889-898
         xt_n = (xs_target - xs_target.min()) / (xs_target.max() - xs_target.min())
         edge_loss = 0.05 * self.crit_mse(xs_n, xt_n) * cfg.TRAIN.edge_loss_scale
-        upsample = cfg.MODEL.upsample
-        plan = self.plan_async(grid, (H_HS, W_HS)) if upsample else None        # overlaps the encoder/decoder
+        high_res = bool(getattr(cfg.MODEL, "loss_at_high_res", False))
+        upsample = cfg.MODEL.upsample or high_res
+        rate = int(cfg.DATASET.segm_downsampling_rate)
+        inv_size = (H_HS // rate, W_HS // rate)                                 # :873 ori_size // segm_downsampling_rate
+        plan = self.plan_async(grid, inv_size) if upsample else None            # overlaps the encoder/decoder
         x_sampled = self._sample_image(x, grid)                                    # :909
         pred = self.decoder(self.encoder(x_sampled, return_feature_maps=True))  # :926
+        if high_res:                                                            # :945-947, :962-965, :1070-1071
+            # the loss is taken on the inverse-upsampled scores: the gradient reaches `pred` through the inverse path
+            pred_sampled, _ = self.inverse_upsample(pred, grid, inv_size, zero_residual=True, plan=plan)
+            loss = self.crit(pred_sampled, feed_dict["seg_label"]) + edge_loss
+            acc = self.pixel_acc(pred_sampled, feed_dict["seg_label"].reshape(pred_sampled.shape[0], *pred_sampled.shape[-2:]))
+            if is_inference:
+                raise NotImplementedError("is_inference with MODEL.loss_at_high_res: the reference's own forward "
+                                          "references unset metrics on this branch (models/models.py:1070-1090)")
+            return loss, acc, edge_loss
         seg_low = y_sampled.long()
         y_hs = feed_dict["seg_label"].squeeze(1)
         feed_dict["seg_label"] = seg_low                                        # :951 (the reference mutates it too)
@@ -366,7 +400,8 @@ class DeformSegmentationModule(SegmentationModuleBase):
         if not upsample:
             target, scored = ground_truth, pred
         else:                                                                   # :933-940, :971
-            scored, _ = self.inverse_upsample(pred, grid, (H_HS, W_HS), zero_residual=False, plan=plan)
+            with torch.no_grad():                                               # only the metrics read it on this branch
+                scored, _ = self.inverse_upsample(pred, grid, inv_size, zero_residual=False, plan=plan)
             target = (y_hs * cls[:, :, None] + (1 - y_hs) * 50).long()
         acc = self.pixel_acc(scored, target)
         if not is_inference:
@@ -374,17 +409,32 @@ class DeformSegmentationModule(SegmentationModuleBase):
         return (loss, acc, edge_loss, self.fg_bin_pixel_acc(scored, target), self.fbg_cls_pixel_acc(scored, target),
                 self.fbg_bin_pixel_acc(scored, target))
 
-    def _forward_inference(self, feed_dict, x, xs, y, segSize):
-        """models_instance.py:840-1121 with rev_deform_opt == 51 ('ours deformed case')."""
+    def _forward_inference(self, feed_dict, x, xs, y, segSize, F_Xlr_acc_map=False):
+        """models_instance.py:840-1121 with rev_deform_opt == 51 ('ours deformed case').  Returns what the reference
+        returns: (pred_sampled, pred, y_sampled[, y_sampled_reverse]) -- also when VAL.no_upsample is set (that flag
+        only renames tensors for the reference's visualisation, :942-949) -- or (pred_sampled, loss) for F_Xlr_acc_map."""
+        cfg = self.cfg
+        if getattr(cfg.MODEL, "rev_deform_opt", 51) != 51:
+            raise NotImplementedError("only MODEL.rev_deform_opt == 51 (the deformed inverse) runs on the B200 path")
         grid, grid_y = self._grid_from_saliency(xs, segSize=segSize)            # :844-845
-        plan = None if getattr(self.cfg.VAL, "no_upsample", False) else self.plan_async(grid, segSize)
+        plan = self.plan_async(grid, segSize)
         x_sampled = self._sample_image(x, grid)                                    # :851-852
         if tuple(x_sampled.shape[-2:]) != tuple(self.input_size_net_infer):
             x_sampled = F.interpolate(x_sampled, self.input_size_net_infer, mode="bilinear")
         pred = self.decoder(self.encoder(x_sampled, return_feature_maps=True), segSize=tuple(self.input_size_net_infer))
         y4 = y.float() if y.dim() == 4 else y.float().unsqueeze(1)
         y_sampled = F.grid_sample(y4, grid_y, mode="nearest", align_corners=False).long().squeeze(1)   # :866 (stock)
-        if getattr(self.cfg.VAL, "no_upsample", False):
-            return pred, x_sampled, xs
         pred_sampled, _ = self.inverse_upsample(pred, grid, segSize, zero_residual=True, plan=plan)   # :883-893, :940
+        if F_Xlr_acc_map:                                                       # :1112-1114
+            return pred_sampled, self.crit(pred_sampled, feed_dict["seg_label"])
+        if getattr(cfg.VAL, "y_sampled_reverse", False):                        # :904-930
+            if cfg.MODEL.rev_deform_interp != "tri":
+                raise NotImplementedError("VAL.y_sampled_reverse is built for rev_deform_interp='tri' only")
+            nclass = int(cfg.DATASET.num_class)
+            onehot = F.one_hot(y_sampled.clamp(0, nclass - 1), nclass).permute(0, 3, 1, 2).float().contiguous()
+            onehot = onehot * (y_sampled[:, None] == torch.arange(nclass, device=y_sampled.device)[None, :, None, None])
+            rev_plan = self._build_plan(grid, segSize, nclass)
+            rev, _ = ops.inverse_fill(rev_plan, onehot, want_scores=True, zero_residual=False)
+            ops.check_plan(rev_plan)
+            return pred_sampled, pred, y_sampled, torch.max(rev, dim=1)[1].long()   # :930 (NaN pixels: argmax 0, as torch)
         return pred_sampled, pred, y_sampled

@@ -23,7 +23,23 @@ def _ptr(t):
 
 
 def _stream():
+    """torch's current stream on the current device; `_req` refuses tensors that live on another device."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req_out(t, dtype, name, shape):
+    """An output buffer supplied by the caller: written through its raw pointer, so it must BE the expected buffer --
+    CUDA, right dtype, exact shape, contiguous (a .contiguous() copy would silently receive the result instead)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise FoveaError(f"{name}: expected a CUDA tensor")
+    dtypes = dtype if isinstance(dtype, tuple) else (dtype,)
+    if t.dtype not in dtypes:
+        raise FoveaError(f"{name}: expected dtype {' or '.join(str(d) for d in dtypes)}, got {t.dtype}")
+    if tuple(t.shape) != tuple(shape):
+        raise FoveaError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise FoveaError(f"{name}: must be contiguous")
+    return t
 
 
 def _req(t, dtype, name, ndim=None):
@@ -34,6 +50,9 @@ def _req(t, dtype, name, ndim=None):
         raise FoveaError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if ndim is not None and t.dim() != ndim:
         raise FoveaError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    if t.device.index != torch.cuda.current_device():    # kernels launch on the CURRENT device's current stream
+        raise FoveaError(f"{name}: tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         f"call inside `with torch.cuda.device({t.device.index})`")
     return t.contiguous()
 
 
@@ -278,6 +297,7 @@ class InversePlan:
     cap: int
     tcap: int
     triangulation: str
+    rounds: torch.Tensor = None   # [B] int32 flip rounds of the device Delaunay kernel; -1 = did not converge (check_plan)
 
 
 def _host_delaunay_one(pts_packed: np.ndarray):
@@ -313,13 +333,18 @@ def _triangulate_host(pts, npts, cap, tcap, pool=None):
     return torch.from_numpy(mesh).to(dev), torch.from_numpy(ntri).to(dev)
 
 
-def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) -> InversePlan:
+def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, sites="tri") -> InversePlan:
     """A7 scatter + A9 point selection + triangulation + walk hints for a batch of sampling grids.
 
     triangulation='host'  : stock SciPy Qhull on the host, exactly what the reference does (parity mode);
     triangulation='device': the sm_100a Delaunay kernel (fast mode; differs from Qhull only in how co-circular
                             point sets are split).
+    sites='tri': interpolation sites of rev_deform_interp='tri' (getPixelsForInterp, models/models.py:169-211);
+    sites='nb' : the sites of 'BI' / 'nearest' (getPixelsForInterp_NB, :213-242; no forced corners: pixels outside the
+                 sites' convex hull stay NaN, as scipy's LinearNDInterpolator leaves them).
     """
+    if sites not in ("tri", "nb"):
+        raise FoveaError(f"unknown site rule {sites!r}")
     g = _req(grid.detach(), torch.float32, "grid", 4)
     B, h, w, _ = g.shape
     H, W = int(segSize[0]), int(segSize[1])
@@ -330,23 +355,36 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None) ->
     pts = torch.empty(B, cap, device=dev, dtype=torch.int32)
     src = torch.empty(B, cap, device=dev, dtype=torch.int32)
     npts = torch.empty(B, device=dev, dtype=torch.int32)
-    _lib.call("fovea_select_points", _ptr(g), _ptr(winner), B, h, w, H, W, int(nchan), cap, _ptr(pts), _ptr(src),
-              _ptr(npts), _stream())
-    hints = None
+    _lib.call("fovea_select_points" if sites == "tri" else "fovea_select_points_nb", _ptr(g), _ptr(winner), B, h, w, H,
+              W, int(nchan), cap, _ptr(pts), _ptr(src), _ptr(npts), _stream())
+    hints = rounds = None
     if triangulation == "host":
         mesh, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
     elif triangulation == "device":
         if _lib.load().fovea_delaunay_hints_fused(tcap, H, W):
-            mesh, ntri, hints = delaunay_device_with_hints(pts, npts, cap, tcap, H, W)
+            mesh, ntri, hints, ws = delaunay_device_with_hints(pts, npts, cap, tcap, H, W)
         else:
-            mesh, ntri, _ = delaunay_device(pts, npts, cap, tcap, max(H, W))
+            mesh, ntri, ws = delaunay_device(pts, npts, cap, tcap, max(H, W))
+        rounds = ws[:B]
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
     if hints is None:
         hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
     trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), h * w)
     loc = _locate(winner, trirec, ntri, hints, h, w, tcap)
-    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, h, w, H, W, cap, tcap, triangulation)
+    return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, h, w, H, W, cap, tcap, triangulation,
+                       rounds)
+
+
+def check_plan(plan: InversePlan):
+    """Raise FoveaError if the device Delaunay kernel reported a frame whose flip loop hit its safety bound (it then
+    emits NO mesh for that frame rather than a non-Delaunay one).  Reads a [B] int32 tensor back: one host sync -- the
+    reference-facing mirrors call it after the fill has been enqueued; pipelines call it when they drain."""
+    if plan.rounds is not None:
+        bad = torch.nonzero(plan.rounds < 0).flatten().tolist()
+        if bad:
+            raise FoveaError(f"device Delaunay did not converge for frame(s) {bad}; use triangulation='host'")
+    return plan
 
 
 def delaunay_device(pts, npts, cap, tcap, max_coord):
@@ -374,7 +412,7 @@ def delaunay_device_with_hints(pts, npts, cap, tcap, H, W):
     ws = torch.zeros((nbytes + 3) // 4, device=dev, dtype=torch.int32)
     _lib.call("fovea_delaunay_with_hints", _ptr(pts), _ptr(npts), B, cap, tcap, H, W, _ptr(mesh), _ptr(ntri),
               _ptr(hints), _ptr(ws), _stream())
-    return mesh, ntri, hints
+    return mesh, ntri, hints, ws
 
 
 def _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W):
@@ -479,21 +517,82 @@ def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
 
 
 def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=None, mask=None):
-    """fovea_inverse_fill on a caller-built value table [B, plan.h*plan.w + 2, Cs]."""
-    B = plan.winner.shape[0]
-    _fill(plan, table, int(C), zero_residual, scores, mask)
+    """fovea_inverse_fill on a caller-built value table [B, plan.h*plan.w + 2, Cs].  Differentiable w.r.t. `table` when it
+    requires grad and scores are produced (interp2d.py:38-47: gradients flow to `values`)."""
+    if scores is not None and torch.is_grad_enabled() and table.requires_grad:
+        return _FillFn.apply(table, plan, int(C), bool(zero_residual), scores, mask), mask
+    _fill(plan, table.detach(), int(C), zero_residual, scores, mask)
     return scores, mask
 
 
 def _fill(plan, table, C, zero_residual, scores, mask):
     mask_u8 = 0
-    if mask is not None:
-        if mask.dtype not in (torch.int64, torch.uint8) or not mask.is_cuda or not mask.is_contiguous():
-            raise FoveaError("inverse_fill: mask must be a contiguous CUDA int64 (torch.argmax's dtype) or uint8 tensor")
+    B = plan.loc.shape[0]
+    if scores is not None:
+        _req_out(scores, torch.float32, "inverse_fill: scores", (B, C, plan.H, plan.W))
+    if mask is not None:   # int64 = torch.argmax's dtype
+        _req_out(mask, (torch.int64, torch.uint8), "inverse_fill: mask", (B, plan.H, plan.W))
         mask_u8 = 1 if mask.dtype == torch.uint8 else 0
+    if table.dim() != 3 or table.shape[0] != B or table.shape[1] != plan.h * plan.w + 2 or table.shape[2] < C:
+        raise FoveaError(f"inverse_fill: value table {tuple(table.shape)} does not match the plan "
+                         f"([{B}, {plan.h * plan.w + 2}, >= {C}])")
+    table = _req(table, torch.float32, "inverse_fill: table", 3)
     _lib.call("fovea_inverse_fill", _ptr(plan.loc), _ptr(plan.trirec), _ptr(table), plan.loc.shape[0], C,
               table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.tcap, 1 if zero_residual else 0, _ptr(scores),
               _ptr(mask), mask_u8, _stream())
+
+
+class _FillFn(torch.autograd.Function):
+    """fovea_inverse_fill with the gradient of the scores w.r.t. the value table (fovea_inverse_fill_bwd): the autograd
+    edge the reference gets from torch.gather / mul / sum in interp2d.py:76-89 and from F.grid_sample(pred, grid_inv)
+    at the pixels that received a node (models/models.py:937).  The argmax mask (if any) is written as a side effect."""
+
+    @staticmethod
+    def forward(ctx, table, plan, C, zero_residual, scores, mask):
+        _fill(plan, table.detach(), C, zero_residual, scores, mask)
+        ctx.plan, ctx.C, ctx.tshape = plan, C, tuple(table.shape)
+        ctx.mark_dirty(scores)
+        return scores
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        plan, C = ctx.plan, ctx.C
+        g = _req(grad_scores, torch.float32, "grad_scores", 4)
+        B, rows, Cs = ctx.tshape
+        gtable = torch.empty(B, rows, Cs, device=g.device, dtype=torch.float32)
+        _lib.call("fovea_inverse_fill_bwd", _ptr(plan.loc), _ptr(plan.trirec), _ptr(g), B, C, Cs, plan.h, plan.w, plan.H,
+                  plan.W, plan.tcap, _ptr(gtable), _stream())
+        return gtable, None, None, None, None, None
+
+
+def _node_grid(B, h, w, device):
+    """The coordinates the reference stores in grid_inv for node (i,j) (models/models.py:652-653): x = j/w*2-1, y = i/h*2-1,
+    fp32 op for op -- fovea_box4_table samples `pred` exactly there."""
+    gx = torch.arange(w, device=device, dtype=torch.float32) / float(w) * 2.0 - 1.0
+    gy = torch.arange(h, device=device, dtype=torch.float32) / float(h) * 2.0 - 1.0
+    g = torch.stack([gx[None, :].expand(h, w), gy[:, None].expand(h, w)], dim=-1)
+    return g[None].expand(B, h, w, 2).contiguous()
+
+
+class _Box4TableFn(torch.autograd.Function):
+    """fovea_box4_table with its transpose: the table is F.grid_sample(pred, node grid) laid out channel-last, so the
+    gradient w.r.t. pred is fovea_grid_sample_bwd's scatter-add at the node coordinates."""
+
+    @staticmethod
+    def forward(ctx, pred, Cs):
+        table = box4_table(pred, Cs)
+        ctx.pshape = tuple(pred.shape)
+        return table
+
+    @staticmethod
+    def backward(ctx, gtable):
+        B, Cc, h, w = ctx.pshape
+        go = gtable[:, :h * w, :Cc].permute(0, 2, 1).reshape(B, Cc, h, w).contiguous()
+        grid = _node_grid(B, h, w, go.device)
+        gi = torch.zeros(B, Cc, h, w, device=go.device, dtype=torch.float32)
+        # grad_input only: the input values themselves are not read (they only enter d/d grid)
+        _lib.call("fovea_grid_sample_bwd", _ptr(go), _ptr(gi), _ptr(grid), B, Cc, h, w, h, w, _ptr(gi), None, _stream())
+        return gi, None
 
 
 def box4_table(pred, Cs=None):
@@ -508,20 +607,24 @@ def box4_table(pred, Cs=None):
 
 def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zero_residual=True, out=None,
                  mask_out=None):
-    """A8 + A9 (+A10): full-resolution scores [B,C,H,W] and/or argmax mask [B,H,W] int64 from pred [B,C,h,w]."""
-    p = _req(pred.detach(), torch.float32, "pred", 4)
+    """A8 + A9 (+A10): full-resolution scores [B,C,H,W] and/or argmax mask [B,H,W] int64 from pred [B,C,h,w].
+    Differentiable w.r.t. `pred` (scores only) when it requires grad: models/models.py:933-940."""
+    p = _req(pred, torch.float32, "pred", 4)
     B, Cc, h, w = p.shape
     if (h, w) != (plan.h, plan.w) or B != plan.winner.shape[0]:
         raise FoveaError(f"inverse_fill: pred {tuple(p.shape)} does not match the plan ({B}x{plan.h}x{plan.w})")
-    table = box4_table(p)
     scores = None
     if want_scores:
         scores = out if out is not None else torch.empty(B, Cc, plan.H, plan.W, device=p.device, dtype=torch.float32)
-        _req(scores, torch.float32, "scores out", 4)
+        _req_out(scores, torch.float32, "inverse_fill: out", (B, Cc, plan.H, plan.W))
     mask = None
     if want_mask:
         mask = mask_out if mask_out is not None else torch.empty(B, plan.H, plan.W, device=p.device, dtype=torch.int64)
-    _fill(plan, table, Cc, zero_residual, scores, mask)
+        _req_out(mask, (torch.int64, torch.uint8), "inverse_fill: mask_out", (B, plan.H, plan.W))
+    if want_scores and torch.is_grad_enabled() and p.requires_grad:
+        table = _Box4TableFn.apply(p, None)
+        return _FillFn.apply(table, plan, Cc, bool(zero_residual), scores, mask), mask
+    _fill(plan, box4_table(p), Cc, zero_residual, scores, mask)
     return scores, mask
 
 

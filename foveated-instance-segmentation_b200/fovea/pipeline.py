@@ -68,7 +68,9 @@ class ResamplePipeline:
 
     def submit(self, hx, hxs, hpred, hmask_out):
         """Enqueue one batch: pinned host image [B,3,H,W], saliency [B,1,g,g], pred [B,C,g,g] -> hmask_out [B,H,W] int64
-        (pinned).  Returns immediately; `drain()` (or reuse of the slot `depth` submits later) orders completion."""
+        (pinned).  Returns x_sampled [B,3,g,g] (ordered on the caller's current stream) immediately; `drain()` (or reuse
+        of the slot `depth` submits later) orders completion of the masks.  The host buffers must stay untouched until
+        then (they are read / written asynchronously)."""
         for t, name in ((hx, "image"), (hxs, "saliency"), (hpred, "pred"), (hmask_out, "mask_out")):
             if t.is_cuda or not t.is_pinned():
                 raise FoveaError(f"ResamplePipeline.submit: {name} must be a pinned host tensor")
@@ -91,6 +93,9 @@ class ResamplePipeline:
                 parts.insert(0, sample(s.x, s.grid[:nc]))
             s.x_sampled = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
             s.h2d_done.record(self.copy_in)
+        # x_sampled is produced on the ingest stream: the caller's stream (where the encoder would consume it) is ordered
+        # behind it here, so the returned tensor is safe to use like any other torch result
+        torch.cuda.current_stream(self.dev).wait_event(s.h2d_done)
         with torch.cuda.stream(self.plan_stream):            # saliency-only half of the inverse stage, high priority:
             self.plan_stream.wait_event(s.h2d_done)          # it overlaps the HBM-bound fill of the previous batch
             plan = ops.build_inverse_plan(s.grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
@@ -127,6 +132,9 @@ class ResamplePipeline:
     def drain(self):
         for st in (self.copy_in, self.plan_stream, self.compute, self.copy_out):
             st.synchronize()
+        for s in self.slots:
+            if s.used:
+                ops.check_plan(s.plan)
 
 
 class DevicePipeline:
@@ -177,6 +185,8 @@ class DevicePipeline:
                 self.plan_stream.wait_event(self.live[0][1])
             grid = ops.saliency_to_grid(xs, self.g1x, self.g1y, g, g, R, R, "replication", (g, g))
             x_sampled = ops.grid_sample(x, grid)
+            sampled = torch.cuda.Event()
+            sampled.record(self.plan_stream)
             if self.interp == "nearest":
                 plan = ops.build_nearest_plan(grid, (self.H, self.W), nchan=self.C)
             else:
@@ -197,7 +207,12 @@ class DevicePipeline:
                 self.fill_events.append((t0, t1))
             done = torch.cuda.Event()
             done.record(self.fill_stream)
-        self.live.append(((plan, grid, table, x_sampled), done))
+        # Contract: x_sampled is ordered on the caller's stream before it is returned (the encoder can consume it like any
+        # torch result); the inputs x, xs, pred are read on the pipeline's streams AFTER submit returns, so references are
+        # held until `depth` batches later -- the caching allocator cannot recycle them under the kernels even if the
+        # caller drops them (they must not be overwritten in place before then).
+        cur.wait_event(sampled)
+        self.live.append(((plan, grid, table, x_sampled, x, xs, pred), done))
         if len(self.live) > self.depth:
             self.live.pop(0)
         return x_sampled, self.scores
@@ -206,3 +221,8 @@ class DevicePipeline:
         stream = stream or torch.cuda.current_stream(self.dev)
         stream.wait_stream(self.plan_stream)
         stream.wait_stream(self.fill_stream)
+
+    def check(self):
+        """Raise if the device Delaunay kernel reported a non-converged frame in any batch still referenced (host sync)."""
+        for item, _ in self.live:
+            ops.check_plan(item[0])

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 10
+#define FOVEA_ABI_VERSION 11
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -157,9 +157,17 @@ int fovea_box4_table(const float* pred, int B, int C, int h, int w, int Cs, floa
  *   nchan     C of the tensor the reference would dilate (enters max(C,H,W)/512, models.py:183)
  *   grid [B,h,w,2] the sampling grid the winners were scattered from
  *   pts  [B,cap] int32  (row<<16 | col)      src [B,cap] int32 row into `table` (h*w = NaN corner)
- *   npts [B]     int32                       h*w+4 <= cap <= 8192 */
+ *   npts [B]     int32                       h*w+4 <= cap <= 16384
+ * fovea_select_points_nb: the site rule of interp_mode 'nearest' / 'BI' instead (getPixelsForInterp_NB,
+ * models/models.py:213-242: cv2.dilate reads the [C,H,W] array as rows=C, cols=H, channels=W, so a filled pixel is a
+ * site iff the pixel directly above or below it is unfilled; no forced corners).  With these sites the 'tri' machinery
+ * (Delaunay + barycentric fill, NaN outside the hull) is rev_deform_interp='BI': scipy's LinearNDInterpolator over the
+ * (class, row, col) voxels (:248-250, 269-272) restricted to a class plane is the 2-D Delaunay interpolant of that plane
+ * (DESIGN.md section 4). */
 int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
                         int cap, int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream);
+int fovea_select_points_nb(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
+                           int cap, int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream);
 
 /* Triangle mesh layout shared by the entry points below:
  *   mesh [B,tcap,8] uint16, one 16-byte record per triangle: (v0, v1, v2, 0, n0, n1, n2, 0)
@@ -234,6 +242,16 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
 int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
                        int H, int W, int tcap, int zero_residual, float* scores, void* mask, int mask_u8,
                        fovea_stream_t stream);
+
+/* Backward of fovea_inverse_fill w.r.t. its value table: the autograd graph the reference builds when it trains through
+ * the inverse path (models/models.py:933-940, MODEL.upsample / MODEL.loss_at_high_res) and the gradient Interp2D
+ * promises for `values` (interp2d.py:38-47):   grad_table[b, row, c] = sum over pixels p and vertices k with
+ * row_k(p) == row of  w_k(p) * grad_scores[b, c, p].   Pixels the forward leaves NaN / zero send nothing.
+ * grad_table [B, h*w+2, Cs] is zeroed by the call and accumulated with atomics (the order of the adds, and so the
+ * last bits, can differ from run to run, exactly like ATen's grid_sampler backward).  The transpose of
+ * fovea_box4_table (table -> pred) is fovea_grid_sample_bwd at the node coordinates. */
+int fovea_inverse_fill_bwd(const uint16_t* loc, const void* trirec, const float* grad_scores, int B, int C, int Cs, int h,
+                           int w, int H, int W, int tcap, float* grad_table, fovea_stream_t stream);
 
 /* rev_deform_interp = 'nearest' (the mode config/deform.yaml:17 ships): fillMissingValues_tensor(..., 'nearest'),
  * models/models.py:213-250, 259-272 = getPixelsForInterp_NB + scipy NearestNDInterpolator on the host.  Produces the

@@ -363,13 +363,28 @@ def fill_missing_values_nearest(t: torch.Tensor, copy: bool = False, return_site
     return (t, mask) if return_sites else t
 
 
+def fill_missing_values_bi(t: torch.Tensor, copy: bool = False) -> torch.Tensor:
+    """models/models.py:159-286 with interp_mode='BI': scipy LinearNDInterpolator over the 3-D (class,row,col) voxels of
+    getPixelsForInterp_NB (:248-250, :259-272); queries outside the convex hull stay NaN (its fill_value)."""
+    import scipy.interpolate
+    if copy:
+        t = t.clone()
+    mask, invalid = pixels_for_interp_nb(t)
+    points = np.argwhere(mask)                                                 # :259
+    values = t[torch.from_numpy(mask)].cpu().numpy()                           # :261
+    interp = scipy.interpolate.LinearNDInterpolator(points, values)            # :248-250, :269
+    t[torch.from_numpy(invalid)] = torch.tensor(interp(np.argwhere(invalid))).float()   # :272
+    return t
+
+
 def inverse_path(pred: torch.Tensor, grid: torch.Tensor, segSize, zero_residual: bool = True,
                  tie: str = "max", interp_mode: str = "tri") -> torch.Tensor:
     """A7 -> A8 -> A9 per sample (models/models.py:933-940; models_instance.py:883-893, 940)."""
     gi = grid_inverse(grid, segSize, tie=tie)
     ps = inverse_sample(pred, gi)
+    fill = {"nearest": fill_missing_values_nearest, "BI": fill_missing_values_bi, "tri": fill_missing_values_tensor}
     for n in range(ps.shape[0]):
-        ps[n] = fill_missing_values_nearest(ps[n]) if interp_mode == "nearest" else fill_missing_values_tensor(ps[n])
+        ps[n] = fill[interp_mode](ps[n])
     if zero_residual:
         ps[torch.isnan(ps)] = 0                                                # models_instance.py:940
     return ps

@@ -162,7 +162,9 @@ def test_device_triangulation_scores_agree_with_host_qhull(ops, H, W):
     frac = close.float().mean().item()
     magree = (mh == md).float().mean().item()
     print(f"{H}x{W}: score pixels equal {frac:.4f}, mask agreement {magree:.4f}")
-    assert frac > 0.5 and magree > 0.8
+    # measured: 0.90-0.95 of the pixels carry identical scores, 0.99 identical masks; which pixels may differ at all is
+    # pinned exactly in tests/test_device_mesh_parity_gpu.py (only inside co-circular cells of Qhull's mesh)
+    assert frac > 0.85 and magree > 0.985
     # both are exact on the sites themselves
     win = plan_d.winner.long()
     b, ys, xs_ = torch.where(win >= 0)

@@ -139,3 +139,33 @@ def test_inverse_mask_c1_equals_general_path(ops, mode, H, W):
     assert exempt.float().mean().item() < 0.02
     assert set(got.unique().tolist()) <= {0, K - 1} | set(torch.argmax(cls_pred[:, :K - 1], 1).tolist())
     assert (got[2] != 7).all()                                        # first maximum among tied constants (3, not 7)
+
+
+@pytest.mark.parametrize("H,W", [(256, 256), (520, 392)])
+def test_inverse_mask_c1_matches_oracle(ops, H, W):
+    """The C1 fast path against the ORACLE (not against this repository's own general path): the reference's decoder tail
+    (models/model_utils.py:298-309) materialised on the CPU, pushed through the oracle's inverse path
+    (models/models.py:933-940, interp2d.py:37-91) and arg-maxed (models/models.py:1044).  Host (Qhull) mesh = the
+    reference's mesh; exempt are only near-ties of the oracle's two best scores and the reference's own path-dependent
+    edge pixels (test_parity_gpu._edge_exempt)."""
+    from test_parity_gpu import _edge_exempt
+    B, K = 2, 51
+    gen = torch.Generator().manual_seed(H + 1)
+    xs, _ = rp.synthetic_saliency(B, seed=H + 1)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    cls_pred = torch.randn(B, K, generator=gen)
+    x = torch.sigmoid(3 * torch.randn(B, 1, 80, 80, generator=gen)) - 0.5
+    pred = cls_pred[:, :, None, None].expand(B, K, 80, 80).clone()            # model_utils.py:300-309 on the CPU
+    pred[:, -1:] = cls_pred[:, -1:, None, None] * x
+    want_scores = rp.inverse_path(pred, grid, (H, W))
+    want = rp.instance_mask(want_scores)
+    plan = ops.build_inverse_plan(grid.cuda(), (H, W), nchan=K, triangulation="host")
+    got = ops.inverse_mask_c1(plan, cls_pred.cuda(), x.cuda()).cpu()
+    scores, _ = ops.inverse_fill(plan, pred.cuda(), want_scores=True)
+    exempt = _edge_exempt(scores.cpu(), want_scores, plan)
+    top2 = want_scores.topk(2, dim=1).values
+    near_tie = (top2[:, 0] - top2[:, 1]).abs() <= 1e-6 * want_scores.abs().amax(dim=1).clamp_min(1e-30)
+    differs = (got != want) & ~exempt & ~near_tie
+    assert int(differs.sum()) == 0, f"{int(differs.sum())} pixels differ from the oracle away from ties"
+    assert near_tie.float().mean().item() < 0.02
