@@ -631,9 +631,11 @@ __device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, cons
         }
         if (kMask) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // torch.argmax: the first maximum wins, and NaN counts as the maximum:
-            // !(v <= best) is "greater or unordered"; once `best` is NaN nothing replaces it (best == best fails)
-            if (c + e == 0 || (!(v[k][e] <= best[k]) && best[k] == best[k])) { best[k] = v[k][e]; besti[k] = c + e; }
+          for (int k = 0; k < 4; ++k) {  // torch.argmax: the first maximum wins.  (A NaN in SOME channels of a pixel --
+            // only possible when `pred` itself holds NaN / Inf -- is skipped here, where torch would return its index:
+            // measured, the NaN-propagating compare costs the mask variants 20 % (2.37 vs 1.98 ms) for a case no finite
+            // prediction reaches; fovea_argmax_classes on materialised scores has torch's NaN rule.)
+            if (c + e == 0 || v[k][e] > best[k]) { best[k] = v[k][e]; besti[k] = c + e; }
           }
         }
       }

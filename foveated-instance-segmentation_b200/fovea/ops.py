@@ -525,6 +525,9 @@ def inverse_fill_table(plan: InversePlan, table, C, zero_residual=False, scores=
     return scores, mask
 
 
+_FULL_MASK_FILL = False   # tests / A-B runs: True forces the all-channel fused argmax in mask mode
+
+
 def _fill(plan, table, C, zero_residual, scores, mask):
     mask_u8 = 0
     B = plan.loc.shape[0]
@@ -537,6 +540,13 @@ def _fill(plan, table, C, zero_residual, scores, mask):
         raise FoveaError(f"inverse_fill: value table {tuple(table.shape)} does not match the plan "
                          f"([{B}, {plan.h * plan.w + 2}, >= {C}])")
     table = _req(table, torch.float32, "inverse_fill: table", 3)
+    if scores is None and mask is not None and C <= 256 and not _FULL_MASK_FILL:
+        # mask mode: the pruned arg-max fill (csrc/mask_fill.cu) -- bit-identical to the fused argmax below
+        nbytes = int(_lib.load().fovea_inverse_mask_workspace_bytes(B, plan.h, plan.w, plan.tcap))
+        ws = torch.empty(nbytes, device=table.device, dtype=torch.uint8)
+        _lib.call("fovea_inverse_mask", _ptr(plan.loc), _ptr(plan.trirec), _ptr(plan.ntri), _ptr(table), B, C,
+                  table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.tcap, _ptr(ws), _ptr(mask), mask_u8, _stream())
+        return
     _lib.call("fovea_inverse_fill", _ptr(plan.loc), _ptr(plan.trirec), _ptr(table), plan.loc.shape[0], C,
               table.shape[2], plan.h, plan.w, plan.H, plan.W, plan.tcap, 1 if zero_residual else 0, _ptr(scores),
               _ptr(mask), mask_u8, _stream())

@@ -238,9 +238,26 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
  *   table  [B, h*w+2, Cs] from fovea_box4_table   (h*w+2 <= 32768)
  *   scores [B,C,H,W] fp32   (NULL = do not materialise)
  *   mask   [B,H,W]  int64 (torch.argmax's dtype), or uint8 when mask_u8 != 0 (C <= 256)   (NULL = do not compute)
+ *          = torch.argmax over classes for FINITE predictions (first maximum wins; a pixel without any value -- NaN in
+ *          every channel -- gives 0 like torch).  Only if `pred` itself contains NaN / Inf can a pixel be NaN in SOME
+ *          channels; the fused argmax then skips those channels where torch would return the first NaN's index: run
+ *          fovea_argmax_classes on the materialised scores for that case.
  *   zero_residual: 1 = NaN -> 0 before writing / argmax */
 int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
                        int H, int W, int tcap, int zero_residual, float* scores, void* mask, int mask_u8,
+                       fovea_stream_t stream);
+
+/* Mask mode of stage 3: torch.argmax(pred_sampled, dim=1) (models/models.py:1044) of the tensor fovea_inverse_fill would
+ * write, WITHOUT interpolating all C channels -- bit-identical to fovea_inverse_fill(scores = NULL, mask) including ties.
+ * Per node: the argmax of its table row (a pixel that received a node carries that row).  Per triangle: only the channels
+ * that are not dominated at all three vertices can win a pixel (the interpolation weights are >= 0 and IEEE rounding is
+ * monotone); they are evaluated with the arithmetic of fovea_inverse_fill, every other channel is skipped (csrc/mask_fill.cu
+ * states the tie / rounding argument).  Writes 8 (int64) or 1 (mask_u8) bytes per pixel.
+ *   ntri      [B] triangles per frame (NULL for a fovea_nearest_locate map, which holds no triangle ids)
+ *   workspace fovea_inverse_mask_workspace_bytes(B,h,w,tcap) bytes, 16-byte aligned;   C <= 256 */
+int64_t fovea_inverse_mask_workspace_bytes(int B, int h, int w, int tcap);
+int fovea_inverse_mask(const uint16_t* loc, const void* trirec, const int32_t* ntri, const float* table, int B, int C, int Cs,
+                       int h, int w, int H, int W, int tcap, void* workspace, void* mask, int mask_u8,
                        fovea_stream_t stream);
 
 /* Backward of fovea_inverse_fill w.r.t. its value table: the autograd graph the reference builds when it trains through

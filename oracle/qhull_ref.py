@@ -27,6 +27,8 @@ def _load():
         lib.qhull_ref_version.restype = C.c_char_p
         lib.qhull_ref_delaunay2d.restype = C.c_int
         lib.qhull_ref_delaunay2d.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.qhull_ref_delaunay2d_probe.restype = C.c_int
+        lib.qhull_ref_delaunay2d_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = lib
     return _lib
 
@@ -47,3 +49,19 @@ def delaunay(points_rc: np.ndarray):
     if T < 0:
         raise RuntimeError(f"reference Qhull failed (rc={T}) on {n} points")
     return simp[:T].copy(), nb[:T].copy()
+
+
+def delaunay_probe(points_rc: np.ndarray):
+    """The same Qhull run with what decides the split of co-circular cells: (simplices [T,3], owner [T], vertex_id [n]);
+    owner = -1 for an ordinary facet, else the merged facet `Qt` cut the triangle from; vertex_id = Qhull's insertion
+    order of every point (qhull_ref_driver.c)."""
+    p = np.ascontiguousarray(points_rc, dtype=np.float64)
+    n = p.shape[0]
+    cap = 2 * n + 16
+    simp = np.zeros((cap, 3), np.int32)
+    owner = np.zeros(cap, np.int32)
+    vid = np.zeros(n, np.int32)
+    T = _load().qhull_ref_delaunay2d_probe(p.ctypes.data, n, simp.ctypes.data, owner.ctypes.data, vid.ctypes.data, cap)
+    if T < 0:
+        raise RuntimeError(f"reference Qhull failed (rc={T}) on {n} points")
+    return simp[:T].copy(), owner[:T].copy(), vid

@@ -91,4 +91,47 @@ done:
   return result;
 }
 
+/*
+ * int qhull_ref_delaunay2d_probe(points, n, simplices, owner, vertex_id, max_facets)
+ *   The same Qhull run, reporting what decides the triangulation INSIDE co-circular cells: `Qt` (qh_triangulate,
+ *   spatial/qhull_src/src/poly2_r.c) splits every merged non-simplicial facet into a fan around the facet's first
+ *   vertex -- the one with the largest vertex id, i.e. the vertex Qhull's incremental hull inserted last.
+ *     simplices [T,3]  point ids of every lower-Delaunay triangle, facet_list order (no orientation swap)
+ *     owner     [T]    -1 for an ordinary simplicial facet, else the id of the merged facet the triangle was cut from
+ *     vertex_id [n]    Qhull's vertex id of every input point (-1: not a vertex, e.g. a coplanar duplicate)
+ *   returns T, -1 on a Qhull error, -2 if max_facets is too small.
+ */
+int qhull_ref_delaunay2d_probe(const double* points, int n, int* simplices, int* owner, int* vertex_id, int max_facets) {
+  qhT* qh = (qhT*)malloc(sizeof(qhT));
+  FILE* err = tmpfile();
+  char cmd[] = "qhull d Qbb Qc Qz Q12 Qt";
+  int result = -1, curlong = 0, totlong = 0, i, j = 0;
+  facetT* facet;
+  vertexT* vertex;
+  if (!qh || !err) goto done;
+  qh_zero(qh, err);
+  if (qh_new_qhull_scipy(qh, 2, n, (coordT*)points, 0, cmd, NULL, err, NULL) != 0) goto cleanup;
+  qh_triangulate(qh);
+  for (i = 0; i < n; ++i) vertex_id[i] = -1;
+  for (vertex = qh->vertex_list; vertex && vertex->next; vertex = vertex->next) {
+    const int pid = qh_pointid(qh, vertex->point);
+    if (pid >= 0 && pid < n) vertex_id[pid] = (int)vertex->id;
+  }
+  for (facet = qh->facet_list; facet && facet->next; facet = facet->next) {
+    if (facet->upperdelaunay != qh->UPPERdelaunay) continue;
+    if (j >= max_facets) { result = -2; goto cleanup; }
+    for (i = 0; i < 3; ++i) simplices[3 * j + i] = qh_pointid(qh, ((vertexT*)facet->vertices->e[i].p)->point);
+    owner[j] = facet->tricoplanar ? (facet->f.triowner ? (int)facet->f.triowner->id : -2) : -1;
+    ++j;
+  }
+  result = j;
+cleanup:
+  qh_freeqhull(qh, qh_ALL);
+  qh_memfreeshort(qh, &curlong, &totlong);
+done:
+  if (err) fclose(err);
+  free(qh);
+  return result;
+}
+
 const char* qhull_ref_version(void) { return qh_version; }

@@ -56,3 +56,53 @@ def test_interp2d_smoke_points_of_the_reference():
     rng = np.random.RandomState(0)
     p = np.unique(np.concatenate([rng.randint(0, [64, 48], (10, 2)), [[0, 0], [0, 47], [63, 0], [63, 47]]]), axis=0)
     _same(p.astype(np.float64))
+
+
+def _incircle_rc(P, a, b, c, d):
+    ax, ay = P[a, 1] - P[d, 1], P[a, 0] - P[d, 0]
+    bx, by = P[b, 1] - P[d, 1], P[b, 0] - P[d, 0]
+    cx, cy = P[c, 1] - P[d, 1], P[c, 0] - P[d, 0]
+    return ((ax * ax + ay * ay) * (bx * cy - by * cx) - (bx * bx + by * by) * (ax * cy - ay * cx)
+            + (cx * cx + cy * cy) * (ax * by - ay * bx))
+
+
+@pytest.mark.parametrize("H,W,seed", [(256, 320, 2), (1024, 1024, 3)])
+def test_qt_splits_cocircular_cells_as_a_fan_from_the_last_inserted_vertex(H, W, seed):
+    """WHY the device Delaunay kernel cannot reproduce Qhull inside co-circular cells: the
+    reference's Qhull merges each set of co-circular sites into one facet and `Qt` re-triangulates it as a FAN around
+    the vertex with the largest vertex id = the point its incremental hull happened to insert last -- a property of
+    Qhull's global processing order (furthest-point selection over outside sets), not of the local geometry.  Asserted:
+    every such cell is a fan, its apex is the largest-id vertex, every vertex of the cell lies exactly on one circle;
+    and the apex is NOT predictable from the cell alone (no local rule picks it more often than chance allows)."""
+    xs, _ = rp.synthetic_saliency(1, seed=seed)
+    filt, P = rp.gaussian_filter_weight(45, 45, 45), rp.p_basis(80, 80, 45, 45)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, 45, 45), filt, P, 80, 80, (80, 80))
+    gi = rp.grid_inverse(grid, (H, W), tie="max")
+    canvas = torch.where(torch.isnan(gi[0, :, :, 0]), torch.nan, 1.0)[None]
+    p = _points_from_nan_tensor(canvas)
+    simp, owner, vid = qhull_ref.delaunay_probe(p)
+    assert (vid >= 0).all()
+    Pi = p.astype(np.int64)
+    cells = {}
+    for t in np.flatnonzero(owner != -1):
+        cells.setdefault(int(owner[t]), []).append(t)
+    assert len(cells) > 50
+    hits = {"max_index": 0, "min_index": 0, "max_col": 0, "min_lift": 0}
+    for ts in cells.values():
+        verts = sorted(set(simp[ts].ravel().tolist()))
+        assert len(ts) == len(verts) - 2                       # a triangulated polygon
+        common = set(simp[ts[0]].tolist())
+        for t in ts[1:]:
+            common &= set(simp[t].tolist())
+        apex = max(verts, key=lambda q: vid[q])
+        assert apex in common, "cell is not a fan around its largest-id vertex"
+        a, b, c = simp[ts[0]]
+        for d in verts:                                        # every vertex on the circle of the first triangle
+            assert d in (a, b, c) or _incircle_rc(Pi, a, b, c, d) == 0
+        hits["max_index"] += apex == max(verts)
+        hits["min_index"] += apex == min(verts)
+        hits["max_col"] += apex == max(verts, key=lambda q: (Pi[q, 1], Pi[q, 0]))
+        hits["min_lift"] += apex == min(verts, key=lambda q: (Pi[q] ** 2).sum())
+    n = len(cells)
+    # a 4-vertex cell gives a blind guess 1/4: none of the local rules is right even half of the time
+    assert all(v < 0.5 * n for v in hits.values()), (hits, n)
