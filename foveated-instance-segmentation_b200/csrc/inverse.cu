@@ -577,7 +577,11 @@ __device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, cons
       const double c1 = static_cast<double>(e1) * inv_area;
       a0 = static_cast<float>(c0);
       a1 = static_cast<float>(c1);
-      a2 = static_cast<float>(1.0 - c0 - c1);
+      // (1 - c0 - c1 is exactly what the reference computes; when the pixel lies ON the edge opposite vertex 2 its true
+      //  value is 0 and the double expression is rounding noise of either sign, ~1e-16 -- the reference's own noise comes
+      //  from a different formula (an LU-inverted transform).  Clamped at zero so that every weight is >= 0, the property
+      //  the pruned arg-max fill (mask_fill.cu) relies on; the scores move by <= 1e-16 * |value| at those pixels.)
+      a2 = fmaxf(static_cast<float>(1.0 - c0 - c1), 0.f);
       n0 = sn0; n1 = sn1; n2 = sn2;
     }
     e0 += d0;  // advance to column x0 + k + 1 (harmless while no triangle is held: d == 0)

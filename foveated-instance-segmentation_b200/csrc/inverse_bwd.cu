@@ -65,7 +65,7 @@ inverse_fill_bwd_kernel(const uint16_t* __restrict__ loc, const TriRec* __restri
         const double c0 = static_cast<double>(e0) * inv_area, c1 = static_cast<double>(e1) * inv_area;
         a0 = static_cast<float>(c0);
         a1 = static_cast<float>(c1);
-        a2 = static_cast<float>(1.0 - c0 - c1);
+        a2 = fmaxf(static_cast<float>(1.0 - c0 - c1), 0.f);
         n0 = sn0; n1 = sn1; n2 = sn2;
       }
       e0 += d0;

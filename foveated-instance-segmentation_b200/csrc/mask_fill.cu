@@ -18,8 +18,11 @@
 //     greater at all three vertices by a margin (2^-20 of the larger magnitude) that exceeds the worst-case rounding of
 //     both evaluations (3 roundings of relative 2^-24 each, weights summing to 1 +- 2^-23), so it is STRICTLY greater
 //     at every pixel;
-//   - the third weight float(1 - c0 - c1) can round to a tiny negative number on an edge; monotonicity then fails in
-//     principle, so such a pixel (and any triangle whose survivors overflow the record) evaluates all C channels;
+//   - all three weights are >= 0: w0, w1 are quotients of non-negative integers; the third, float(1 - c0 - c1), is pure
+//     rounding noise (|.| ~ 1e-16) when the pixel lies exactly on the edge opposite vertex 2 and is clamped at zero by
+//     every stage-3 kernel (fill_tile) -- the reference's own value there is noise of its own LU-based formula;
+//   - a triangle whose survivors overflow the 16-slot record evaluates all C channels (0.3 % of the triangles on
+//     i.i.d. N(0,1) predictions);
 //   - survivors are kept in increasing channel order and compared with `>`, like the full loop.
 #include <math_constants.h>
 
@@ -28,8 +31,11 @@
 
 namespace fovea {
 
-constexpr int kCandMax = 16;          // survivors kept per triangle (one 256-byte record); more -> full evaluation
+constexpr int kCandMax = 32;          // survivors kept per triangle (one 512-byte record, only the used slots are ever
+                                      // touched); more -> full evaluation.  (16 slots overflow for ~10 % of the huge hull
+                                      // triangles, whose three nodes are far apart -- and those cover a fifth of a canvas.)
 constexpr int kCandThreads = 128;
+constexpr int kCandSmem = 16;         // survivor slots held in shared memory; the rare slots beyond live in the global record
 constexpr unsigned kCandFull = 0xFFu;  // ncand marker: evaluate every channel
 constexpr unsigned kCandNaN = 0xFEu;   // ncand marker: a vertex has no value -> NaN in every channel -> label 0
 
@@ -49,16 +55,30 @@ node_argmax_kernel(const float* __restrict__ table, uint8_t* __restrict__ nodear
   nodearg[static_cast<size_t>(b) * rows + r] = static_cast<uint8_t>(best == best ? bi : 0);
 }
 
-// One thread per triangle.  The survivor list lives in shared memory, [slot][field][thread] (conflict-free).
+// One thread per triangle.  Channels are offered in index order, so every survivor has a LOWER index than the newcomer:
+//   the newcomer is dropped if some survivor is >= at the three vertices (that survivor wins every tie as well);
+//   a survivor is dropped if the newcomer exceeds it at the three vertices by more than M = 2^-20 * (largest magnitude
+//   among the triangle's vertex values): more than the rounding of both evaluations, i.e. strictly greater at every pixel.
+// The survivor list lives in shared memory, [slot][field][thread] (conflict-free), and stays in index order.
+// Before a channel meets the list it is compared with the three channels that are the argmax at the triangle's vertices
+// (node_argmax_kernel): registers only, no loop -- most channels end there.  (Being beaten by a real channel is reason
+// enough to drop one, whatever becomes of that channel later: the relation is transitive.)
 __global__ void __launch_bounds__(kCandThreads)
 triangle_candidates_kernel(const TriRec* __restrict__ trirec, const int32_t* __restrict__ ntri,
-                           const float* __restrict__ table, float4* __restrict__ cand, uint8_t* __restrict__ ncand,
-                           int hw, int C, int Cs, int tcap) {
-  __shared__ float sv[kCandMax][4][kCandThreads];
+                           const float* __restrict__ table, const uint8_t* __restrict__ nodearg,
+                           float4* cand, uint8_t* __restrict__ ncand, int hw, int C, int Cs, int tcap) {
+  __shared__ float sv[kCandSmem][4][kCandThreads];
   const int b = blockIdx.y;
   const int t = blockIdx.x * kCandThreads + threadIdx.x;
   if (t >= ntri[b]) return;
   const int tid = threadIdx.x;
+  float4* out = cand + (static_cast<size_t>(b) * tcap + t) * kCandMax;   // (also the spill space of slots >= kCandSmem)
+#define SV_LD(k, f) ((k) < kCandSmem ? sv[(k)][(f)][tid] : reinterpret_cast<const float*>(out + (k))[(f)])
+#define SV_ST(k, f, v)                                                                  \
+  do {                                                                                  \
+    if ((k) < kCandSmem) sv[(k)][(f)][tid] = (v);                                       \
+    else reinterpret_cast<float*>(out + (k))[(f)] = (v);                                \
+  } while (0)
   const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(trirec + static_cast<size_t>(b) * tcap + t) + 3);
   const int r0 = static_cast<int>(q3.x & 0xFFFFu), r1 = static_cast<int>(q3.x >> 16), r2 = static_cast<int>(q3.y);
   uint8_t* nc = ncand + static_cast<size_t>(b) * tcap + t;
@@ -67,46 +87,90 @@ triangle_candidates_kernel(const TriRec* __restrict__ trirec, const int32_t* __r
   const float4* p0 = reinterpret_cast<const float4*>(tb + static_cast<size_t>(r0) * Cs);
   const float4* p1 = reinterpret_cast<const float4*>(tb + static_cast<size_t>(r1) * Cs);
   const float4* p2 = reinterpret_cast<const float4*>(tb + static_cast<size_t>(r2) * Cs);
-  int n = 0;
-  bool overflow = false;
-  for (int c4 = 0; c4 < C && !overflow; c4 += 4) {
+  // pass 1: the margin (padding channels of the table are zero: they do not raise it)
+  float mag = 0.f;
+  for (int c4 = 0; c4 < C; c4 += 4) {
+    const float4 A = __ldg(p0 + (c4 >> 2)), Bv = __ldg(p1 + (c4 >> 2)), Cv = __ldg(p2 + (c4 >> 2));
+    mag = fmaxf(mag, fmaxf(fmaxf(fmaxf(fabsf(A.x), fabsf(A.y)), fmaxf(fabsf(A.z), fabsf(A.w))),
+                           fmaxf(fmaxf(fmaxf(fabsf(Bv.x), fabsf(Bv.y)), fmaxf(fabsf(Bv.z), fabsf(Bv.w))),
+                                 fmaxf(fmaxf(fabsf(Cv.x), fabsf(Cv.y)), fmaxf(fabsf(Cv.z), fabsf(Cv.w))))));
+  }
+  const float M = 9.5367431640625e-07f * mag;  // 2^-20 * mag   (NaN / Inf magnitudes: no comparison below succeeds)
+  // the three vertex-argmax channels: index, values at the three vertices, values lowered by the margin
+  const uint8_t* na = nodearg + static_cast<size_t>(b) * (hw + 2);
+  const float* f0 = reinterpret_cast<const float*>(p0);
+  const float* f1 = reinterpret_cast<const float*>(p1);
+  const float* f2 = reinterpret_cast<const float*>(p2);
+  int si[3] = {na[r0], na[r1], na[r2]};
+  float sa[3], sb[3], sc[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { sa[q] = __ldg(f0 + si[q]); sb[q] = __ldg(f1 + si[q]); sc[q] = __ldg(f2 + si[q]); }
+  // pass 2 (uniform control flow: every lane walks the same 51 channels): which channels survive the three seeds?
+  unsigned long long alive = 0;
+  for (int c4 = 0; c4 < C; c4 += 4) {
     const float4 A = __ldg(p0 + (c4 >> 2)), Bv = __ldg(p1 + (c4 >> 2)), Cv = __ldg(p2 + (c4 >> 2));
     const float a4[4] = {A.x, A.y, A.z, A.w}, b4[4] = {Bv.x, Bv.y, Bv.z, Bv.w}, c4v[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (c4 + e >= C || overflow) continue;
+      const int c = c4 + e;
       const float a = a4[e], bb = b4[e], cc = c4v[e];
-      const float mag = fmaxf(fmaxf(fabsf(a), fabsf(bb)), fabsf(cc));
-      bool dominated = false;
-      for (int k = 0; k < n && !dominated; ++k)      // a lower index that is never smaller wins every tie anyway
-        dominated = sv[k][0][tid] >= a && sv[k][1][tid] >= bb && sv[k][2][tid] >= cc;
-      if (dominated) continue;
-      int keep = 0;
-      for (int k = 0; k < n; ++k) {                  // survivors the newcomer (a higher index) beats STRICTLY everywhere
-        const float ka = sv[k][0][tid], kb = sv[k][1][tid], kc = sv[k][2][tid];
-        const float m = 9.5367431640625e-07f * fmaxf(mag, fmaxf(fmaxf(fabsf(ka), fabsf(kb)), fabsf(kc)));
-        if ((a - ka > m) && (bb - kb > m) && (cc - kc > m)) continue;
-        if (keep != k) {
-          sv[keep][0][tid] = ka; sv[keep][1][tid] = kb; sv[keep][2][tid] = kc; sv[keep][3][tid] = sv[k][3][tid];
-        }
-        ++keep;
+      bool beaten = c >= C;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        // (bitwise & | on purpose: short-circuit operators compile to branches, and the lanes of a warp -- 32 different
+        //  triangles -- would take them apart: measured 9 active lanes per instruction)
+        const bool lower = si[q] < c, higher = si[q] > c;
+        beaten = beaten | (lower & (sa[q] >= a) & (sb[q] >= bb) & (sc[q] >= cc)) |
+                 (higher & (sa[q] - M > a) & (sb[q] - M > bb) & (sc[q] - M > cc));
       }
-      n = keep;
-      if (n == kCandMax) { overflow = true; continue; }
-      sv[n][0][tid] = a; sv[n][1][tid] = bb; sv[n][2][tid] = cc; sv[n][3][tid] = __int_as_float(c4 + e);
-      ++n;
+      if (!beaten) alive |= 1ull << (c & 63);
     }
   }
+  // pass 3: exact pruning among the channels left (in index order: every lane takes its next one in the same iteration)
+  int n = 0;
+  bool overflow = false;
+  const bool wide = C > 64;   // more than 64 channels: the bit mask cannot hold them, offer every channel
+  for (int c = wide ? 0 : (alive ? __ffsll(static_cast<long long>(alive)) - 1 : C); c < C && !overflow;
+       c = wide ? c + 1 : ((alive &= alive - 1) ? __ffsll(static_cast<long long>(alive)) - 1 : C)) {
+    const float a = __ldg(f0 + c), bb = __ldg(f1 + c), cc = __ldg(f2 + c);
+    const float am = a - M, bm = bb - M, cm = cc - M;
+    bool dominated = false;
+    int keep = 0;
+    for (int k = 0; k < n; ++k) {
+      const float ka = SV_LD(k, 0), kb = SV_LD(k, 1), kc = SV_LD(k, 2);
+      dominated = dominated | ((ka >= a) & (kb >= bb) & (kc >= cc));
+      if ((am > ka) & (bm > kb) & (cm > kc)) continue;       // the newcomer beats survivor k strictly everywhere
+      if (keep != k) {
+        const float ki = SV_LD(k, 3);
+        SV_ST(keep, 0, ka); SV_ST(keep, 1, kb); SV_ST(keep, 2, kc); SV_ST(keep, 3, ki);
+      }
+      ++keep;
+    }
+    // (a dominated newcomer removes nothing: whatever it exceeds by M its dominator exceeds by M too -- one margin per
+    //  triangle, monotone rounding -- and that survivor either removed it when it entered the list, or, if it entered
+    //  earlier, would have kept it out; entries the newcomer did remove lose to it at every pixel in any case)
+    n = keep;
+    if (dominated) continue;
+    if (n == kCandMax) { overflow = true; continue; }
+    SV_ST(n, 0, a); SV_ST(n, 1, bb); SV_ST(n, 2, cc); SV_ST(n, 3, __int_as_float(c));
+    ++n;
+  }
   if (overflow) { *nc = static_cast<uint8_t>(kCandFull); return; }
-  float4* out = cand + (static_cast<size_t>(b) * tcap + t) * kCandMax;
-  for (int k = 0; k < n; ++k) out[k] = make_float4(sv[k][0][tid], sv[k][1][tid], sv[k][2][tid], sv[k][3][tid]);
+  for (int k = 0; k < n && k < kCandSmem; ++k) out[k] = make_float4(sv[k][0][tid], sv[k][1][tid], sv[k][2][tid], sv[k][3][tid]);
   *nc = static_cast<uint8_t>(n);
+#undef SV_LD
+#undef SV_ST
 }
 
 constexpr int kMaskThreads = 256;
 constexpr int kMaskWL = 16;  // the fill's mapping: a warp covers 64 px x 2 rows, a thread 4 consecutive pixels
 
-__global__ void __launch_bounds__(kMaskThreads)
+__device__ __forceinline__ float interp3(float a, float b, float c, float w0, float w1, float w2) {
+  // interp2d.py:85-89 as fill_tile evaluates it: three products, summed in vertex order, every step rounded
+  return __fadd_rn(__fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1)), __fmul_rn(c, w2));
+}
+
+__global__ void __launch_bounds__(kMaskThreads, 3)
 inverse_mask_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__ trirec, const float* __restrict__ table,
                     const float4* __restrict__ cand, const uint8_t* __restrict__ ncand,
                     const uint8_t* __restrict__ nodearg, void* __restrict__ mask, FillParams p) {
@@ -121,17 +185,17 @@ inverse_mask_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__
   const unsigned pixoff = static_cast<unsigned>(y) * p.W + x0;
   const TriRec* recs = trirec + static_cast<size_t>(b) * p.tcap;
   const uint8_t* na = nodearg + static_cast<size_t>(b) * (hw + 2);
-  const float* tb = table + static_cast<size_t>(b) * (hw + 2) * p.Cs;
 
+  // ---- phase 1: what produces each of my four pixels (the arithmetic of fill_tile, inverse.cu)
   const uint2 l2 = __ldcs(reinterpret_cast<const uint2*>(loc + static_cast<size_t>(b) * plane + pixoff));
   const int lc[4] = {decode_loc(l2.x & 0xFFFFu), decode_loc(l2.x >> 16), decode_loc(l2.y & 0xFFFFu), decode_loc(l2.y >> 16)};
-  int label[4];
-  int cur = -1, e0 = 0, e1 = 0, d0 = 0, d1 = 0, sn0 = hw, sn1 = hw, sn2 = hw;
-  unsigned n = 0;
+  int label[4] = {0, 0, 0, 0};
+  float w0[4], w1[4], w2[4];
+  int cur = -1, e0 = 0, e1 = 0, d0 = 0, d1 = 0;
   double inv_area = 0.0;
-  const float4* cl = nullptr;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    w0[k] = w1[k] = w2[k] = 0.f;
     if (lc[k] < 0) {                       // the pixel received a node: the label of that node's row
       label[k] = na[-(lc[k] + 1)];
     } else {
@@ -143,39 +207,62 @@ inverse_mask_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__
         d1 = static_cast<int>(q1.x);
         e0 = static_cast<int>(q0.x) * y + d0 * (x0 + k) + static_cast<int>(q0.z);
         e1 = static_cast<int>(q0.w) * y + d1 * (x0 + k) + static_cast<int>(q1.y);
-        sn0 = static_cast<int>(q3.x & 0xFFFFu); sn1 = static_cast<int>(q3.x >> 16); sn2 = static_cast<int>(q3.y);
         inv_area = __hiloint2double(static_cast<int>(q3.w), static_cast<int>(q3.z));
-        n = ncand[static_cast<size_t>(b) * p.tcap + cur];
-        cl = cand + (static_cast<size_t>(b) * p.tcap + cur) * kCandMax;
       }
       // interp2d.py:58-65 / qhull.pyx:1210-1264: c0, c1 in float64, c2 = 1 - c0 - c1, then cast to float32
       const double c0 = static_cast<double>(e0) * inv_area, c1 = static_cast<double>(e1) * inv_area;
-      const float w0 = static_cast<float>(c0), w1 = static_cast<float>(c1), w2 = static_cast<float>(1.0 - c0 - c1);
-      int bi = 0;
-      if (n == kCandNaN) {
-        bi = 0;                              // NaN (or zeroed) in every channel: torch.argmax gives 0
-      } else if (n == kCandFull || w2 < 0.f || w0 < 0.f || w1 < 0.f) {
-        float best = 0.f;                    // every channel, the arithmetic of fill_tile (inverse.cu)
-        const float* ra = tb + static_cast<size_t>(sn0) * p.Cs;
-        const float* rb = tb + static_cast<size_t>(sn1) * p.Cs;
-        const float* rc = tb + static_cast<size_t>(sn2) * p.Cs;
-        for (int c = 0; c < p.C; ++c) {
-          const float v = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(ra + c), w0), __fmul_rn(__ldg(rb + c), w1)),
-                                    __fmul_rn(__ldg(rc + c), w2));
-          if (c == 0 || v > best) { best = v; bi = c; }
-        }
-      } else {
-        float best = 0.f;
-        for (unsigned j = 0; j < n; ++j) {
-          const float4 s = __ldg(cl + j);
-          const float v = __fadd_rn(__fadd_rn(__fmul_rn(s.x, w0), __fmul_rn(s.y, w1)), __fmul_rn(s.z, w2));
-          if (j == 0 || v > best) { best = v; bi = __float_as_int(s.w); }
-        }
-      }
-      label[k] = bi;
+      w0[k] = static_cast<float>(c0); w1[k] = static_cast<float>(c1);
+      w2[k] = fmaxf(static_cast<float>(1.0 - c0 - c1), 0.f);   // (see fill_tile: rounding noise below zero is clamped)
     }
     e0 += d0;
     e1 += d1;
+  }
+
+  // ---- phase 2: every pixel walks the surviving channels of ITS triangle in one loop that all lanes share (a pixel in
+  // the same triangle as its left neighbour reuses the neighbour's record instead of loading it again)
+  unsigned nk[4], raw[4];
+  const float4* cl[4];
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned nmax = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    nk[k] = 0;
+    raw[k] = 0;
+    cl[k] = cand;
+    if (lc[k] < 0) continue;
+    raw[k] = (k > 0 && lc[k] == lc[k - 1]) ? raw[k - 1] : ncand[static_cast<size_t>(b) * p.tcap + lc[k]];
+    cl[k] = cand + (static_cast<size_t>(b) * p.tcap + lc[k]) * kCandMax;
+    if (raw[k] == kCandNaN) continue;      // NaN (or zeroed) in every channel: torch.argmax gives 0
+    if (raw[k] == kCandFull) {             // more survivors than a record holds (rare): every channel, from the table
+      const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(recs + lc[k]) + 3);
+      const float* tb = table + static_cast<size_t>(b) * (hw + 2) * p.Cs;
+      const float* ra = tb + static_cast<size_t>(q3.x & 0xFFFFu) * p.Cs;
+      const float* rb = tb + static_cast<size_t>(q3.x >> 16) * p.Cs;
+      const float* rc = tb + static_cast<size_t>(q3.y) * p.Cs;
+      float bst = 0.f;
+      for (int c = 0; c < p.C; ++c) {
+        const float v = interp3(__ldg(ra + c), __ldg(rb + c), __ldg(rc + c), w0[k], w1[k], w2[k]);
+        if (c == 0 || v > bst) { bst = v; label[k] = c; }
+      }
+      continue;
+    }
+    nk[k] = raw[k];
+    nmax = max(nmax, raw[k]);
+  }
+  bool own[4];   // the pixel loads its triangle's record itself (its left neighbour lies in another triangle)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) own[k] = (k == 0) | (lc[k] != lc[max(k - 1, 0)]);
+  for (unsigned j = 0; j < nmax; ++j) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {          // branch-free: predicated load, selects
+      const bool live = j < nk[k];
+      if (live & own[k]) s = __ldg(cl[k] + j);
+      const float v = interp3(s.x, s.y, s.z, w0[k], w1[k], w2[k]);
+      const bool take = live & ((j == 0) | (v > best[k]));
+      best[k] = take ? v : best[k];
+      label[k] = take ? __float_as_int(s.w) : label[k];
+    }
   }
   if (p.mask_u8) {
     *reinterpret_cast<uchar4*>(static_cast<unsigned char*>(mask) + static_cast<size_t>(b) * plane + pixoff) =
@@ -218,7 +305,7 @@ extern "C" int fovea_inverse_mask(const uint16_t* loc, const void* trirec, const
   node_argmax_kernel<<<dim3(ceil_div(rows, 256), B), 256, 0, s>>>(table, nodearg, rows, C, Cs);
   if (ntri)  // 'nearest' plans carry no triangles: every pixel is a direct row
     triangle_candidates_kernel<<<dim3(ceil_div(tcap, kCandThreads), B), kCandThreads, 0, s>>>(
-        static_cast<const TriRec*>(trirec), ntri, table, cand, ncand, h * w, C, Cs, tcap);
+        static_cast<const TriRec*>(trirec), ntri, table, nodearg, cand, ncand, h * w, C, Cs, tcap);
   FillParams p{C, Cs, h, w, H, W, 0, tcap, 1, mask_u8 ? 1 : 0};
   dim3 grid(ceil_div(W, 4 * kMaskWL * 2), ceil_div(H, (32 / kMaskWL) * (kMaskThreads / 32 / 2)), B);
   inverse_mask_kernel<<<grid, kMaskThreads, 0, s>>>(loc, static_cast<const TriRec*>(trirec), table, cand, ncand, nodearg,

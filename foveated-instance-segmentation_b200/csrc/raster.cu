@@ -1,0 +1,161 @@
+// Point location by RASTERISATION: find_simplex for every pixel of the canvas (interp2d.py:58) computed triangle by
+// triangle instead of pixel by pixel.
+//
+// fovea_locate_pixels walks the mesh from every 32-pixel run of every row: 360 M warp instructions per 64 frames of
+// 1024^2 (0.39 ms, issue-bound; plus the walk-start hints another kernel has to prepare).  Here one warp takes one
+// triangle: lane l owns rows ymin + l, ymin + l + 32, ... of its bounding box, solves the three edge inequalities
+// e_i(y, x) = A_i y + B_i x + C_i >= m_i of the setup record for the row's span [lo, hi] in closed form (exact integer
+// arithmetic, the SAME predicate the walker tests pixel by pixel, so the two kernels produce the same map) and stores
+// the triangle id over the span.  Spans of different triangles are disjoint (the tie rule gives every pixel exactly one
+// owner), so there is nothing to synchronise.  The pixels that received a node are stamped afterwards from the
+// 6 400 nodes themselves (stamp_nodes_kernel) -- the 4-byte-per-pixel winner map is no longer read by stage 3's locate.
+#include "common.cuh"
+#include "fill.cuh"
+
+namespace fovea {
+
+constexpr int kRasThreads = 256;
+constexpr int kRasTileMax = 2048;   // bounding boxes up to this many pixels are swept pixel by pixel
+
+// floor(a / b) for b > 0 and |a / b| < 2^22: float quotient, exact fix-up
+__device__ __forceinline__ int floor_div_pos(int a, int b) {
+  int q = __float2int_rd(__fdividef(static_cast<float>(a), static_cast<float>(b)));
+  const long long r = static_cast<long long>(a) - static_cast<long long>(q) * b;
+  if (r < 0) --q;
+  else if (r >= b) ++q;
+  return q;
+}
+
+__device__ __forceinline__ void store_span(uint16_t* row, int lo, int hi, unsigned id) {
+  int x = lo;
+  const unsigned v2 = id | (id << 16);
+  while (x <= hi && (x & 7)) row[x++] = static_cast<uint16_t>(id);             // up to the next 16-byte boundary
+  for (; x + 7 <= hi; x += 8) *reinterpret_cast<uint4*>(row + x) = make_uint4(v2, v2, v2, v2);
+  while (x <= hi) row[x++] = static_cast<uint16_t>(id);
+}
+
+__global__ void __launch_bounds__(kRasThreads)
+raster_locate_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
+                     const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, int hw, int H, int W, int cap, int tcap) {
+  const int b = blockIdx.y;
+  const int T = ntri[b];
+  uint16_t* lb = loc + static_cast<size_t>(b) * H * W;
+  if (T <= 0) {  // no mesh for this frame (see fovea_delaunay): nothing owns anything
+    const unsigned none = 0x8000u | static_cast<unsigned>(hw);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kRasThreads + threadIdx.x; i < static_cast<size_t>(H) * W;
+         i += static_cast<size_t>(gridDim.x) * kRasThreads)
+      lb[i] = static_cast<uint16_t>(none);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (kRasThreads / 32) + warp;
+  if (t >= T) return;
+  const uint4* r = reinterpret_cast<const uint4*>(trirec + static_cast<size_t>(b) * tcap + t);
+  const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+  if (q2.w == 0u) return;  // degenerate triangle (host meshes only): owns nothing
+  const uint4 mq = __ldg(mesh + static_cast<size_t>(b) * tcap + t);
+  const int32_t* pb = pts + static_cast<size_t>(b) * cap;
+  const int p0 = __ldg(pb + (mq.x & 0xFFFFu)), p1 = __ldg(pb + (mq.x >> 16)), p2 = __ldg(pb + (mq.y & 0xFFFFu));
+  const int ymin = min(min(p0 >> 16, p1 >> 16), p2 >> 16), ymax = max(max(p0 >> 16, p1 >> 16), p2 >> 16);
+  const int xmin = min(min(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF), xmax = max(max(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF);
+  const int A[3] = {static_cast<int>(q0.x), static_cast<int>(q0.w), static_cast<int>(q1.z)};
+  const int Bx[3] = {static_cast<int>(q0.y), static_cast<int>(q1.x), static_cast<int>(q1.w)};
+  const int Cc[3] = {static_cast<int>(q0.z), static_cast<int>(q1.y), static_cast<int>(q2.x)};
+  const unsigned m = q2.z >> 16;
+  // Small bounding boxes (the typical triangle covers ~80 pixels): the warp sweeps the box in 4 x 8-pixel steps, every
+  // lane testing ITS pixel against the three edge functions -- no divisions, ~12 instructions per step.  Large boxes
+  // (the few hull / periphery triangles that cover a tenth of the canvas each) take the row-span path below, where the
+  // three divisions per row are amortised over long 16-byte stores.
+  const int bh = ymax - ymin + 1, bw = xmax - xmin + 1;
+  if (bh * bw <= kRasTileMax) {
+    const int dy = lane >> 3, dx = lane & 7;
+    int e0 = A[0] * (ymin + dy) + Bx[0] * (xmin + dx) + Cc[0] - static_cast<int>(m & 1u);
+    int e1 = A[1] * (ymin + dy) + Bx[1] * (xmin + dx) + Cc[1] - static_cast<int>((m >> 1) & 1u);
+    int e2 = A[2] * (ymin + dy) + Bx[2] * (xmin + dx) + Cc[2] - static_cast<int>((m >> 2) & 1u);
+    for (int y = ymin + dy; y <= ymax; y += 4) {
+      int f0 = e0, f1 = e1, f2 = e2;
+      uint16_t* row = lb + static_cast<size_t>(y) * W;
+      for (int x = xmin + dx; x <= xmax; x += 8) {
+        if ((f0 | f1 | f2) >= 0) row[x] = static_cast<uint16_t>(t);    // all three >= 0  <=>  no sign bit set
+        f0 += 8 * Bx[0]; f1 += 8 * Bx[1]; f2 += 8 * Bx[2];
+      }
+      e0 += 4 * A[0]; e1 += 4 * A[1]; e2 += 4 * A[2];
+    }
+    return;
+  }
+  for (int y = ymin + lane; y <= ymax; y += 32) {
+    int lo = xmin, hi = xmax;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = A[i] * y + Cc[i] - static_cast<int>((m >> i) & 1u);   // the pixel is inside iff B x + k >= 0
+      if (Bx[i] > 0) lo = max(lo, -floor_div_pos(k, Bx[i]));                // x >= ceil(-k / B) = -floor(k / B)
+      else if (Bx[i] < 0) hi = min(hi, floor_div_pos(k, -Bx[i]));           // x <= floor(k / -B)
+      else if (k < 0) hi = -1;                                              // the whole row is outside
+    }
+    if (lo <= hi) store_span(lb + static_cast<size_t>(y) * W, lo, hi, static_cast<unsigned>(t));
+  }
+}
+
+// u = int(((gx+1)/2)*(W-1)), v = int(((gy+1)/2)*(H-1))  -- models/models.py:644-645, fp32 op for op (as inverse.cu)
+__device__ __forceinline__ int raster_target(float g, int size) {
+  const float f = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), static_cast<float>(size - 1));
+  return f == f ? __float2int_rz(f) : -1;
+}
+
+// loc[v,u] = 0x8000 | n for every node n that won its target pixel (models/models.py:650-651), and the "no value" code
+// at image corners no node landed on (corner sites carry the NaN row; several triangles meet there).
+__global__ void stamp_nodes_kernel(const float2* __restrict__ grid, const int32_t* __restrict__ winner,
+                                   uint16_t* __restrict__ loc, int B, int hw, int H, int W) {
+  const int total = B * (hw + 4);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / (hw + 4), node = idx - b * (hw + 4);
+    const size_t img = static_cast<size_t>(b) * H * W;
+    if (node >= hw) {
+      const int c = node - hw, v = (c & 2) ? H - 1 : 0, u = (c & 1) ? W - 1 : 0;
+      if (winner[img + static_cast<size_t>(v) * W + u] < 0) loc[img + static_cast<size_t>(v) * W + u] = static_cast<uint16_t>(0x8000u | hw);
+      continue;
+    }
+    const float2 g = grid[static_cast<size_t>(b) * hw + node];
+    const int u = raster_target(g.x, W), v = raster_target(g.y, H);
+    if (u < 0 || u >= W || v < 0 || v >= H) continue;
+    const size_t p = img + static_cast<size_t>(v) * W + u;
+    if (winner[p] == node) loc[p] = static_cast<uint16_t>(0x8000u | node);
+  }
+}
+
+__global__ void fill_none_kernel(uint4* __restrict__ loc, size_t n16, unsigned none2) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    loc[i] = make_uint4(none2, none2, none2, none2);
+}
+
+}  // namespace fovea
+
+using namespace fovea;
+
+extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
+                                   const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap,
+                                   int tcap, int prefill, uint16_t* loc, fovea_stream_t stream) {
+  FOVEA_REQUIRE(pts && mesh && trirec && ntri && loc, "fovea_locate_raster: null pointer");
+  FOVEA_REQUIRE((grid == nullptr) == (winner == nullptr), "fovea_locate_raster: grid and winner go together");
+  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && cap > 0 && tcap > 0, "fovea_locate_raster: bad sizes");
+  FOVEA_REQUIRE(H <= 16384 && W <= 16384 && W % 8 == 0, "fovea_locate_raster: canvas side must be <= 16384 and the width "
+                "a multiple of 8 (16-byte span stores)");
+  FOVEA_REQUIRE(tcap <= 32768 && static_cast<long long>(h) * w < 32767, "fovea_locate_raster: triangle ids / table rows must fit 15 bits");
+  FOVEA_REQUIRE(B <= 65535, "fovea_locate_raster: B too large for the grid");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int hw = h * w;
+  if (prefill) {  // canvases the triangulation does not cover (no forced corners): everything starts as "no value"
+    const size_t n16 = static_cast<size_t>(B) * H * W / 8;
+    const unsigned none = 0x8000u | static_cast<unsigned>(hw);
+    fill_none_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(loc), n16, none | (none << 16));
+  }
+  raster_locate_kernel<<<dim3(ceil_div(tcap, kRasThreads / 32), B), kRasThreads, 0, s>>>(
+      pts, reinterpret_cast<const uint4*>(mesh), static_cast<const TriRec*>(trirec), ntri, loc, hw, H, W, cap, tcap);
+  if (grid) {
+    const int total = B * (hw + 4);
+    stamp_nodes_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(reinterpret_cast<const float2*>(grid), winner,
+                                                                             loc, B, hw, H, W);
+  }
+  return check_launch("fovea_locate_raster");
+}

@@ -358,22 +358,44 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, si
     _lib.call("fovea_select_points" if sites == "tri" else "fovea_select_points_nb", _ptr(g), _ptr(winner), B, h, w, H,
               W, int(nchan), cap, _ptr(pts), _ptr(src), _ptr(npts), _stream())
     hints = rounds = None
+    raster = _use_raster(W)
     if triangulation == "host":
         mesh, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
     elif triangulation == "device":
-        if _lib.load().fovea_delaunay_hints_fused(tcap, H, W):
+        if not raster and _lib.load().fovea_delaunay_hints_fused(tcap, H, W):
             mesh, ntri, hints, ws = delaunay_device_with_hints(pts, npts, cap, tcap, H, W)
         else:
             mesh, ntri, ws = delaunay_device(pts, npts, cap, tcap, max(H, W))
         rounds = ws[:B]
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
-    if hints is None:
-        hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
     trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), h * w)
-    loc = _locate(winner, trirec, ntri, hints, h, w, tcap)
+    if raster:   # sites='nb' has no forced corners: the hull does not cover the canvas, start from "no value"
+        loc = _locate_raster(pts, mesh, trirec, ntri, g, winner, h, w, cap, tcap, prefill=sites != "tri")
+    else:
+        if hints is None:
+            hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
+        loc = _locate(winner, trirec, ntri, hints, h, w, tcap)
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, h, w, H, W, cap, tcap, triangulation,
                        rounds)
+
+
+def _use_raster(W):
+    """fovea_locate_raster (one warp per triangle) unless FOVEA_LOCATE=walk asks for the scan-line walker
+    (fovea_locate_hints + fovea_locate_pixels) or the canvas width is not a multiple of 8 (its 16-byte span stores)."""
+    import os
+    return os.environ.get("FOVEA_LOCATE", "raster") != "walk" and W % 8 == 0
+
+
+def _locate_raster(pts, mesh, trirec, ntri, grid, winner, h, w, cap, tcap, prefill):
+    """interp2d.py:58 (find_simplex for every pixel) by rasterising the mesh, merged with the A7 winners (grid may be
+    None: no pixel carries a node): the per-pixel source map `loc`."""
+    B, H, W = winner.shape
+    loc = torch.empty(B, H, W, device=winner.device, dtype=torch.int16)    # uint16 bit patterns
+    _lib.call("fovea_locate_raster", _ptr(pts), _ptr(mesh), _ptr(trirec), _ptr(ntri), _ptr(grid),
+              _ptr(winner if grid is not None else None), B, h, w, H, W, cap, tcap, 1 if prefill else 0, _ptr(loc),
+              _stream())
+    return loc
 
 
 def check_plan(plan: InversePlan):
@@ -510,9 +532,13 @@ def plan_from_mesh(pts, src, npts, mesh, ntri, H, W, table_rows) -> InversePlan:
     B, cap = pts.shape
     tcap = mesh.shape[1]
     winner = torch.full((B, H, W), -1, device=pts.device, dtype=torch.int32)
-    hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
     trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), table_rows)
-    loc = _locate(winner, trirec, ntri, hints, table_rows, 1, tcap)
+    hints = None
+    if _use_raster(W):
+        loc = _locate_raster(pts, mesh, trirec, ntri, None, winner, table_rows, 1, cap, tcap, prefill=True)
+    else:
+        hints = _hints(pts, npts, mesh, ntri, B, cap, tcap, H, W)
+        loc = _locate(winner, trirec, ntri, hints, table_rows, 1, tcap)
     return InversePlan(winner, pts, src, npts, mesh, ntri, hints, trirec, loc, table_rows, 1, H, W, cap, tcap, "given")
 
 

@@ -229,6 +229,18 @@ int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t*
 int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t* ntri, const int32_t* hints, int B,
                         int h, int w, int H, int W, int tcap, uint16_t* loc, fovea_stream_t stream);
 
+/* The same per-pixel source map as fovea_locate_pixels, computed by RASTERISING the mesh (one warp per triangle, closed-form
+ * row spans from the setup records' exact integer edge functions -- the predicate fovea_locate_pixels tests pixel by
+ * pixel, so the two maps are identical) and then stamping the pixels that received a node from the nodes themselves.
+ * Needs no walk-start hints and does not read the winner map except at the 6 400 node targets.
+ *   grid, winner : the sampling grid [B,h,w,2] and fovea_grid_inv_scatter's map; both NULL when no pixel carries a node
+ *                  (Interp2D on an arbitrary point set)
+ *   prefill != 0 : first mark every pixel "no value" -- required when the triangulation does not cover the canvas (no
+ *                  forced corners: 'BI' sites, arbitrary point sets);  W must be a multiple of 8 */
+int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
+                        const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap, int tcap,
+                        int prefill, uint16_t* loc, fovea_stream_t stream);
+
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
  * fillMissingValues_tensor(..., 'tri') = Interp2D barycentric gather (models/models.py:939-940,
  * interp2d.py:65-91), residual NaN -> 0 (models_instance.py:940) and torch.argmax over classes
