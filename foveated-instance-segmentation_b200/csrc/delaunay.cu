@@ -149,7 +149,7 @@ __global__ void __maxnreg__(DT_MAXNREG)
 delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
                 uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
                 int max_rounds, int32_t* __restrict__ dbg, unsigned short* __restrict__ row_ws,
-                int32_t* __restrict__ hints_out, int H, int W) {
+                int32_t* __restrict__ hints_out, int H, int W, int mesh_stride, unsigned* __restrict__ lock_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int warp_sums[33];
   __shared__ int s_ntri;
@@ -169,8 +169,14 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     A.n0 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
     A.n1 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
     A.n2 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
-    A.lock = reinterpret_cast<unsigned*>(p); p += 4 * tcap;
-    A.dirty = reinterpret_cast<unsigned*>(p); p += 4 * ((tcap + 31) / 32);
+    if (lock_g) {  // large site sets (e.g. the 64 x 128 lattice): claims and dirty bits live in global memory (L2), the
+                   // mesh itself and the points still fit one CTA's shared memory
+      A.lock = lock_g + static_cast<size_t>(b) * (tcap + (tcap + 31) / 32);
+      A.dirty = A.lock + tcap;
+    } else {
+      A.lock = reinterpret_cast<unsigned*>(p); p += 4 * tcap;
+      A.dirty = reinterpret_cast<unsigned*>(p); p += 4 * ((tcap + 31) / 32);
+    }
     A.spts = reinterpret_cast<int*>(p);
     A.rowStart = row_ws + static_cast<size_t>(b) * (cap + 2);
     unsigned short* s = reinterpret_cast<unsigned short*>(A.lock);  // 2*tcap shorts of scratch
@@ -179,7 +185,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     A.cnext = s + 2 * cap;
     A.cown = s + 3 * cap;
   }
-  uint16_t* mesh = mesh_out + static_cast<size_t>(b) * tcap * 8;
+  uint16_t* mesh = mesh_out + static_cast<size_t>(b) * mesh_stride * 8;
   for (int i = tid; i < n; i += kDtThreads) A.spts[i] = pts_in[i];
   const int* pts = A.spts;
   __syncthreads();
@@ -201,6 +207,14 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   }
   if (tid == 0) A.rowStart[R] = static_cast<unsigned short>(n);
   __syncthreads();
+  if (n > cap || 2 * n - 5 > tcap) {  // more triangles than the 16-bit mesh encoding holds: report, never overrun
+    if (tid == 0) { ntri_out[b] = 0; if (rounds_out) rounds_out[b] = -1; }
+    if (hints_out) {
+      const int nh = ceil_div(H, FOVEA_HINT_CELL_H) * ceil_div(W, FOVEA_HINT_CELL_W);
+      for (int i = tid; i < nh; i += kDtThreads) hints_out[static_cast<size_t>(b) * nh + i] = 0;
+    }
+    return;
+  }
   if (n < 3 || R < 2) {  // nothing to triangulate (all points collinear in one row)
     if (tid == 0) { ntri_out[b] = 0; if (rounds_out) rounds_out[b] = 0; }
     if (hints_out) {
@@ -763,19 +777,28 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   }
 }
 
-static size_t dt_smem_bytes(int cap, int tcap) {
-  return static_cast<size_t>(12) * tcap + 4 * static_cast<size_t>(tcap) + 4 * static_cast<size_t>((tcap + 31) / 32) +
+constexpr int kDtMaxTri = 16383;     // triangle ids are stored as (id << 2 | slot) in 16 bits; 0xFFFD..0xFFFF are markers
+constexpr size_t kDtMaxSmem = 227 * 1024;
+
+// triangles the kernel can address for this capacity (a full triangulation of n sites has at most 2n - 5 of them)
+static int dt_kernel_tcap(int tcap) { return tcap < kDtMaxTri ? tcap : kDtMaxTri; }
+static size_t dt_smem_bytes(int cap, int tk, bool big) {
+  return static_cast<size_t>(12) * tk + (big ? 0 : 4 * static_cast<size_t>(tk) + 4 * static_cast<size_t>((tk + 31) / 32)) +
          4 * static_cast<size_t>(cap);
 }
+static bool dt_big(int cap, int tcap) { return dt_smem_bytes(cap, dt_kernel_tcap(tcap), false) > kDtMaxSmem; }
 
 }  // namespace fovea
 
 using namespace fovea;
 
 extern "C" int64_t fovea_delaunay_workspace_bytes(int B, int cap) {
-  (void)cap;
-  // [B] flip rounds + [B,8] stage counters (int32), then [B, cap+2] row starts (uint16)
-  return static_cast<int64_t>(B) * 4 * 9 + static_cast<int64_t>(B) * (cap + 2) * 2;
+  // [B] flip rounds + [B,8] stage counters (int32), then [B, cap+2] row starts (uint16); site sets too large for the
+  // all-shared-memory layout add [B, tk + tk/32] claim words + dirty bits (uint32)
+  int64_t bytes = static_cast<int64_t>(B) * 4 * 9 + (static_cast<int64_t>(B) * (cap + 2) * 2 + 3) / 4 * 4;
+  const int tk = dt_kernel_tcap(2 * cap);
+  if (dt_big(cap, 2 * cap)) bytes += static_cast<int64_t>(B) * (tk + (tk + 31) / 32) * 4;
+  return bytes;
 }
 
 static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int cap, int tcap, int max_coord,
@@ -785,12 +808,15 @@ static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int c
   FOVEA_REQUIRE(B > 0 && cap >= 4 && tcap >= 2 * cap, "%s: need tcap >= 2*cap (cap=%d tcap=%d)", who, cap, tcap);
   FOVEA_REQUIRE(max_coord > 0 && max_coord <= 8192,
                 "%s: coordinates must be < 8192 for the exact int64 in-circle test (got %d)", who, max_coord);
-  if (tcap > 16383 || cap > 8190) {
-    set_error("%s: tcap=%d exceeds the 16-bit mesh encoding (max 16383 triangles)", who, tcap);
+  if (cap > 8196) {   // (8196 = the 64 x 128 lattice of config/deform.yaml + the four corners)
+    set_error("%s: cap=%d exceeds the 16-bit mesh encoding (at most 8196 sites, 16383 triangles)", who, cap);
     return FOVEA_ERR_CAPACITY;
   }
-  const size_t smem = dt_smem_bytes(cap, tcap);
-  if (smem > 227 * 1024) {
+  const int tk = dt_kernel_tcap(tcap);
+  const bool big = dt_big(cap, tcap);
+  FOVEA_REQUIRE(!(big && hints), "%s: the fused walk hints need the all-shared-memory layout (cap=%d)", who, cap);
+  const size_t smem = dt_smem_bytes(cap, tk, big);
+  if (smem > kDtMaxSmem) {
     set_error("%s: %zu B of shared memory needed for cap=%d (> 227 KB); use the host triangulation", who, smem, cap);
     return FOVEA_ERR_CAPACITY;
   }
@@ -799,10 +825,11 @@ static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int c
   // non-convergence report in the tests
   int max_rounds = 20000;
   if (const char* e = getenv("FOVEA_DT_MAX_ROUNDS")) max_rounds = atoi(e) > 0 ? atoi(e) : max_rounds;
-  delaunay_kernel<<<B, kDtThreads, smem, stream>>>(
-      pts, npts, cap, tcap, mesh, ntri, static_cast<int32_t*>(workspace), max_rounds,
-      static_cast<int32_t*>(workspace) + B, reinterpret_cast<unsigned short*>(static_cast<int32_t*>(workspace) + 9 * B),
-      hints, H, W);
+  int32_t* ws32 = static_cast<int32_t*>(workspace);
+  unsigned short* row_ws = reinterpret_cast<unsigned short*>(ws32 + 9 * B);
+  unsigned* lock_g = big ? reinterpret_cast<unsigned*>(ws32 + 9 * B + (static_cast<size_t>(B) * (cap + 2) * 2 + 3) / 4) : nullptr;
+  delaunay_kernel<<<B, kDtThreads, smem, stream>>>(pts, npts, cap, tk, mesh, ntri, ws32, max_rounds, ws32 + B, row_ws, hints, H,
+                                                   W, tcap, lock_g);
   return check_launch(who);
 }
 
@@ -813,7 +840,8 @@ extern "C" int fovea_delaunay(const int32_t* pts, const int32_t* npts, int B, in
 }
 
 extern "C" int fovea_delaunay_hints_fused(int tcap, int H, int W) {
-  // the two coarse levels live in the kernel's dead lock array (4*tcap bytes)
+  // the two coarse levels live in the kernel's dead lock array (4*tcap bytes) -- when that array is in shared memory
+  if (dt_big(tcap / 2, tcap)) return 0;
   const long long ch = ceil_div(H, FOVEA_HINT_CELL_H), cw = ceil_div(W, FOVEA_HINT_CELL_W);
   return (256 + ceil_div(static_cast<int>(ch), 4) * cw) * 4 <= 4ll * tcap ? 1 : 0;
 }

@@ -46,6 +46,12 @@ inline int make_plane_store_map(CUtensorMap* map, float* base, long long planes,
   return FOVEA_OK;
 }
 
+// the same map for LOADS of box_w x box_h pixel tiles; elements outside the tensor arrive as zeros (F.grid_sample's
+// padding_mode='zeros' for free)
+inline int make_plane_load_map(CUtensorMap* map, const float* base, long long planes, int H, int W, int box_w, int box_h) {
+  return make_plane_store_map(map, const_cast<float*>(base), planes, H, W, box_w, box_h);
+}
+
 __device__ __forceinline__ unsigned smem_addr(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
@@ -61,6 +67,33 @@ template <int N>
 __device__ __forceinline__ void tma_wait_read() {  // at most N committed groups may still be READING shared memory
   asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
 }
+// ---- loads: global -> shared tile, completion signalled on an mbarrier (transaction bytes)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// one thread: load the [box_h][box_w] tile whose first element is (x, y) of plane z into `smem` (x, y may be negative or
+// reach past the tensor: those elements are zero-filled).  x * 4 bytes must be a multiple of 16: a misaligned inner
+// coordinate raises "illegal instruction" (measured with tools/_build/tma_load_test.cu: x = -1 faults, x = -4 does not)
+__device__ __forceinline__ void tma_load_tile(const CUtensorMap* map, void* smem, unsigned long long* bar, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(smem_addr(smem)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_addr(bar)), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
+
 // generic-proxy writes to shared memory (st.shared) become visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -182,3 +182,36 @@ def test_device_delaunay_is_deterministic(ops):
             T = int(p.ntri[b])
             assert torch.equal(p.mesh[b, :T].view(torch.int16), plans[0].mesh[b, :T].view(torch.int16))
         assert torch.equal(p.loc, plans[0].loc)
+
+
+def test_yaml_saliency_size_64x128(ops):
+    """config/deform.yaml:42 sets saliency_input_size (64,128) = 8 192 nodes (+ 4 corners): beyond the all-shared-memory
+    layout of the Delaunay kernel (claims and dirty bits then live in global memory) and at the edge of its 16-bit mesh
+    encoding.  Exact mesh validation, agreement with the host-Qhull path, and one frame against the oracle."""
+    from test_device_mesh_parity_gpu import _cocircular_flags
+    from test_parity_gpu import _check_masks, _edge_exempt
+    B, C, gh, gw, Rx, Ry, H, W = 2, 3, 64, 128, 15, 30, 1024, 2048
+    xs, _ = rp.synthetic_saliency(B, gh, gw, seed=64)
+    filt, P = rp.gaussian_filter_weight(Rx, Ry, Rx), rp.p_basis(gh, gw, Rx, Ry)
+    grid, _ = rp.create_grid(rp.pad_saliency(xs, Rx, Ry), filt, P, gh, gw, (gh, gw))
+    pred = rp.synthetic_pred(B, C, gh, gw, seed=64)
+    plan_d = ops.check_plan(ops.build_inverse_plan(grid.cuda(), (H, W), nchan=C, triangulation="device"))
+    plan_h = ops.build_inverse_plan(grid.cuda(), (H, W), nchan=C, triangulation="host")
+    assert plan_d.cap == gh * gw + 4
+    npts, pts = plan_d.npts.cpu().numpy(), plan_d.pts.cpu().numpy()
+    mesh, ntri = plan_d.mesh.cpu().numpy(), plan_d.ntri.cpu().numpy()
+    print("sites per frame", npts.tolist(), "triangles", ntri.tolist(), "flip rounds", plan_d.rounds.tolist())
+    assert (npts > 6600).all(), "the case must exceed the shared-memory-only capacity to mean anything"
+    for b in range(B):
+        check_mesh(np.stack([pts[b, : npts[b]] >> 16, pts[b, : npts[b]] & 0xFFFF], 1), mesh[b], int(ntri[b]))
+    sd, md = ops.inverse_fill(plan_d, pred.cuda(), want_scores=True, want_mask=True)
+    sh, mh = ops.inverse_fill(plan_h, pred.cuda(), want_scores=True, want_mask=True)
+    for b in range(B):     # differences only inside co-circular cells of Qhull's mesh
+        flag, _ = _cocircular_flags(plan_h, b)
+        differs = ((sd[b] - sh[b]).abs() > 1e-5 * sh.abs().max()).any(0)
+        loc = plan_h.loc[b].view(torch.int16).long() & 0xFFFF
+        assert ((loc[differs] & 0x8000) == 0).all() and flag[loc[differs]].all()
+    assert (md == mh).float().mean().item() > 0.985
+    want = rp.inverse_path(pred[:1], grid[:1], (H, W))
+    exempt = _edge_exempt(sh[:1].cpu(), want, plan_h)
+    _check_masks(mh[:1].cpu(), want, exempt)
