@@ -42,7 +42,7 @@ WORKLOADS = {
     "b16_4096": dict(B=16, H=4096, W=4096, C=51, g=80, R=45),
     "tiny": dict(B=4, H=256, W=256, C=51, g=80, R=45),
 }
-KERNELS_PER_STEP = 9  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay(+hints), triangle_setup, locate_pixels, box4_table, inverse_fill
+KERNELS_PER_STEP = 10  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay, triangle_setup, raster_locate, stamp_nodes, box4_table, inverse_fill
 
 
 def peaks():

@@ -34,6 +34,40 @@ __device__ __forceinline__ void store_span(uint16_t* row, int lo, int hi, unsign
   while (x <= hi) row[x++] = static_cast<uint16_t>(id);
 }
 
+// Everything a lane needs about the triangle it works on.
+struct RasTri {
+  int A0, B0, C0, A1, B1, C1, A2, B2, C2;   // edge functions with the tie bit already subtracted: inside <=> all >= 0
+  int ymin, ymax, xmin, xmax;
+  bool live;
+};
+
+__device__ __forceinline__ RasTri ras_load(const int32_t* __restrict__ pb, const uint4* __restrict__ mesh,
+                                           const TriRec* __restrict__ recs, int t, int T) {
+  RasTri R;
+  R.live = t < T;
+  R.A0 = R.B0 = R.C0 = R.A1 = R.B1 = R.C1 = R.A2 = R.B2 = R.C2 = 0;
+  R.ymin = R.xmin = 0; R.ymax = R.xmax = -1;
+  if (!R.live) return R;
+  const uint4* r = reinterpret_cast<const uint4*>(recs + t);
+  const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+  const uint4 mq = __ldg(mesh + t);
+  if (q2.w == 0u) { R.live = false; return R; }  // degenerate triangle (host meshes only): owns nothing
+  const int p0 = __ldg(pb + (mq.x & 0xFFFFu)), p1 = __ldg(pb + (mq.x >> 16)), p2 = __ldg(pb + (mq.y & 0xFFFFu));
+  R.ymin = min(min(p0 >> 16, p1 >> 16), p2 >> 16); R.ymax = max(max(p0 >> 16, p1 >> 16), p2 >> 16);
+  R.xmin = min(min(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF); R.xmax = max(max(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF);
+  const unsigned m = q2.z >> 16;
+  R.A0 = static_cast<int>(q0.x); R.B0 = static_cast<int>(q0.y); R.C0 = static_cast<int>(q0.z) - static_cast<int>(m & 1u);
+  R.A1 = static_cast<int>(q0.w); R.B1 = static_cast<int>(q1.x); R.C1 = static_cast<int>(q1.y) - static_cast<int>((m >> 1) & 1u);
+  R.A2 = static_cast<int>(q1.z); R.B2 = static_cast<int>(q1.w); R.C2 = static_cast<int>(q2.x) - static_cast<int>((m >> 2) & 1u);
+  return R;
+}
+
+// One warp takes FOUR triangles, eight lanes each (the typical triangle covers ~80 pixels in a ~13 x 13 box: a whole warp
+// per triangle leaves most lanes idle and pays the set-up 4 times over -- measured 290 instructions per triangle).  The
+// eight lanes sweep their triangle's bounding box row by row, 8 pixels per step, each lane testing ITS pixel against the
+// three edge functions (no divisions).  Triangles with a large box (the few hull / periphery triangles that cover a tenth
+// of the canvas each) are then taken one after the other by the WHOLE warp on the row-span path: lane l owns rows
+// ymin + l, + 32, ..., solves the three inequalities for the row's span in closed form and stores it 16 bytes at a time.
 __global__ void __launch_bounds__(kRasThreads)
 raster_locate_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
                      const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, int hw, int H, int W, int cap, int tcap) {
@@ -48,51 +82,50 @@ raster_locate_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ 
     return;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (kRasThreads / 32) + warp;
-  if (t >= T) return;
-  const uint4* r = reinterpret_cast<const uint4*>(trirec + static_cast<size_t>(b) * tcap + t);
-  const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
-  if (q2.w == 0u) return;  // degenerate triangle (host meshes only): owns nothing
-  const uint4 mq = __ldg(mesh + static_cast<size_t>(b) * tcap + t);
-  const int32_t* pb = pts + static_cast<size_t>(b) * cap;
-  const int p0 = __ldg(pb + (mq.x & 0xFFFFu)), p1 = __ldg(pb + (mq.x >> 16)), p2 = __ldg(pb + (mq.y & 0xFFFFu));
-  const int ymin = min(min(p0 >> 16, p1 >> 16), p2 >> 16), ymax = max(max(p0 >> 16, p1 >> 16), p2 >> 16);
-  const int xmin = min(min(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF), xmax = max(max(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF);
-  const int A[3] = {static_cast<int>(q0.x), static_cast<int>(q0.w), static_cast<int>(q1.z)};
-  const int Bx[3] = {static_cast<int>(q0.y), static_cast<int>(q1.x), static_cast<int>(q1.w)};
-  const int Cc[3] = {static_cast<int>(q0.z), static_cast<int>(q1.y), static_cast<int>(q2.x)};
-  const unsigned m = q2.z >> 16;
-  // Small bounding boxes (the typical triangle covers ~80 pixels): the warp sweeps the box in 4 x 8-pixel steps, every
-  // lane testing ITS pixel against the three edge functions -- no divisions, ~12 instructions per step.  Large boxes
-  // (the few hull / periphery triangles that cover a tenth of the canvas each) take the row-span path below, where the
-  // three divisions per row are amortised over long 16-byte stores.
-  const int bh = ymax - ymin + 1, bw = xmax - xmin + 1;
-  if (bh * bw <= kRasTileMax) {
-    const int dy = lane >> 3, dx = lane & 7;
-    int e0 = A[0] * (ymin + dy) + Bx[0] * (xmin + dx) + Cc[0] - static_cast<int>(m & 1u);
-    int e1 = A[1] * (ymin + dy) + Bx[1] * (xmin + dx) + Cc[1] - static_cast<int>((m >> 1) & 1u);
-    int e2 = A[2] * (ymin + dy) + Bx[2] * (xmin + dx) + Cc[2] - static_cast<int>((m >> 2) & 1u);
-    for (int y = ymin + dy; y <= ymax; y += 4) {
+  const int t0 = (blockIdx.x * (kRasThreads / 32) + warp) * 4;   // first of this warp's four triangles
+  if (t0 >= T) return;
+  const int sub = lane >> 3, sl = lane & 7;
+  const int t = t0 + sub;
+  const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
+                            trirec + static_cast<size_t>(b) * tcap, t, T);
+  const int bh = R.ymax - R.ymin + 1, bw = R.xmax - R.xmin + 1;
+  const bool large = R.live && bh * bw > kRasTileMax;
+  if (R.live && !large) {
+    int e0 = R.A0 * R.ymin + R.B0 * (R.xmin + sl) + R.C0;
+    int e1 = R.A1 * R.ymin + R.B1 * (R.xmin + sl) + R.C1;
+    int e2 = R.A2 * R.ymin + R.B2 * (R.xmin + sl) + R.C2;
+    for (int y = R.ymin; y <= R.ymax; ++y) {
       int f0 = e0, f1 = e1, f2 = e2;
       uint16_t* row = lb + static_cast<size_t>(y) * W;
-      for (int x = xmin + dx; x <= xmax; x += 8) {
+      for (int x = R.xmin + sl; x <= R.xmax; x += 8) {
         if ((f0 | f1 | f2) >= 0) row[x] = static_cast<uint16_t>(t);    // all three >= 0  <=>  no sign bit set
-        f0 += 8 * Bx[0]; f1 += 8 * Bx[1]; f2 += 8 * Bx[2];
+        f0 += 8 * R.B0; f1 += 8 * R.B1; f2 += 8 * R.B2;
       }
-      e0 += 4 * A[0]; e1 += 4 * A[1]; e2 += 4 * A[2];
+      e0 += R.A0; e1 += R.A1; e2 += R.A2;
     }
-    return;
   }
-  for (int y = ymin + lane; y <= ymax; y += 32) {
-    int lo = xmin, hi = xmax;
+  // the large ones: whole warp, one after the other (their parameters come from the first lane of their group)
+  unsigned todo = __ballot_sync(0xffffffffu, large) & 0x01010101u;
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int A[3] = {__shfl_sync(0xffffffffu, R.A0, src), __shfl_sync(0xffffffffu, R.A1, src), __shfl_sync(0xffffffffu, R.A2, src)};
+    const int Bx[3] = {__shfl_sync(0xffffffffu, R.B0, src), __shfl_sync(0xffffffffu, R.B1, src), __shfl_sync(0xffffffffu, R.B2, src)};
+    const int Cc[3] = {__shfl_sync(0xffffffffu, R.C0, src), __shfl_sync(0xffffffffu, R.C1, src), __shfl_sync(0xffffffffu, R.C2, src)};
+    const int ymin = __shfl_sync(0xffffffffu, R.ymin, src), ymax = __shfl_sync(0xffffffffu, R.ymax, src);
+    const int xmin = __shfl_sync(0xffffffffu, R.xmin, src), xmax = __shfl_sync(0xffffffffu, R.xmax, src);
+    const unsigned id = static_cast<unsigned>(t0 + (src >> 3));
+    for (int y = ymin + lane; y <= ymax; y += 32) {
+      int lo = xmin, hi = xmax;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int k = A[i] * y + Cc[i] - static_cast<int>((m >> i) & 1u);   // the pixel is inside iff B x + k >= 0
-      if (Bx[i] > 0) lo = max(lo, -floor_div_pos(k, Bx[i]));                // x >= ceil(-k / B) = -floor(k / B)
-      else if (Bx[i] < 0) hi = min(hi, floor_div_pos(k, -Bx[i]));           // x <= floor(k / -B)
-      else if (k < 0) hi = -1;                                              // the whole row is outside
+      for (int i = 0; i < 3; ++i) {
+        const int k = A[i] * y + Cc[i];                                       // the pixel is inside iff B x + k >= 0
+        if (Bx[i] > 0) lo = max(lo, -floor_div_pos(k, Bx[i]));                // x >= ceil(-k / B) = -floor(k / B)
+        else if (Bx[i] < 0) hi = min(hi, floor_div_pos(k, -Bx[i]));           // x <= floor(k / -B)
+        else if (k < 0) hi = -1;                                              // the whole row is outside
+      }
+      if (lo <= hi) store_span(lb + static_cast<size_t>(y) * W, lo, hi, id);
     }
-    if (lo <= hi) store_span(lb + static_cast<size_t>(y) * W, lo, hi, static_cast<unsigned>(t));
   }
 }
 
@@ -150,7 +183,7 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
     const unsigned none = 0x8000u | static_cast<unsigned>(hw);
     fill_none_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(loc), n16, none | (none << 16));
   }
-  raster_locate_kernel<<<dim3(ceil_div(tcap, kRasThreads / 32), B), kRasThreads, 0, s>>>(
+  raster_locate_kernel<<<dim3(ceil_div(tcap, 4 * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(
       pts, reinterpret_cast<const uint4*>(mesh), static_cast<const TriRec*>(trirec), ntri, loc, hw, H, W, cap, tcap);
   if (grid) {
     const int total = B * (hw + 4);
