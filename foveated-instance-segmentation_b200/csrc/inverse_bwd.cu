@@ -100,44 +100,59 @@ inverse_fill_bwd_kernel(const uint16_t* __restrict__ loc, const TriRec* __restri
   }
   const bool single = nd0[lead] == nd1[lead] && nd1[lead] == nd2[lead];  // a pixel that received a node: one row, weight 1
 
-  const float* gp = gout + static_cast<size_t>(b) * p.C * plane + pixoff;
-  float* tb = gtable + static_cast<size_t>(b) * (hw + 2) * p.Cs;
-  for (int c = 0; c < p.C; ++c, gp += plane) {
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(gp));
-      g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
-    }
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  // group-0 weights with the other pixels' zeroed: the channel loop below is then free of per-pixel predicates
+  float u0[4], u1[4], u2[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if ((g0 >> k) & 1u) {
-        s0 = fmaf(w0[k], g[k], s0); s1 = fmaf(w1[k], g[k], s1); s2 = fmaf(w2[k], g[k], s2);
-      } else if ((solo >> k) & 1u) {
-        float* r = tb + c;
-        if (nd0[k] == nd1[k] && nd1[k] == nd2[k]) {
-          atomicAdd(r + static_cast<size_t>(nd0[k]) * p.Cs, g[k]);
-        } else {
-          atomicAdd(r + static_cast<size_t>(nd0[k]) * p.Cs, w0[k] * g[k]);
-          atomicAdd(r + static_cast<size_t>(nd1[k]) * p.Cs, w1[k] * g[k]);
-          atomicAdd(r + static_cast<size_t>(nd2[k]) * p.Cs, w2[k] * g[k]);
-        }
-      }
-    }
-    if (single) { s0 += s1 + s2; s1 = s2 = 0.f; }
+  for (int k = 0; k < 4; ++k) {
+    const bool in = (g0 >> k) & 1u;
+    u0[k] = in ? w0[k] : 0.f; u1[k] = in ? w1[k] : 0.f; u2[k] = in ? w2[k] : 0.f;
+  }
+  const bool emit = head && g0;
+  // byte offsets of the three rows inside the frame's table (rows < 2^15, Cs <= 2^16: fits 32 bits)
+  const unsigned o0 = nd0[lead] * static_cast<unsigned>(p.Cs) * 4u, o1 = nd1[lead] * static_cast<unsigned>(p.Cs) * 4u,
+                 o2 = nd2[lead] * static_cast<unsigned>(p.Cs) * 4u;
+  const float* gp = gout + static_cast<size_t>(b) * p.C * plane + pixoff;
+  char* tb = reinterpret_cast<char*>(gtable + static_cast<size_t>(b) * (hw + 2) * p.Cs);
+  for (int c = 0; c < p.C; ++c, gp += plane, tb += 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) v = __ldcs(reinterpret_cast<const float4*>(gp));
+    float s0 = fmaf(u0[3], v.w, fmaf(u0[2], v.z, fmaf(u0[1], v.y, u0[0] * v.x)));
+    float s1 = fmaf(u1[3], v.w, fmaf(u1[2], v.z, fmaf(u1[1], v.y, u1[0] * v.x)));
+    float s2 = fmaf(u2[3], v.w, fmaf(u2[2], v.z, fmaf(u2[1], v.y, u2[0] * v.x)));
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       const float t0 = __shfl_down_sync(0xffffffffu, s0, 1 << i);
       const float t1 = __shfl_down_sync(0xffffffffu, s1, 1 << i);
       const float t2 = __shfl_down_sync(0xffffffffu, s2, 1 << i);
-      if ((okmask >> i) & 1u) { s0 += t0; s1 += t1; s2 += t2; }
+      const bool ok = (okmask >> i) & 1u;
+      s0 += ok ? t0 : 0.f; s1 += ok ? t1 : 0.f; s2 += ok ? t2 : 0.f;
     }
-    if (head && g0) {
-      float* r = tb + c;
-      atomicAdd(r + static_cast<size_t>(nd0[lead]) * p.Cs, s0);
+    if (emit) {
+      atomicAdd(reinterpret_cast<float*>(tb + o0), s0);   // (a pixel that received a node: weights (1,0,0), one row)
       if (!single) {
-        atomicAdd(r + static_cast<size_t>(nd1[lead]) * p.Cs, s1);
-        atomicAdd(r + static_cast<size_t>(nd2[lead]) * p.Cs, s2);
+        atomicAdd(reinterpret_cast<float*>(tb + o1), s1);
+        atomicAdd(reinterpret_cast<float*>(tb + o2), s2);
+      }
+    }
+  }
+  // the pixels of this thread that do not share their rows with its first live pixel (triangle boundaries inside the
+  // thread's 4 pixels, the densely filled fovea): their own adds, outside the warp-synchronous loop
+  if (solo) {
+    const float* gq = gout + static_cast<size_t>(b) * p.C * plane + pixoff;
+    float* tq = gtable + static_cast<size_t>(b) * (hw + 2) * p.Cs;
+    for (int c = 0; c < p.C; ++c, gq += plane, ++tq) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(gq));
+      const float g[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!((solo >> k) & 1u)) continue;
+        if (nd0[k] == nd1[k] && nd1[k] == nd2[k]) {
+          atomicAdd(tq + static_cast<size_t>(nd0[k]) * p.Cs, g[k]);
+        } else {
+          atomicAdd(tq + static_cast<size_t>(nd0[k]) * p.Cs, w0[k] * g[k]);
+          atomicAdd(tq + static_cast<size_t>(nd1[k]) * p.Cs, w1[k] * g[k]);
+          atomicAdd(tq + static_cast<size_t>(nd2[k]) * p.Cs, w2[k] * g[k]);
+        }
       }
     }
   }

@@ -97,7 +97,9 @@ def test_module_forward_matches_reference(golden_dir, upsample, triangulation):
         nan_ref = np.unpackbits(g["scored_nan"])[: B * H * W].reshape(B, H, W).astype(bool)
         nan_agree = (torch.isnan(sc[:, 0]).cpu().numpy() == nan_ref).mean()
         print(f"upsample/{triangulation}: full-res mask agreement {agree:.4f}, NaN-pattern agreement {nan_agree:.4f}")
-        assert agree > 0.93 and nan_agree > 0.97
+        # measured: 0.9999 / 0.9999 with the reference's own mesh (host Qhull), 0.9996 / 0.9999 with the device mesh (the
+        # remainder: the reference's undefined winners at collision pixels, and co-circular cells for the device mesh)
+        assert agree > (0.999 if triangulation == "host" else 0.998) and nan_agree > 0.999
 
 
 def test_module_training_step_backward():
@@ -152,7 +154,7 @@ def test_fill_missing_values_and_interp2d_api(golden_dir):
         out = Interp2D(h, w, triangulation=tri_mode)(pts.cuda(), vals.cuda()).cpu().numpy()
         close = np.isclose(out, g["out"], rtol=0, atol=1e-5)
         print("Interp2D", tri_mode, "agreement", close.mean())
-        assert close.mean() > (0.999 if tri_mode == "host" else 0.7)
+        assert close.mean() > (0.999 if tri_mode == "host" else 0.95)   # measured 1.0 / 0.981 (co-circular cells)
     gi = dict(np.load(os.path.join(golden_dir, "inverse_80_to_128.npz")))
     t = torch.from_numpy(gi["pred_sampled_nan"][0]).cuda()
     want = rp.fill_missing_values_tensor(torch.from_numpy(gi["pred_sampled_nan"][0]).clone())
@@ -262,3 +264,35 @@ def test_module_inference_accepts_uint8_frames():
     m.train()
     with pytest.raises(NotImplementedError):
         m(dict(feed8))
+
+
+def test_inference_return_tuples_match_the_reference_signature():
+    """models_instance.py:1112-1121: (pred_sampled, pred, y_sampled) -- also with VAL.no_upsample (that flag only renames
+    tensors for the reference's visualisation) --, a 4-tuple with VAL.y_sampled_reverse, (pred_sampled, loss) for
+    F_Xlr_acc_map; rev_deform_interp='BI' runs on the same kernels with the NB site rule."""
+    from fovea.models import CompressNet, DeformSegmentationModule
+    from fovea.saliency_network import fov_simple
+    feed = {k: v.cuda() for k, v in synthetic_batch(2, 128, 160, 9).items()}
+    cfg = make_cfg(True)
+    torch.manual_seed(5)
+    m = DeformSegmentationModule(TinyEncoder(), TinyDecoder(), fov_simple(cfg), CompressNet(cfg), None, cfg,
+                                 triangulation="device").cuda().eval()
+    with torch.no_grad():
+        cfg.VAL.no_upsample = True
+        a = m(dict(feed), segSize=(128, 160))
+        cfg.VAL.no_upsample = False
+        b = m(dict(feed), segSize=(128, 160))
+        assert len(a) == len(b) == 3 and all(torch.equal(u, v) for u, v in zip(a, b))
+        assert a[0].shape == (2, 51, 128, 160) and a[1].shape == (2, 51, 80, 80) and a[2].shape == (2, 80, 80)
+        cfg.VAL.y_sampled_reverse = True
+        c = m(dict(feed), segSize=(128, 160))
+        assert len(c) == 4 and c[3].shape == (2, 128, 160) and c[3].dtype == torch.int64
+        assert set(c[3].unique().tolist()) <= {0, 1}                  # the label is {0,1}: its inverse upsampling too
+        # the label pushed down and up again agrees with the label on most of the frame (the intrinsic upsampling error)
+        assert (c[3] == feed["seg_label"].squeeze(1).long()).float().mean().item() > 0.9
+        cfg.VAL.y_sampled_reverse = False
+        ps, loss = m(dict(feed), segSize=(128, 160), F_Xlr_acc_map=True)
+        assert torch.equal(ps, a[0]) and loss.dim() == 0 and torch.isfinite(loss)
+        cfg.MODEL.rev_deform_interp = "BI"
+        d = m(dict(feed), segSize=(128, 160))
+        assert d[0].shape == a[0].shape and torch.isfinite(d[0]).all() and not torch.equal(d[0], a[0])

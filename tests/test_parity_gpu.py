@@ -272,7 +272,8 @@ def test_inverse_fill_matches_oracle_and_golden(ops, golden_dir, name, grid_name
     if zero_residual:
         ref[np.isnan(ref)] = 0
     ok = np.isclose(scores.cpu().numpy(), ref, rtol=1e-5, atol=1e-5, equal_nan=True)
-    assert ok.mean() > 0.9, f"only {ok.mean():.3f} of pixels agree with the reference golden"
+    print(f"{name} (zero_residual={zero_residual}): {ok.mean():.5f} of the values equal the reference's own output")
+    assert ok.mean() > 0.99, f"only {ok.mean():.3f} of pixels agree with the reference golden"   # measured 0.9960 / 0.9998
 
 
 def _check_masks(mask, want_scores, exempt=None, tie=1e-5):
