@@ -9,8 +9,9 @@
 //   * inside a triangle every channel's score is  fl(fl(fl(a*w0) + fl(b*w1)) + fl(c*w2))  with weights >= 0 and IEEE
 //     rounding monotone, so a channel that is <= another channel at all three vertices can never beat it at any pixel
 //     of the triangle.  triangle_candidates_kernel keeps, per TRIANGLE, the channels that survive this dominance test
-//     (typically 2-8 of 51 on i.i.d. predictions, 2 on the reference's C1 decoder) together with their three vertex
-//     values; inverse_mask_kernel evaluates only those -- with exactly the arithmetic of fovea_inverse_fill.
+//     against the two strongest channels of each vertex (typically 3-10 of 51 on i.i.d. predictions, 2 on the reference's
+//     C1 decoder) together with their three vertex values; inverse_mask_kernel evaluates only those -- with exactly the
+//     arithmetic of fovea_inverse_fill.
 //
 // Exactness (the mask equals the fused argmax of fovea_inverse_fill bit for bit, ties included):
 //   - torch.argmax returns the FIRST maximum.  A channel may be dropped because of a LOWER-index channel that is >= at
@@ -35,7 +36,7 @@ constexpr int kCandMax = 32;          // survivors kept per triangle (one 512-by
                                       // touched); more -> full evaluation.  (16 slots overflow for ~10 % of the huge hull
                                       // triangles, whose three nodes are far apart -- and those cover a fifth of a canvas.)
 constexpr int kCandThreads = 128;
-constexpr int kCandSmem = 16;         // survivor slots held in shared memory; the rare slots beyond live in the global record
+constexpr int kCandRefine = 10;       // lists longer than this are pruned exactly (warp-cooperatively)
 constexpr unsigned kCandFull = 0xFFu;  // ncand marker: evaluate every channel
 constexpr unsigned kCandNaN = 0xFEu;   // ncand marker: a vertex has no value -> NaN in every channel -> label 0
 
@@ -55,58 +56,72 @@ node_argmax_kernel(const float* __restrict__ table, uint8_t* __restrict__ nodear
   nodearg[static_cast<size_t>(b) * rows + r] = static_cast<uint8_t>(best == best ? bi : 0);
 }
 
-// One thread per triangle.  Channels are offered in index order, so every survivor has a LOWER index than the newcomer:
-//   the newcomer is dropped if some survivor is >= at the three vertices (that survivor wins every tie as well);
-//   a survivor is dropped if the newcomer exceeds it at the three vertices by more than M = 2^-20 * (largest magnitude
-//   among the triangle's vertex values): more than the rounding of both evaluations, i.e. strictly greater at every pixel.
-// The survivor list lives in shared memory, [slot][field][thread] (conflict-free), and stays in index order.
-// Before a channel meets the list it is compared with the three channels that are the argmax at the triangle's vertices
-// (node_argmax_kernel): registers only, no loop -- most channels end there.  (Being beaten by a real channel is reason
-// enough to drop one, whatever becomes of that channel later: the relation is transitive.)
+// One thread per triangle, uniform control flow (the 32 triangles of a warp walk the same C channels in lock step; an
+// earlier version kept an exact survivor list per thread and ran at 8-11 active lanes per instruction).
+//   pass 1: per vertex the two largest channels (value and index) -> up to six "seeds", and the margin
+//           M = 2^-20 * (largest magnitude among the triangle's vertex values);
+//   pass 2: a channel is dropped if some seed makes it irrelevant on the whole triangle:
+//             seed index lower : seed >= channel at the three vertices (the seed wins every tie as well);
+//             seed index higher: seed exceeds the channel at the three vertices by more than M -- more than the rounding of
+//                                both evaluations, i.e. strictly greater at every pixel;
+//           what is left is written out in index order.  The seeds are real channels, so being beaten by one is reason
+//           enough whatever becomes of the seed itself (the relation is transitive).  On i.i.d. N(0,1) predictions 6.8
+//           channels are left per triangle where an exact all-pairs pruning leaves 5.9.
 __global__ void __launch_bounds__(kCandThreads)
 triangle_candidates_kernel(const TriRec* __restrict__ trirec, const int32_t* __restrict__ ntri,
-                           const float* __restrict__ table, const uint8_t* __restrict__ nodearg,
-                           float4* cand, uint8_t* __restrict__ ncand, int hw, int C, int Cs, int tcap) {
-  __shared__ float sv[kCandSmem][4][kCandThreads];
+                           const float* __restrict__ table, float4* __restrict__ cand, uint8_t* __restrict__ ncand,
+                           int hw, int C, int Cs, int tcap) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * kCandThreads + threadIdx.x;
-  if (t >= ntri[b]) return;
-  const int tid = threadIdx.x;
-  float4* out = cand + (static_cast<size_t>(b) * tcap + t) * kCandMax;   // (also the spill space of slots >= kCandSmem)
-#define SV_LD(k, f) ((k) < kCandSmem ? sv[(k)][(f)][tid] : reinterpret_cast<const float*>(out + (k))[(f)])
-#define SV_ST(k, f, v)                                                                  \
-  do {                                                                                  \
-    if ((k) < kCandSmem) sv[(k)][(f)][tid] = (v);                                       \
-    else reinterpret_cast<float*>(out + (k))[(f)] = (v);                                \
-  } while (0)
-  const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(trirec + static_cast<size_t>(b) * tcap + t) + 3);
+  const bool exists = t < ntri[b];            // (no early return: pass 3 needs every lane of the warp)
+  const uint4 q3 = exists ? __ldg(reinterpret_cast<const uint4*>(trirec + static_cast<size_t>(b) * tcap + t) + 3)
+                          : make_uint4(0, 0, 0, 0);
   const int r0 = static_cast<int>(q3.x & 0xFFFFu), r1 = static_cast<int>(q3.x >> 16), r2 = static_cast<int>(q3.y);
-  uint8_t* nc = ncand + static_cast<size_t>(b) * tcap + t;
-  if (r0 >= hw || r1 >= hw || r2 >= hw) { *nc = static_cast<uint8_t>(kCandNaN); return; }
+  uint8_t* nc = ncand + static_cast<size_t>(b) * tcap + (exists ? t : 0);
+  const bool valid = exists && r0 < hw && r1 < hw && r2 < hw;   // a vertex without a value: NaN in every channel
+  float M = 0.f;
+  float4* out = cand + (static_cast<size_t>(b) * tcap + (exists ? t : 0)) * kCandMax;
+  int n = 0;
+  if (valid) {
   const float* tb = table + static_cast<size_t>(b) * (hw + 2) * Cs;
   const float4* p0 = reinterpret_cast<const float4*>(tb + static_cast<size_t>(r0) * Cs);
   const float4* p1 = reinterpret_cast<const float4*>(tb + static_cast<size_t>(r1) * Cs);
   const float4* p2 = reinterpret_cast<const float4*>(tb + static_cast<size_t>(r2) * Cs);
-  // pass 1: the margin (padding channels of the table are zero: they do not raise it)
+  // ---- pass 1
   float mag = 0.f;
+  float top[3][2] = {{-CUDART_INF_F, -CUDART_INF_F}, {-CUDART_INF_F, -CUDART_INF_F}, {-CUDART_INF_F, -CUDART_INF_F}};
+  int topi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   for (int c4 = 0; c4 < C; c4 += 4) {
     const float4 A = __ldg(p0 + (c4 >> 2)), Bv = __ldg(p1 + (c4 >> 2)), Cv = __ldg(p2 + (c4 >> 2));
-    mag = fmaxf(mag, fmaxf(fmaxf(fmaxf(fabsf(A.x), fabsf(A.y)), fmaxf(fabsf(A.z), fabsf(A.w))),
-                           fmaxf(fmaxf(fmaxf(fabsf(Bv.x), fabsf(Bv.y)), fmaxf(fabsf(Bv.z), fabsf(Bv.w))),
-                                 fmaxf(fmaxf(fabsf(Cv.x), fabsf(Cv.y)), fmaxf(fabsf(Cv.z), fabsf(Cv.w))))));
+    const float v[3][4] = {{A.x, A.y, A.z, A.w}, {Bv.x, Bv.y, Bv.z, Bv.w}, {Cv.x, Cv.y, Cv.z, Cv.w}};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool in = c4 + e < C;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float x = v[k][e];
+        mag = fmaxf(mag, in ? fabsf(x) : 0.f);
+        const bool g1 = in & (x > top[k][0]), g2 = in & (x > top[k][1]);
+        top[k][1] = g1 ? top[k][0] : (g2 ? x : top[k][1]);
+        topi[k][1] = g1 ? topi[k][0] : (g2 ? c4 + e : topi[k][1]);
+        top[k][0] = g1 ? x : top[k][0];
+        topi[k][0] = g1 ? c4 + e : topi[k][0];
+      }
+    }
   }
-  const float M = 9.5367431640625e-07f * mag;  // 2^-20 * mag   (NaN / Inf magnitudes: no comparison below succeeds)
-  // the three vertex-argmax channels: index, values at the three vertices, values lowered by the margin
-  const uint8_t* na = nodearg + static_cast<size_t>(b) * (hw + 2);
+  M = 9.5367431640625e-07f * mag;  // 2^-20 * mag   (NaN / Inf magnitudes: no comparison below succeeds)
+  // the seeds' values at the three vertices (nine scalar loads each way; duplicates among the six are harmless)
   const float* f0 = reinterpret_cast<const float*>(p0);
   const float* f1 = reinterpret_cast<const float*>(p1);
   const float* f2 = reinterpret_cast<const float*>(p2);
-  int si[3] = {na[r0], na[r1], na[r2]};
-  float sa[3], sb[3], sc[3];
+  int si[6];
+  float sa[6], sb[6], sc[6];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) { sa[q] = __ldg(f0 + si[q]); sb[q] = __ldg(f1 + si[q]); sc[q] = __ldg(f2 + si[q]); }
-  // pass 2 (uniform control flow: every lane walks the same 51 channels): which channels survive the three seeds?
-  unsigned long long alive = 0;
+  for (int q = 0; q < 6; ++q) {
+    si[q] = topi[q >> 1][q & 1];
+    sa[q] = __ldg(f0 + si[q]); sb[q] = __ldg(f1 + si[q]); sc[q] = __ldg(f2 + si[q]);
+  }
+  // ---- pass 2
   for (int c4 = 0; c4 < C; c4 += 4) {
     const float4 A = __ldg(p0 + (c4 >> 2)), Bv = __ldg(p1 + (c4 >> 2)), Cv = __ldg(p2 + (c4 >> 2));
     const float a4[4] = {A.x, A.y, A.z, A.w}, b4[4] = {Bv.x, Bv.y, Bv.z, Bv.w}, c4v[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
@@ -116,50 +131,51 @@ triangle_candidates_kernel(const TriRec* __restrict__ trirec, const int32_t* __r
       const float a = a4[e], bb = b4[e], cc = c4v[e];
       bool beaten = c >= C;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
+      for (int q = 0; q < 6; ++q) {
         // (bitwise & | on purpose: short-circuit operators compile to branches, and the lanes of a warp -- 32 different
-        //  triangles -- would take them apart: measured 9 active lanes per instruction)
+        //  triangles -- would take them apart)
         const bool lower = si[q] < c, higher = si[q] > c;
         beaten = beaten | (lower & (sa[q] >= a) & (sb[q] >= bb) & (sc[q] >= cc)) |
                  (higher & (sa[q] - M > a) & (sb[q] - M > bb) & (sc[q] - M > cc));
       }
-      if (!beaten) alive |= 1ull << (c & 63);
-    }
-  }
-  // pass 3: exact pruning among the channels left (in index order: every lane takes its next one in the same iteration)
-  int n = 0;
-  bool overflow = false;
-  const bool wide = C > 64;   // more than 64 channels: the bit mask cannot hold them, offer every channel
-  for (int c = wide ? 0 : (alive ? __ffsll(static_cast<long long>(alive)) - 1 : C); c < C && !overflow;
-       c = wide ? c + 1 : ((alive &= alive - 1) ? __ffsll(static_cast<long long>(alive)) - 1 : C)) {
-    const float a = __ldg(f0 + c), bb = __ldg(f1 + c), cc = __ldg(f2 + c);
-    const float am = a - M, bm = bb - M, cm = cc - M;
-    bool dominated = false;
-    int keep = 0;
-    for (int k = 0; k < n; ++k) {
-      const float ka = SV_LD(k, 0), kb = SV_LD(k, 1), kc = SV_LD(k, 2);
-      dominated = dominated | ((ka >= a) & (kb >= bb) & (kc >= cc));
-      if ((am > ka) & (bm > kb) & (cm > kc)) continue;       // the newcomer beats survivor k strictly everywhere
-      if (keep != k) {
-        const float ki = SV_LD(k, 3);
-        SV_ST(keep, 0, ka); SV_ST(keep, 1, kb); SV_ST(keep, 2, kc); SV_ST(keep, 3, ki);
+      if (!beaten) {
+        if (n < kCandMax) out[n] = make_float4(a, bb, cc, __int_as_float(c));
+        ++n;
       }
-      ++keep;
     }
-    // (a dominated newcomer removes nothing: whatever it exceeds by M its dominator exceeds by M too -- one margin per
-    //  triangle, monotone rounding -- and that survivor either removed it when it entered the list, or, if it entered
-    //  earlier, would have kept it out; entries the newcomer did remove lose to it at every pixel in any case)
-    n = keep;
-    if (dominated) continue;
-    if (n == kCandMax) { overflow = true; continue; }
-    SV_ST(n, 0, a); SV_ST(n, 1, bb); SV_ST(n, 2, cc); SV_ST(n, 3, __int_as_float(c));
-    ++n;
   }
-  if (overflow) { *nc = static_cast<uint8_t>(kCandFull); return; }
-  for (int k = 0; k < n && k < kCandSmem; ++k) out[k] = make_float4(sv[k][0][tid], sv[k][1][tid], sv[k][2][tid], sv[k][3][tid]);
-  *nc = static_cast<uint8_t>(n);
-#undef SV_LD
-#undef SV_ST
+  }
+  // ---- pass 3: long lists (the large hull / periphery triangles, whose three nodes are far apart and whose strongest
+  // channels beat little -- and which cover a good part of the canvas) are pruned exactly, one after the other, by the
+  // whole warp: lane i holds entry i and drops it if ANY other entry makes it irrelevant (same two rules)
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = 0xffffffffu;
+  unsigned todo = __ballot_sync(peers, n > kCandRefine && n <= kCandMax);
+  __syncwarp(peers);   // the lists were written by their owners: order those stores before the peers' loads
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int ns = __shfl_sync(peers, n, src);
+    const float Ms = __shfl_sync(peers, M, src);
+    const unsigned long long base = __shfl_sync(peers, reinterpret_cast<unsigned long long>(out), src);
+    float4* list = reinterpret_cast<float4*>(base);
+    const float4 me = lane < ns ? list[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int my = __float_as_int(me.w);
+    bool keep = lane < ns;
+    for (int j = 0; j < ns; ++j) {
+      const float ja = __shfl_sync(peers, me.x, j), jb = __shfl_sync(peers, me.y, j), jc = __shfl_sync(peers, me.z, j);
+      const int jd = __shfl_sync(peers, my, j);
+      const bool lower = jd < my, higher = jd > my;
+      keep = keep & !((lower & (ja >= me.x) & (jb >= me.y) & (jc >= me.z)) |
+                      (higher & (ja - Ms > me.x) & (jb - Ms > me.y) & (jc - Ms > me.z)));
+    }
+    const unsigned kept = __ballot_sync(peers, keep);
+    __syncwarp(peers);                               // every lane has read its entry before the list is rewritten
+    if (keep) list[__popc(kept & ((1u << lane) - 1u))] = me;
+    if (lane == src) n = __popc(kept);
+    __syncwarp(peers);
+  }
+  if (exists) *nc = static_cast<uint8_t>(!valid ? kCandNaN : (n <= kCandMax ? n : kCandFull));
 }
 
 constexpr int kMaskThreads = 256;
@@ -305,7 +321,7 @@ extern "C" int fovea_inverse_mask(const uint16_t* loc, const void* trirec, const
   node_argmax_kernel<<<dim3(ceil_div(rows, 256), B), 256, 0, s>>>(table, nodearg, rows, C, Cs);
   if (ntri)  // 'nearest' plans carry no triangles: every pixel is a direct row
     triangle_candidates_kernel<<<dim3(ceil_div(tcap, kCandThreads), B), kCandThreads, 0, s>>>(
-        static_cast<const TriRec*>(trirec), ntri, table, nodearg, cand, ncand, h * w, C, Cs, tcap);
+        static_cast<const TriRec*>(trirec), ntri, table, cand, ncand, h * w, C, Cs, tcap);
   FillParams p{C, Cs, h, w, H, W, 0, tcap, 1, mask_u8 ? 1 : 0};
   dim3 grid(ceil_div(W, 4 * kMaskWL * 2), ceil_div(H, (32 / kMaskWL) * (kMaskThreads / 32 / 2)), B);
   inverse_mask_kernel<<<grid, kMaskThreads, 0, s>>>(loc, static_cast<const TriRec*>(trirec), table, cand, ncand, nodearg,
