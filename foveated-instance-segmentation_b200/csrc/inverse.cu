@@ -930,12 +930,19 @@ static int launch_fill(const uint16_t* loc, const TriRec* recs, const float* tab
                        const FillParams& p, int B, cudaStream_t s) {
   constexpr int kTileH = (32 / FOVEA_FILL_WL) * (kFillThreads / 32 / WX);
   dim3 grid(ceil_div(p.W, 4 * FOVEA_FILL_WL * WX), ceil_div(p.H, kTileH * kFillTilesY), B);
-  if (scores && mk)
-    inverse_fill_kernel<true, true, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
-  else if (scores)
-    inverse_fill_kernel<true, false, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
-  else
+  // Experiment switch FOVEA_FILL_PAD_KB: unused dynamic shared memory per CTA, i.e. a cap on the fill's CTAs per SM (the
+  // kernel alone is insensitive to 3 vs 4 CTAs/SM); the registers and thread slots it leaves free let the latency-bound plan
+  // kernels of the next batch co-reside under the pipelined schedule instead of displacing fill CTAs.
+  static const int pad = [] { const char* e = getenv("FOVEA_FILL_PAD_KB"); return e ? atoi(e) * 1024 : 0; }();
+  if (scores && mk) {
+    if (pad) cudaFuncSetAttribute(inverse_fill_kernel<true, true, G, WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    inverse_fill_kernel<true, true, G, WX><<<grid, kFillThreads, pad, s>>>(loc, recs, table, scores, mk, p);
+  } else if (scores) {
+    if (pad) cudaFuncSetAttribute(inverse_fill_kernel<true, false, G, WX>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    inverse_fill_kernel<true, false, G, WX><<<grid, kFillThreads, pad, s>>>(loc, recs, table, scores, mk, p);
+  } else {
     inverse_fill_kernel<false, true, G, WX><<<grid, kFillThreads, 0, s>>>(loc, recs, table, scores, mk, p);
+  }
   return check_launch("fovea_inverse_fill");
 }
 
