@@ -946,6 +946,9 @@ static int launch_fill(const uint16_t* loc, const TriRec* recs, const float* tab
   return check_launch("fovea_inverse_fill");
 }
 
+int fovea_launch_fill_smem(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h, int w,
+                           int H, int W, int tcap, int zero_residual, float* scores, int mode, cudaStream_t s);   // inverse_smem.cu
+
 extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const float* table, int B, int C, int Cs, int h,
                                   int w, int H, int W, int tcap, int zero_residual, float* scores, void* mask,
                                   int mask_u8, fovea_stream_t stream) {
@@ -963,6 +966,13 @@ extern "C" int fovea_inverse_fill(const uint16_t* loc, const void* trirec, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const TriRec* recs = static_cast<const TriRec*>(trirec);
   long long* mk = reinterpret_cast<long long*>(mask);
+  // experiment switch FOVEA_FILL_SMEM=1: scores-only fills stage the tile's table rows in shared memory (inverse_smem.cu)
+  const char* smem_env = getenv("FOVEA_FILL_SMEM");   // (read per call: the A/B test flips it between launches)
+  const int smem_rows = smem_env ? atoi(smem_env) : 0;   // 1: rows in shared memory; 2: + TMA tile stores
+  if (smem_rows && scores && !mask) {
+    const int rc = fovea_launch_fill_smem(loc, trirec, table, B, C, Cs, h, w, H, W, tcap, zero_residual, scores, smem_rows, s);
+    if (rc >= 0) return rc;
+  }
   // 8-channel groups (256-bit table loads) need 32-byte aligned rows: Cs % 8 == 0 and a 32-byte aligned table
   const bool wide = Cs % 8 == 0 && (reinterpret_cast<uintptr_t>(table) & 31u) == 0 && fill_wide_requested();
   if (wide) return launch_fill<8, 2>(loc, recs, table, scores, mk, p, B, s);
