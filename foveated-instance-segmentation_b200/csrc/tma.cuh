@@ -87,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 // one thread: load the [box_h][box_w] tile whose first element is (x, y) of plane z into `smem` (x, y may be negative or
 // reach past the tensor: those elements are zero-filled).  x * 4 bytes must be a multiple of 16: a misaligned inner
-// coordinate raises "illegal instruction" (measured with tools/_build/tma_load_test.cu: x = -1 faults, x = -4 does not)
+// coordinate raises "illegal instruction" (measured with tools/probes/tma_load_test.cu: x = -1 faults, x = -4 does not)
 __device__ __forceinline__ void tma_load_tile(const CUtensorMap* map, void* smem, unsigned long long* bar, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                :: "r"(smem_addr(smem)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_addr(bar)), "r"(x), "r"(y), "r"(z)

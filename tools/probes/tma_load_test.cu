@@ -2,7 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../../foveated-instance-segmentation_b200/csrc/tma.cuh"
+#include "../../foveated-instance-segmentation_b200/csrc/tma.cuh"  // nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I include -o tools/_build/tma_load_test tools/probes/tma_load_test.cu
 namespace fovea { void set_error(const char* fmt, ...) { printf("error: %s\n", fmt); } }
 using namespace fovea;
 __global__ void k(const __grid_constant__ CUtensorMap tmap, float* out, int x, int y, int z, int step) {
