@@ -521,7 +521,25 @@ def main():
                       "(fovea_inverse_mask: per-node argmax + per-triangle dominance pruning, bit-identical) vs the "
                       "all-channel fused argmax of fovea_inverse_fill it replaces; c1_tail = 3-channel fill + relabel"}
         del plan_, tab_, tab_n, pred_c1
+    # ... and the same mode through the product's DevicePipeline (plan of step i+1 over the mask fill of step i)
+    from fovea.pipeline import DevicePipeline as _DP
+    mpipe = _DP(B, C, H, W, cfg["g"], cfg["R"], dev, args.triangulation, depth=2, want_mask=True, want_scores=False,
+                interp=args.interp)
+    for _ in range(3):
+        mpipe.submit(x, xs, pred)
+    mpipe.fence()
+    barrier()
+    m0.record()
+    for _ in range(args.steps):
+        mpipe.submit(x, xs, pred)
+    mpipe.fence()
+    m1.record()
+    barrier()
+    mpipe.check()
+    mask_pipe_ms = _max_over_ranks([m0.elapsed_time(m1) / args.steps], dev, world)[0]
+    del mpipe
     mask_mode = {"c1_tail": c1, "serial_ms_per_step": mask_ms, "frames_s_per_gpu": B / (mask_ms * 1e-3), "steps": km,
+                 "pipelined_ms_per_step": mask_pipe_ms, "pipelined_frames_s": world * B / (mask_pipe_ms * 1e-3),
                  "algorithmic_bytes_per_frame": 8 * H * W,
                  "what": "grid + grid_sample + plan + mask fill (scores never materialised, mask=int64), one stream"}
 

@@ -156,7 +156,9 @@ class DevicePipeline:
     """
 
     def __init__(self, B, C, H, W, g=80, R=45, device=None, triangulation="device", depth=2, want_mask=False,
-                 filter_weight=None, scores=None, interp="tri"):
+                 filter_weight=None, scores=None, interp="tri", want_scores=True):
+        """want_scores=False (with want_mask=True): mask mode -- the [B,C,H,W] score tensor is never materialised, stage 3
+        runs the pruned arg-max fill (fovea_inverse_mask) and `submit` returns (x_sampled, mask)."""
         if not torch.cuda.is_available():
             raise FoveaError("DevicePipeline needs a CUDA device: there is no CPU fallback")
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -168,7 +170,9 @@ class DevicePipeline:
         self.g1x, self.g1y = (t.to(self.dev) for t in ops.separable_factors(filter_weight))
         self.plan_stream = torch.cuda.Stream(self.dev, priority=-1)
         self.fill_stream = torch.cuda.Stream(self.dev, priority=0)
-        self.scores = scores if scores is not None else torch.empty(B, C, H, W, device=self.dev)
+        if not want_scores and not want_mask:
+            raise FoveaError("DevicePipeline: nothing to produce (want_scores=False needs want_mask=True)")
+        self.scores = None if not want_scores else (scores if scores is not None else torch.empty(B, C, H, W, device=self.dev))
         self.mask = torch.empty(B, H, W, device=self.dev, dtype=torch.int64) if want_mask else None
         self.live = []               # (tensors kept alive, fill-done event) of the batches in flight
         self.fill_events = []        # optional (start, end) timing events of the fill kernel
@@ -215,7 +219,7 @@ class DevicePipeline:
         self.live.append(((plan, grid, table, x_sampled, x, xs, pred), done))
         if len(self.live) > self.depth:
             self.live.pop(0)
-        return x_sampled, self.scores
+        return x_sampled, (self.scores if self.scores is not None else self.mask)
 
     def fence(self, stream=None):
         stream = stream or torch.cuda.current_stream(self.dev)

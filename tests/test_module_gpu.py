@@ -296,3 +296,38 @@ def test_inference_return_tuples_match_the_reference_signature():
         cfg.MODEL.rev_deform_interp = "BI"
         d = m(dict(feed), segSize=(128, 160))
         assert d[0].shape == a[0].shape and torch.isfinite(d[0]).all() and not torch.equal(d[0], a[0])
+
+
+def test_device_pipeline_matches_direct_path():
+    """fovea.pipeline.DevicePipeline (plan of batch i+1 on a high-priority stream over the fill of batch i): scores mode and
+    mask mode (want_scores=False: the pruned arg-max fill) give the direct path's results; x_sampled is ordered on the
+    caller's stream when submit returns."""
+    from fovea import ops
+    from fovea.pipeline import DevicePipeline
+    from oracle import reference_port as rp
+    B, C, H, W, g, R = 3, 9, 256, 320, 80, 45
+    g1x, g1y = (t.cuda() for t in ops.separable_factors(rp.gaussian_filter_weight(R, R, R)))
+    batches, want = [], []
+    for seed in range(4):
+        xs, _ = rp.synthetic_saliency(B, seed=seed)
+        x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(seed)).cuda()
+        pred = rp.synthetic_pred(B, C, seed=seed).cuda()
+        batches.append((x, xs.cuda(), pred))
+        grid = ops.saliency_to_grid(xs.cuda(), g1x, g1y, g, g, R, R, "replication", (g, g))
+        plan = ops.build_inverse_plan(grid, (H, W), nchan=C, triangulation="device")
+        s, m = ops.inverse_fill(plan, pred, want_scores=True, want_mask=True)
+        want.append((ops.grid_sample(x, grid), s, m))
+    pipe = DevicePipeline(B, C, H, W, g, R, triangulation="device", depth=2)
+    for (x, xs, pred), (xs_want, s_want, _) in zip(batches, want):
+        x_sampled, scores = pipe.submit(x, xs, pred)
+        assert torch.equal(x_sampled, xs_want)            # consumed on the caller's stream, no explicit fence
+        pipe.fence()
+        assert torch.equal(scores, s_want)
+    pipe.check()
+    mpipe = DevicePipeline(B, C, H, W, g, R, triangulation="device", depth=2, want_mask=True, want_scores=False)
+    for (x, xs, pred), (_, _, m_want) in zip(batches, want):
+        _, mask = mpipe.submit(x, xs, pred)
+        mpipe.fence()
+        assert mask.dtype == torch.int64 and torch.equal(mask, m_want)
+    with pytest.raises(Exception):
+        DevicePipeline(B, C, H, W, g, R, want_mask=False, want_scores=False)
