@@ -9,13 +9,16 @@
 // the triangle id over the span.  Spans of different triangles are disjoint (the tie rule gives every pixel exactly one
 // owner), so there is nothing to synchronise.  The pixels that received a node are stamped afterwards from the
 // 6 400 nodes themselves (stamp_nodes_kernel) -- the 4-byte-per-pixel winner map is no longer read by stage 3's locate.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fill.cuh"
 
 namespace fovea {
 
 constexpr int kRasThreads = 256;
-constexpr int kRasTileMax = 2048;   // bounding boxes up to this many pixels are swept pixel by pixel
+constexpr int kRasTileMax = 1024;   // bounding boxes up to this many pixels are swept pixel by pixel (measured 32 .. 2048: flat,
+                                    // 356 us at 1024 against 378 at 2048 and 396 at 320; FOVEA_RAS_TILE_MAX overrides)
 
 // floor(a / b) for b > 0 and |a / b| < 2^22: float quotient, exact fix-up
 __device__ __forceinline__ int floor_div_pos(int a, int b) {
@@ -70,7 +73,8 @@ __device__ __forceinline__ RasTri ras_load(const int32_t* __restrict__ pb, const
 // ymin + l, + 32, ..., solves the three inequalities for the row's span in closed form and stores it 16 bytes at a time.
 __global__ void __launch_bounds__(kRasThreads)
 raster_locate_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
-                     const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, int hw, int H, int W, int cap, int tcap) {
+                     const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, int hw, int H, int W, int cap, int tcap,
+                     int tile_max) {
   const int b = blockIdx.y;
   const int T = ntri[b];
   uint16_t* lb = loc + static_cast<size_t>(b) * H * W;
@@ -89,7 +93,7 @@ raster_locate_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ 
   const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
                             trirec + static_cast<size_t>(b) * tcap, t, T);
   const int bh = R.ymax - R.ymin + 1, bw = R.xmax - R.xmin + 1;
-  const bool large = R.live && bh * bw > kRasTileMax;
+  const bool large = R.live && bh * bw > tile_max;
   if (R.live && !large) {
     int e0 = R.A0 * R.ymin + R.B0 * (R.xmin + sl) + R.C0;
     int e1 = R.A1 * R.ymin + R.B1 * (R.xmin + sl) + R.C1;
@@ -178,13 +182,14 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
   FOVEA_REQUIRE(B <= 65535, "fovea_locate_raster: B too large for the grid");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int hw = h * w;
+  static const int tile_max = [] { const char* e = getenv("FOVEA_RAS_TILE_MAX"); return e ? atoi(e) : kRasTileMax; }();
   if (prefill) {  // canvases the triangulation does not cover (no forced corners): everything starts as "no value"
     const size_t n16 = static_cast<size_t>(B) * H * W / 8;
     const unsigned none = 0x8000u | static_cast<unsigned>(hw);
     fill_none_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(loc), n16, none | (none << 16));
   }
   raster_locate_kernel<<<dim3(ceil_div(tcap, 4 * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(
-      pts, reinterpret_cast<const uint4*>(mesh), static_cast<const TriRec*>(trirec), ntri, loc, hw, H, W, cap, tcap);
+      pts, reinterpret_cast<const uint4*>(mesh), static_cast<const TriRec*>(trirec), ntri, loc, hw, H, W, cap, tcap, tile_max);
   if (grid) {
     const int total = B * (hw + 4);
     stamp_nodes_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(reinterpret_cast<const float2*>(grid), winner,
