@@ -132,6 +132,8 @@ __device__ __forceinline__ int ck(int idx, int lim, int line) {
 #define CK(i, lim) (i)
 #endif
 
+__device__ __forceinline__ int nx3(int k) { return (0x09 >> (2 * k)) & 3; }   // (k + 1) % 3 for k in 0..2
+__device__ __forceinline__ int pv3(int k) { return (0x12 >> (2 * k)) & 3; }   // (k + 2) % 3
 __device__ __forceinline__ unsigned short& nb_slot(const DtArrays& A, int t, int k) {
   return k == 0 ? A.n0[t] : (k == 1 ? A.n1[t] : A.n2[t]);
 }
@@ -142,6 +144,16 @@ __device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsi
   if (code < kPendingCode) nb_slot(A, code >> 2, code & 3) = static_cast<unsigned short>(me);
 }
 
+#ifndef DT_CLAIM2
+#define DT_CLAIM2 1   // 1: a flip claims its two triangles (back links through postings); 0: the six-triangle claim
+#endif
+// Lock words of the block-wide flip rounds: [31:26] round tag (decreasing), then either a CLAIM -- bit 25 set, 11 random
+// priority bits, the proposing triangle -- or, once a flip has won, a POSTING -- bit 25 clear, bit 16 = second triangle
+// of the pair, [15:14] this triangle's slot of the old diagonal, [13:0] its partner.
+constexpr unsigned kClaimBit = 1u << 25, kPostIsU = 1u << 16;
+__device__ __forceinline__ unsigned claim_word(unsigned tag, int t, int round) {
+  return tag | kClaimBit | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0x7FFu) << 14) | static_cast<unsigned>(t);
+}
 #ifndef DT_MAXNREG
 #define DT_MAXNREG 64   // (48 would let one inverse_fill CTA co-reside per SM under the pipelined schedule: measured, no gain)
 #endif
@@ -433,7 +445,14 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   // costs ceil(dirty/32) full-warp test iterations instead of one mostly-idle iteration per 32 triangles.
   const int lane = tid & 31, warp = tid >> 5;
   const int wpw = (nwords + 31) / 32;  // dirty words per warp (<= 16 for tcap <= 16383)
-  const int wbase = warp * wpw;
+#ifndef DT_STRIDED
+#define DT_STRIDED 1
+#endif
+#if DT_STRIDED   // word j of a warp: interleaved over the mesh (a hot region's words spread over all warps) ...
+#define DT_WORD(j) (warp + 32 * (j))
+#else            // ... or one contiguous range per warp
+#define DT_WORD(j) (warp * wpw + (j))
+#endif
   int round = 0, tail_hold = 0;
   bool flips_done = false;
   for (; round < max_rounds; ++round) {
@@ -459,20 +478,20 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     // thinning costs few wins per round but removes 3/4 of the tests and claims.  Unselected bits stay dirty.
     unsigned myword = 0;
     bool deferred = false;
-    if (lane < wpw && wbase + lane < nwords) {
-      const unsigned w = A.dirty[wbase + lane];
+    if (lane < wpw && DT_WORD(lane) < nwords) {
+      const unsigned w = A.dirty[DT_WORD(lane)];
 #ifndef DT_THIN
 #define DT_THIN 4   // keep one dirty triangle in DT_THIN of a dense word per round (2, 4 or 8)
 #endif
 #ifndef DT_DENSE
-#define DT_DENSE 8  // a word is dense when more than this many of its 32 triangles are dirty
+#define DT_DENSE 32  // a word is dense when more than this many of its 32 triangles are dirty (32: no thinning)
 #endif
       const bool dense = __popc(w) > DT_DENSE;
-      const unsigned h = hash32((wbase + lane) * 0x9E3779B9u + round * 0x85EBCA6Bu);
+      const unsigned h = hash32(DT_WORD(lane) * 0x9E3779B9u + round * 0x85EBCA6Bu);
       const unsigned keep = DT_THIN == 2 ? h : (DT_THIN == 4 ? (h & hash32(h)) : (h & hash32(h) & hash32(h ^ 0x5bd1e995u)));
       myword = dense ? (w & keep) : w;
       if (dense && myword == 0u) myword = w & (0u - w);  // keep at least one (lowest) bit so progress is guaranteed
-      A.dirty[wbase + lane] = w & ~myword;
+      A.dirty[DT_WORD(lane)] = w & ~myword;
       deferred = (w & ~myword) != 0u;  // unselected dirty triangles: the loop must not terminate this round
     }
     // inclusive prefix of the per-word popcounts across the warp (lane j <-> word j)
@@ -501,7 +520,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       jsel = min(jsel, 31);
       const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
       const int ex = __shfl_sync(0xffffffffu, excl, jsel);
-      const int t = rank < total ? (wbase + jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
       if (t < 0) continue;
       const int pa = pts[DT_V(t, 0)], pb = pts[DT_V(t, 1)], pc = pts[DT_V(t, 2)];
       // all three neighbours are fetched and tested together (no early exit): the round's critical path is this
@@ -521,18 +540,140 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       any = true;
       cand |= static_cast<unsigned>(found + 1) << (2 * it);
       atomicOr(&A.dirty[t >> 5], 1u << (t & 31));  // stays dirty until it wins
-      const unsigned pri = tag | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0xFFFu) << 14) | static_cast<unsigned>(t);
-      const int u = ucode >> 2, ku = ucode & 3;
+      const unsigned pri = claim_word(tag, t, round);
+      const int u = ucode >> 2;
+#if !DT_CLAIM2
+      const int ku = ucode & 3;
+#endif
       atomicMin(&A.lock[t], pri);
       atomicMin(&A.lock[u], pri);
+#if !DT_CLAIM2
       const unsigned o1 = DT_N(t, (found + 1) % 3), o2 = DT_N(t, (found + 2) % 3);
       const unsigned o3 = DT_N(u, (ku + 1) % 3), o4 = DT_N(u, (ku + 2) % 3);
       if (o1 < kPendingCode) atomicMin(&A.lock[o1 >> 2], pri);
       if (o2 < kPendingCode) atomicMin(&A.lock[o2 >> 2], pri);
       if (o3 < kPendingCode) atomicMin(&A.lock[o3 >> 2], pri);
       if (o4 < kPendingCode) atomicMin(&A.lock[o4 >> 2], pri);
+#endif
     }
     if (!__syncthreads_or(any)) { flips_done = true; break; }
+#if DT_CLAIM2
+    // P2 with TWO-triangle claims.  A flip claims only the two triangles it rewrites, so flips of neighbouring quads win in
+    // the same round (tools/prototypes/dt_claims.py: a third of the rounds with > 100 illegal edges).  What the
+    // six-triangle claim protected were the back links: a flip re-points the slots of its four outer neighbours, and a
+    // neighbour that flips in the same round is being rewritten itself.  Hence two steps:
+    //   P2a  every winner replaces the claim words of its two triangles by a POSTING (same round tag, bit 25 clear):
+    //        which triangle of the pair this is, its slot of the old diagonal, and its partner.  Other proposers still
+    //        comparing claim words are not disturbed: a posting equals nobody's claim (bit 25), and both words were
+    //        already lost to them.  The next round's claims (smaller tag) overwrite postings like any stale claim.
+    //   P2b  every winner rewrites its two triangles; across each outer edge it reads the neighbour's lock word: a
+    //        posting of this round means the neighbour flipped too -- the edge's new owner on that side follows from the
+    //        posting, and the neighbour learns mine the same way -- else the unchanged neighbour's slot is re-pointed.
+    unsigned wins = 0;
+    it = 0;
+    for (int base = 0; base < total; base += 32, ++it) {
+      const int sel = (cand >> (2 * it)) & 3;
+      if (!__any_sync(0xffffffffu, sel != 0)) continue;  // warp-uniform: the shuffles below need every lane
+      const int rank = base + lane;
+      int jsel = 0;
+#pragma unroll
+      for (int sstep = 16; sstep > 0; sstep >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, incl, jsel + sstep - 1);
+        if (v <= rank) jsel += sstep;
+      }
+      jsel = min(jsel, 31);
+      const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
+      const int ex = __shfl_sync(0xffffffffu, excl, jsel);
+      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      if (!sel) continue;
+      const int k = sel - 1;
+      const unsigned pri = claim_word(tag, t, round);
+      const unsigned lt = A.lock[t];
+      const unsigned ucode = DT_N(t, k);
+      const int u = ucode < kPendingCode ? static_cast<int>(ucode >> 2) : t, ku = ucode & 3;  // (a hull marker is no index)
+      const unsigned lu = A.lock[u];
+      if (lt != pri || ucode >= kPendingCode || lu != pri) continue;
+      wins |= 1u << it;
+      A.lock[t] = tag | static_cast<unsigned>(k << 14) | static_cast<unsigned>(u);
+      A.lock[u] = tag | kPostIsU | static_cast<unsigned>(ku << 14) | static_cast<unsigned>(t);
+    }
+    __syncthreads();
+    // Winners are sparse among a warp's proposals (a few lanes per 32-triangle iteration), and the rewrite is the longest
+    // straight-line piece of a round: gather them into dense lanes first -- 32 at a time, across iterations -- so the
+    // rewrite is issued once per 32 winners instead of once per iteration.
+    auto rewrite = [&](int tk) {   // tk = (t << 2 | slot of the illegal edge), or -1
+      if (tk < 0) return;
+      const int t = tk >> 2, k = tk & 3;
+      // (my two triangles are mine alone in this step: neighbours that flipped read my posting, not my slots)
+      const unsigned ucode = DT_N(t, k);
+      const int u = static_cast<int>(ucode >> 2), ku = ucode & 3;
+      unsigned n_ca = DT_N(t, nx3(k)), n_ab = DT_N(t, pv3(k));
+      unsigned n_bd = DT_N(u, nx3(ku)), n_dc = DT_N(u, pv3(ku));
+      const unsigned short a = DT_V(t, k), bq = DT_V(t, nx3(k)), c = DT_V(t, pv3(k));
+      const unsigned short d = DT_V(u, ku);
+      auto across = [&](unsigned code, unsigned mine) -> unsigned {   // the neighbour's side of an outer edge after this round
+        if (code >= kPendingCode) return code;                       // hull edge
+        const unsigned x = code >> 2, sx = code & 3;
+        const unsigned L = A.lock[x];
+        if ((L & (0xFC000000u | kClaimBit)) == tag) {                // a posting of this round: x flipped too
+          const unsigned partner = L & 0x3FFFu;
+          // sx is x's slot kd+1 or kd+2 (kd = its slot of the old diagonal, L[15:14]); second <=> sx == (kd + 2) % 3
+          const bool second = (0x214u >> (((L >> 12) & 0xCu) | sx)) & 1u;
+          // first triangle of a pair (a,b,c | d): slot k+1 = edge (c,a) -> (partner, 1); slot k+2 = edge (a,b) -> (itself, 2)
+          // second triangle:                      slot ku+1 = edge (b,d) -> (partner, 0); slot ku+2 = edge (d,c) -> (itself, 0)
+          if (L & kPostIsU) return ((second ? x : partner) << 2) | 0u;
+          return second ? ((x << 2) | 2u) : ((partner << 2) | 1u);
+        }
+        DT_N(x, sx) = static_cast<unsigned short>(mine);             // unchanged: re-point its slot at me
+        return code;
+      };
+      n_bd = across(n_bd, (t << 2) | 0);
+      n_ab = across(n_ab, (t << 2) | 2);
+      n_dc = across(n_dc, (u << 2) | 0);
+      n_ca = across(n_ca, (u << 2) | 1);
+      // t <- (a,b,d), u <- (a,d,c); the new diagonal (a,d) is opposite v1 in t and opposite v2 in u
+      A.v0[t] = a; A.v1[t] = bq; A.v2[t] = d;
+      A.n0[t] = static_cast<unsigned short>(n_bd); A.n1[t] = static_cast<unsigned short>((u << 2) | 2);
+      A.n2[t] = static_cast<unsigned short>(n_ab);
+      A.v0[u] = a; A.v1[u] = d; A.v2[u] = c;
+      A.n0[u] = static_cast<unsigned short>(n_dc); A.n1[u] = static_cast<unsigned short>(n_ca);
+      A.n2[u] = static_cast<unsigned short>((t << 2) | 1);
+      atomicOr(&A.dirty[u >> 5], 1u << (u & 31));  // t's bit is already set
+    };
+    int pend = -1, npend = 0;   // gathered winners: lane j < npend holds one
+    it = 0;
+    for (int base = 0; base < total; base += 32, ++it) {
+      const bool win = (wins >> it) & 1u;
+      const unsigned wm = __ballot_sync(0xffffffffu, win);
+      if (!wm) continue;
+      const int rank = base + lane;
+      int jsel = 0;
+#pragma unroll
+      for (int sstep = 16; sstep > 0; sstep >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, incl, jsel + sstep - 1);
+        if (v <= rank) jsel += sstep;
+      }
+      jsel = min(jsel, 31);
+      const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
+      const int ex = __shfl_sync(0xffffffffu, excl, jsel);
+      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      const int mine = win ? ((t << 2) | (static_cast<int>((cand >> (2 * it)) & 3) - 1)) : -1;
+      const int cnt = __popc(wm);
+      const int j = lane - npend;                                   // lanes npend.. take this iteration's winners in order
+      const int got = __shfl_sync(0xffffffffu, mine, (j >= 0 && j < cnt) ? nth_set_bit(wm, j) : 0);
+      if (j >= 0 && j < cnt) pend = got;
+      if (npend + cnt >= 32) {
+        rewrite(pend);
+        const int j2 = lane + 32 - npend;                           // the winners that did not fit start the next set
+        const int got2 = __shfl_sync(0xffffffffu, mine, j2 < cnt ? nth_set_bit(wm, j2) : 0);
+        pend = j2 < cnt ? got2 : -1;
+        npend += cnt - 32;
+      } else {
+        npend += cnt;
+      }
+    }
+    if (npend > 0) rewrite(lane < npend ? pend : -1);
+#else
     // P2: winners flip
     it = 0;
     for (int base = 0; base < total; base += 32, ++it) {
@@ -549,7 +690,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       jsel = min(jsel, 31);
       const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
       const int ex = __shfl_sync(0xffffffffu, excl, jsel);
-      const int t = rank < total ? (wbase + jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
       if (!sel) continue;
       const int k = sel - 1;
       const unsigned pri = tag | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0xFFFu) << 14) | static_cast<unsigned>(t);
@@ -581,6 +722,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       link_back(A, n_ca, (u << 2) | 1);
       atomicOr(&A.dirty[u >> 5], 1u << (u & 31));  // t's bit is already set
     }
+#endif
 #ifndef DT_TAIL
 #define DT_TAIL 10   // enter the single-warp tail when at most this many threads proposed a flip (0 = never)
 #endif
@@ -704,6 +846,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
   }
 #undef DT_V
 #undef DT_N
+#undef DT_WORD
 
   if (dbg && tid == 0) dbg[b * 8 + 0] = (int)((clock64() - clk0) >> 4);
   // A loop that ran into its safety bound (flips: max_rounds; pockets: 4R + 64 rounds) leaves a mesh that is not
