@@ -17,6 +17,7 @@
 namespace fovea {
 
 constexpr int kRasThreads = 256;
+constexpr int kRasMode = 0;        // default of FOVEA_RAS_MODE (see fovea_locate_raster)
 constexpr int kRasTileMax = 1024;   // bounding boxes up to this many pixels are swept pixel by pixel (measured 32 .. 2048: flat,
                                     // 356 us at 1024 against 378 at 2048 and 396 at 320; FOVEA_RAS_TILE_MAX overrides)
 
@@ -133,6 +134,210 @@ raster_locate_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ 
   }
 }
 
+// The same map with NO per-pixel tests: every triangle is handled like the large ones above -- a lane takes a row of the
+// bounding box, solves the three edge inequalities for the row's span in closed form and stores it -- only with LPT
+// lanes per triangle (rows ymin + l, + LPT, ...) so that the typical 13-row triangle keeps its lanes busy.  Per
+// (triangle, row): three float-quotient divisions with exact fix-up and ~4 stores, against 2 x 8 lane-steps of the sweep.
+__device__ __forceinline__ void store_span_short(uint16_t* row, int lo, int hi, unsigned id) {
+  if (hi - lo >= 23) { store_span(row, lo, hi, id); return; }
+  int x = lo;
+  if (x & 1) row[x++] = static_cast<uint16_t>(id);
+  const unsigned v2 = id | (id << 16);
+  for (; x < hi; x += 2) *reinterpret_cast<unsigned*>(row + x) = v2;
+  if (x == hi) row[x] = static_cast<uint16_t>(id);
+}
+
+template <int LPT>
+__global__ void __launch_bounds__(kRasThreads)
+raster_span_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
+                   const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, int hw, int H, int W, int cap, int tcap,
+                   int tile_max) {
+  constexpr int TPW = 32 / LPT;   // triangles per warp
+  const int b = blockIdx.y;
+  const int T = ntri[b];
+  uint16_t* lb = loc + static_cast<size_t>(b) * H * W;
+  if (T <= 0) {  // no mesh for this frame (see fovea_delaunay): nothing owns anything
+    const unsigned none = 0x8000u | static_cast<unsigned>(hw);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kRasThreads + threadIdx.x; i < static_cast<size_t>(H) * W;
+         i += static_cast<size_t>(gridDim.x) * kRasThreads)
+      lb[i] = static_cast<uint16_t>(none);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = (blockIdx.x * (kRasThreads / 32) + warp) * TPW;
+  if (t0 >= T) return;
+  const int sub = lane / LPT, sl = lane % LPT;
+  const int t = t0 + sub;
+  const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
+                            trirec + static_cast<size_t>(b) * tcap, t, T);
+  const int bh = R.ymax - R.ymin + 1, bw = R.xmax - R.xmin + 1;
+  const bool large = R.live && bh * bw > tile_max;
+  auto row_span = [&](const int (&A)[3], const int (&Bx)[3], const int (&Cc)[3], int y, int& lo, int& hi) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = A[i] * y + Cc[i];                                       // the pixel is inside iff B x + k >= 0
+      if (Bx[i] > 0) lo = max(lo, -floor_div_pos(k, Bx[i]));                // x >= ceil(-k / B) = -floor(k / B)
+      else if (Bx[i] < 0) hi = min(hi, floor_div_pos(k, -Bx[i]));           // x <= floor(k / -B)
+      else if (k < 0) hi = -1;                                              // the whole row is outside
+    }
+  };
+  if (R.live && !large) {
+    const int A[3] = {R.A0, R.A1, R.A2}, Bx[3] = {R.B0, R.B1, R.B2}, Cc[3] = {R.C0, R.C1, R.C2};
+    for (int y = R.ymin + sl; y <= R.ymax; y += LPT) {
+      int lo = R.xmin, hi = R.xmax;
+      row_span(A, Bx, Cc, y, lo, hi);
+      if (lo <= hi) store_span_short(lb + static_cast<size_t>(y) * W, lo, hi, static_cast<unsigned>(t));
+    }
+  }
+  // the large ones: whole warp, one after the other (their parameters come from the first lane of their group)
+  unsigned leaders = 0;
+#pragma unroll
+  for (int g = 0; g < TPW; ++g) leaders |= 1u << (g * LPT);
+  unsigned todo = __ballot_sync(0xffffffffu, large) & leaders;
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int A[3] = {__shfl_sync(0xffffffffu, R.A0, src), __shfl_sync(0xffffffffu, R.A1, src), __shfl_sync(0xffffffffu, R.A2, src)};
+    const int Bx[3] = {__shfl_sync(0xffffffffu, R.B0, src), __shfl_sync(0xffffffffu, R.B1, src), __shfl_sync(0xffffffffu, R.B2, src)};
+    const int Cc[3] = {__shfl_sync(0xffffffffu, R.C0, src), __shfl_sync(0xffffffffu, R.C1, src), __shfl_sync(0xffffffffu, R.C2, src)};
+    const int ymin = __shfl_sync(0xffffffffu, R.ymin, src), ymax = __shfl_sync(0xffffffffu, R.ymax, src);
+    const int xmin = __shfl_sync(0xffffffffu, R.xmin, src), xmax = __shfl_sync(0xffffffffu, R.xmax, src);
+    const unsigned id = static_cast<unsigned>(t0 + src / LPT);
+    for (int y = ymin + lane; y <= ymax; y += 32) {
+      int lo = xmin, hi = xmax;
+      row_span(A, Bx, Cc, y, lo, hi);
+      if (lo <= hi) store_span(lb + static_cast<size_t>(y) * W, lo, hi, id);
+    }
+  }
+}
+
+// ---- Marker raster.  On a canvas the triangulation covers (forced corners: the convex hull IS the canvas) the spans of
+// one row partition it, so the map is fixed by where every span STARTS: raster_mark_kernel stores the triangle id at the
+// first pixel of each (triangle, row) span and sets that pixel's bit in a start bitmap; raster_fill_rows_kernel then
+// sweeps every row once, carrying the last started id forward, with coalesced 16-byte loads and stores.  One lane takes
+// one triangle and walks its rows with an exact integer DDA (quotient + remainder of every edge's crossing, advanced by
+// one addition and one conditional carry per row -- two integer divisions per edge per TRIANGLE instead of one per
+// row); ~35 lane-instructions and one 2-byte store per (triangle, row), against ~8 per PIXEL tested by the sweep.
+constexpr int kMarkCoopRows = 64;   // taller triangles are taken by the whole warp, rows strided by 32 (direct divisions)
+
+__device__ __forceinline__ void mark_start(uint16_t* loc, unsigned* bits, size_t lin, unsigned id) {   // lin: pixel index in the batch
+  loc[lin] = static_cast<uint16_t>(id);
+  atomicOr(bits + (lin >> 5), 1u << (lin & 31));
+}
+
+struct EdgeDda {   // floor((A y + C) / m), m = |B| (1 when B == 0), as quotient + remainder, advanced row by row
+  int q, r, dq, dr, m;
+  __device__ __forceinline__ void init(int A, int B, int C, int y) {
+    m = B > 0 ? B : (B < 0 ? -B : 1);
+    const int k = A * y + C;
+    q = k / m; r = k - q * m;
+    if (r < 0) { r += m; --q; }
+    dq = A / m; dr = A - dq * m;
+    if (dr < 0) { dr += m; --dq; }
+  }
+  __device__ __forceinline__ void step() {
+    q += dq; r += dr;
+    if (r >= m) { r -= m; ++q; }
+  }
+};
+
+__global__ void __launch_bounds__(kRasThreads)
+raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
+                   const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ bits, int H, int W,
+                   int cap, int tcap) {
+  const int b = blockIdx.y;
+  const int T = ntri[b];
+  if (T <= 0) return;  // no mesh for this frame: no starts, the row sweep leaves "no value" everywhere
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * kRasThreads + threadIdx.x;
+  if (t - lane >= T) return;
+  const size_t img = static_cast<size_t>(b) * H * W;
+  const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
+                            trirec + static_cast<size_t>(b) * tcap, t, T);
+  const bool large = R.live && R.ymax - R.ymin + 1 > kMarkCoopRows;
+  if (R.live && !large) {
+    EdgeDda e0, e1, e2;
+    e0.init(R.A0, R.B0, R.C0, R.ymin); e1.init(R.A1, R.B1, R.C1, R.ymin); e2.init(R.A2, R.B2, R.C2, R.ymin);
+    size_t rowoff = img + static_cast<size_t>(R.ymin) * W;
+    for (int y = R.ymin; y <= R.ymax; ++y, rowoff += W) {
+      // B > 0: x >= -floor(k / B);  B < 0: x <= floor(k / -B);  B == 0: the row is inside iff k >= 0 (q = k)
+      int lo = R.xmin, hi = R.xmax;
+      lo = max(lo, R.B0 > 0 ? -e0.q : lo); hi = min(hi, R.B0 < 0 ? e0.q : (R.B0 == 0 && e0.q < 0 ? -1 : hi));
+      lo = max(lo, R.B1 > 0 ? -e1.q : lo); hi = min(hi, R.B1 < 0 ? e1.q : (R.B1 == 0 && e1.q < 0 ? -1 : hi));
+      lo = max(lo, R.B2 > 0 ? -e2.q : lo); hi = min(hi, R.B2 < 0 ? e2.q : (R.B2 == 0 && e2.q < 0 ? -1 : hi));
+      if (lo <= hi) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
+      e0.step(); e1.step(); e2.step();
+    }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, large);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int A[3] = {__shfl_sync(0xffffffffu, R.A0, src), __shfl_sync(0xffffffffu, R.A1, src), __shfl_sync(0xffffffffu, R.A2, src)};
+    const int Bx[3] = {__shfl_sync(0xffffffffu, R.B0, src), __shfl_sync(0xffffffffu, R.B1, src), __shfl_sync(0xffffffffu, R.B2, src)};
+    const int Cc[3] = {__shfl_sync(0xffffffffu, R.C0, src), __shfl_sync(0xffffffffu, R.C1, src), __shfl_sync(0xffffffffu, R.C2, src)};
+    const int ymin = __shfl_sync(0xffffffffu, R.ymin, src), ymax = __shfl_sync(0xffffffffu, R.ymax, src);
+    const int xmin = __shfl_sync(0xffffffffu, R.xmin, src), xmax = __shfl_sync(0xffffffffu, R.xmax, src);
+    const unsigned id = static_cast<unsigned>(t - lane + src);
+    for (int y = ymin + lane; y <= ymax; y += 32) {
+      int lo = xmin, hi = xmax;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int k = A[i] * y + Cc[i];
+        if (Bx[i] > 0) lo = max(lo, -floor_div_pos(k, Bx[i]));
+        else if (Bx[i] < 0) hi = min(hi, floor_div_pos(k, -Bx[i]));
+        else if (k < 0) hi = -1;
+      }
+      if (lo <= hi) mark_start(loc, bits, img + static_cast<size_t>(y) * W + lo, id);
+    }
+  }
+}
+
+// One warp per canvas row: 256 pixels per step (8 per lane, one 16-byte load + store), the id of the last span start
+// carried from lane to lane by a 5-step shuffle scan and from step to step in a register.
+__global__ void __launch_bounds__(256)
+raster_fill_rows_kernel(uint16_t* __restrict__ loc, const unsigned char* __restrict__ bits, long long rows, int W, unsigned none) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  uint16_t* lr = loc + row * W;
+  const unsigned char* br = bits + row * (W / 8);
+  constexpr unsigned kNoVal = 0xFFFFFFFFu;
+  unsigned carry = none;
+  for (int x0 = 0; x0 < W; x0 += 256) {
+    const int x = x0 + lane * 8;
+    const bool act = x < W;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    unsigned f = 0;
+    if (act) {
+      f = br[x >> 3];
+      v = *reinterpret_cast<const uint4*>(lr + x);
+    }
+    unsigned px[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+    unsigned last = kNoVal;  // the id started last inside my 8 pixels
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if ((f >> j) & 1u) last = px[j];
+    unsigned inc = last;    // inclusive scan: the last start at or before my pixels (within this step)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o && inc == kNoVal) inc = y;
+    }
+    unsigned cur = __shfl_up_sync(0xffffffffu, inc, 1);   // the last start strictly before my pixels
+    if (lane == 0 || cur == kNoVal) cur = carry;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((f >> j) & 1u) cur = px[j];
+      px[j] = cur;
+    }
+    if (act)
+      *reinterpret_cast<uint4*>(lr + x) = make_uint4(px[0] | (px[1] << 16), px[2] | (px[3] << 16), px[4] | (px[5] << 16), px[6] | (px[7] << 16));
+    const unsigned tail = __shfl_sync(0xffffffffu, inc, 31);
+    if (tail != kNoVal) carry = tail;
+  }
+}
+
 // u = int(((gx+1)/2)*(W-1)), v = int(((gy+1)/2)*(H-1))  -- models/models.py:644-645, fp32 op for op (as inverse.cu)
 __device__ __forceinline__ int raster_target(float g, int size) {
   const float f = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), static_cast<float>(size - 1));
@@ -170,9 +375,13 @@ __global__ void fill_none_kernel(uint4* __restrict__ loc, size_t n16, unsigned n
 
 using namespace fovea;
 
+extern "C" int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W) {
+  return (static_cast<int64_t>(B) * H * W + 31) / 32 * 4;   // one span-start bit per pixel
+}
+
 extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
                                    const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap,
-                                   int tcap, int prefill, uint16_t* loc, fovea_stream_t stream) {
+                                   int tcap, int prefill, uint16_t* loc, void* workspace, fovea_stream_t stream) {
   FOVEA_REQUIRE(pts && mesh && trirec && ntri && loc, "fovea_locate_raster: null pointer");
   FOVEA_REQUIRE((grid == nullptr) == (winner == nullptr), "fovea_locate_raster: grid and winner go together");
   FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && cap > 0 && tcap > 0, "fovea_locate_raster: bad sizes");
@@ -188,8 +397,33 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
     const unsigned none = 0x8000u | static_cast<unsigned>(hw);
     fill_none_kernel<<<kNumSMs * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(loc), n16, none | (none << 16));
   }
-  raster_locate_kernel<<<dim3(ceil_div(tcap, 4 * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(
-      pts, reinterpret_cast<const uint4*>(mesh), static_cast<const TriRec*>(trirec), ntri, loc, hw, H, W, cap, tcap, tile_max);
+  // FOVEA_RAS_MODE (read per call, so one process can compare): 0 = the pixel sweep, 64 = span-start markers + row sweep, 1 / 2 / 4 / 8 / 16 / 32 = row spans with that many
+  // lanes per triangle
+  int mode = kRasMode;
+  if (const char* e = getenv("FOVEA_RAS_MODE")) mode = atoi(e);
+  const uint4* mesh4 = reinterpret_cast<const uint4*>(mesh);
+  const TriRec* recs = static_cast<const TriRec*>(trirec);
+#define FOVEA_RAS_SPAN(LPT)                                                                                      \
+  raster_span_kernel<LPT><<<dim3(ceil_div(tcap, (32 / LPT) * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(       \
+      pts, mesh4, recs, ntri, loc, hw, H, W, cap, tcap, tile_max)
+  if (mode == 64 && workspace && !prefill) {   // markers + row sweep (needs a canvas the mesh covers: every row starts a span)
+    const size_t npix = static_cast<size_t>(B) * H * W;
+    FOVEA_CUDA(cudaMemsetAsync(workspace, 0, (npix + 31) / 32 * 4, s));
+    raster_mark_kernel<<<dim3(ceil_div(tcap, kRasThreads), B), kRasThreads, 0, s>>>(
+        pts, mesh4, recs, ntri, loc, static_cast<unsigned*>(workspace), H, W, cap, tcap);
+    const long long rows = static_cast<long long>(B) * H;
+    raster_fill_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
+        loc, static_cast<const unsigned char*>(workspace), rows, W, 0x8000u | static_cast<unsigned>(hw));
+  } else if (mode == 1) FOVEA_RAS_SPAN(1);
+  else if (mode == 2) FOVEA_RAS_SPAN(2);
+  else if (mode == 4) FOVEA_RAS_SPAN(4);
+  else if (mode == 8) FOVEA_RAS_SPAN(8);
+  else if (mode == 16) FOVEA_RAS_SPAN(16);
+  else if (mode == 32) FOVEA_RAS_SPAN(32);
+  else
+    raster_locate_kernel<<<dim3(ceil_div(tcap, 4 * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(
+        pts, mesh4, recs, ntri, loc, hw, H, W, cap, tcap, tile_max);
+#undef FOVEA_RAS_SPAN
   if (grid) {
     const int total = B * (hw + 4);
     stamp_nodes_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(reinterpret_cast<const float2*>(grid), winner,

@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 
 class FoveaError(RuntimeError):
@@ -53,7 +53,8 @@ PROTOTYPES = {
     "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "fovea_locate_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "fovea_locate_raster_workspace_bytes": (_i64, [_i, _i, _i]),
+    "fovea_locate_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "fovea_inverse_mask_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "fovea_inverse_mask": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 11
+#define FOVEA_ABI_VERSION 12
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -229,17 +229,23 @@ int fovea_triangle_setup(const int32_t* pts, const int32_t* src, const uint16_t*
 int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t* ntri, const int32_t* hints, int B,
                         int h, int w, int H, int W, int tcap, uint16_t* loc, fovea_stream_t stream);
 
-/* The same per-pixel source map as fovea_locate_pixels, computed by RASTERISING the mesh (one warp per triangle, closed-form
- * row spans from the setup records' exact integer edge functions -- the predicate fovea_locate_pixels tests pixel by
- * pixel, so the two maps are identical) and then stamping the pixels that received a node from the nodes themselves.
- * Needs no walk-start hints and does not read the winner map except at the 6 400 node targets.
+/* The same per-pixel source map as fovea_locate_pixels, computed by RASTERISING the mesh from the setup records' exact
+ * integer edge functions -- the predicate fovea_locate_pixels tests pixel by pixel, so the two maps are identical --
+ * and then stamping the pixels that received a node from the nodes themselves.  Needs no walk-start hints and does not
+ * read the winner map except at the 6 400 node targets.
+ *   On a canvas the triangulation covers (prefill == 0) and with a workspace: one lane per triangle walks its rows with an
+ *   exact integer DDA and marks where each (triangle, row) span STARTS; one sweep per row then carries the last started
+ *   id forward with coalesced 16-byte accesses.  Otherwise (or with FOVEA_RAS_MODE=0): every triangle's bounding box is
+ *   swept pixel by pixel, the few huge hull triangles row span by row span.
  *   grid, winner : the sampling grid [B,h,w,2] and fovea_grid_inv_scatter's map; both NULL when no pixel carries a node
  *                  (Interp2D on an arbitrary point set)
  *   prefill != 0 : first mark every pixel "no value" -- required when the triangulation does not cover the canvas (no
- *                  forced corners: 'BI' sites, arbitrary point sets);  W must be a multiple of 8 */
+ *                  forced corners: 'BI' sites, arbitrary point sets);  W must be a multiple of 8
+ *   workspace    : fovea_locate_raster_workspace_bytes(B, H, W) bytes (the span-start bitmap), or NULL */
+int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W);
 int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
                         const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap, int tcap,
-                        int prefill, uint16_t* loc, fovea_stream_t stream);
+                        int prefill, uint16_t* loc, void* workspace, fovea_stream_t stream);
 
 /* A8 + A9 + A10 fused: F.grid_sample(pred, grid_inv) + NaN mask (models/models.py:935-938), the per-sample
  * fillMissingValues_tensor(..., 'tri') = Interp2D barycentric gather (models/models.py:939-940,
