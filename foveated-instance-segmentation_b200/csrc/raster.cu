@@ -17,7 +17,7 @@
 namespace fovea {
 
 constexpr int kRasThreads = 256;
-constexpr int kRasMode = 0;        // default of FOVEA_RAS_MODE (see fovea_locate_raster)
+constexpr int kRasMode = 64;       // default of FOVEA_RAS_MODE (see fovea_locate_raster)
 constexpr int kRasTileMax = 1024;   // bounding boxes up to this many pixels are swept pixel by pixel (measured 32 .. 2048: flat,
                                     // 356 us at 1024 against 378 at 2048 and 396 at 320; FOVEA_RAS_TILE_MAX overrides)
 
@@ -42,6 +42,7 @@ __device__ __forceinline__ void store_span(uint16_t* row, int lo, int hi, unsign
 struct RasTri {
   int A0, B0, C0, A1, B1, C1, A2, B2, C2;   // edge functions with the tie bit already subtracted: inside <=> all >= 0
   int ymin, ymax, xmin, xmax;
+  int p0, p1, p2;                           // the vertices, packed (row << 16 | column)
   bool live;
 };
 
@@ -51,12 +52,14 @@ __device__ __forceinline__ RasTri ras_load(const int32_t* __restrict__ pb, const
   R.live = t < T;
   R.A0 = R.B0 = R.C0 = R.A1 = R.B1 = R.C1 = R.A2 = R.B2 = R.C2 = 0;
   R.ymin = R.xmin = 0; R.ymax = R.xmax = -1;
+  R.p0 = R.p1 = R.p2 = -1;
   if (!R.live) return R;
   const uint4* r = reinterpret_cast<const uint4*>(recs + t);
   const uint4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
   const uint4 mq = __ldg(mesh + t);
   if (q2.w == 0u) { R.live = false; return R; }  // degenerate triangle (host meshes only): owns nothing
   const int p0 = __ldg(pb + (mq.x & 0xFFFFu)), p1 = __ldg(pb + (mq.x >> 16)), p2 = __ldg(pb + (mq.y & 0xFFFFu));
+  R.p0 = p0; R.p1 = p1; R.p2 = p2;
   R.ymin = min(min(p0 >> 16, p1 >> 16), p2 >> 16); R.ymax = max(max(p0 >> 16, p1 >> 16), p2 >> 16);
   R.xmin = min(min(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF); R.xmax = max(max(p0 & 0xFFFF, p1 & 0xFFFF), p2 & 0xFFFF);
   const unsigned m = q2.z >> 16;
@@ -218,22 +221,47 @@ raster_span_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
 // one triangle and walks its rows with an exact integer DDA (quotient + remainder of every edge's crossing, advanced by
 // one addition and one conditional carry per row -- two integer divisions per edge per TRIANGLE instead of one per
 // row); ~35 lane-instructions and one 2-byte store per (triangle, row), against ~8 per PIXEL tested by the sweep.
-constexpr int kMarkCoopRows = 64;   // taller triangles are taken by the whole warp, rows strided by 32 (direct divisions)
+constexpr int kMarkCoopRows = 64;   // taller triangles are ALWAYS taken by the whole warp, rows strided by 32 (direct divisions)
+constexpr int kMarkThreads = 128;
 
 __device__ __forceinline__ void mark_start(uint16_t* loc, unsigned* bits, size_t lin, unsigned id) {   // lin: pixel index in the batch
   loc[lin] = static_cast<uint16_t>(id);
   atomicOr(bits + (lin >> 5), 1u << (lin & 31));
 }
 
+// At a vertex the tie rule is not exclusive: several of the triangles around a site can own its pixel (harmless for the
+// sweep -- the pixel carries a node and is stamped afterwards -- but two span STARTS on one pixel would lose one).
+// A span made only of its triangle's own vertices (an apex, or a one-pixel horizontal edge) carries no information: skip.
+__device__ __forceinline__ bool only_vertices_pts(int p0, int p1, int p2, int y, int lo, int hi) {
+  if (hi - lo > 2) return false;
+  auto in = [&](int p) { return (p >> 16) == y && (p & 0xFFFF) >= lo && (p & 0xFFFF) <= hi ? 1 : 0; };
+  return in(p0) + in(p1) + in(p2) == hi - lo + 1;
+}
+__device__ __forceinline__ bool only_vertices(const RasTri& R, int y, int lo, int hi) {
+  return only_vertices_pts(R.p0, R.p1, R.p2, y, lo, hi);
+}
+
 struct EdgeDda {   // floor((A y + C) / m), m = |B| (1 when B == 0), as quotient + remainder, advanced row by row
   int q, r, dq, dr, m;
+  // floor(a / m) and the remainder, m > 0: float quotient + one fix-up step, verified -- the remainder is formed modulo
+  // 2^32 from the estimate (off by at most |a / m| * 2^-22 <= 2^8 units, i.e. the true remainder is within 2^8 * m < 2^23
+  // of [0, m): no wrap) and an estimate that one step does not repair falls back to the integer division.
+  static __device__ __forceinline__ void fdiv(int a, int m, int& q, int& r) {
+    q = __float2int_rd(__fdividef(static_cast<float>(a), static_cast<float>(m)));
+    r = static_cast<int>(static_cast<unsigned>(a) - static_cast<unsigned>(q) * static_cast<unsigned>(m));
+    if (r < 0) { r += m; --q; }
+    else if (r >= m) { r -= m; ++q; }
+    if (r < 0 || r >= m) {   // (far from an edge's end points its crossing can leave the float quotient's exact range)
+      q = a / m; r = a - q * m;
+      if (r < 0) { r += m; --q; }
+    }
+  }
   __device__ __forceinline__ void init(int A, int B, int C, int y) {
     m = B > 0 ? B : (B < 0 ? -B : 1);
     const int k = A * y + C;
-    q = k / m; r = k - q * m;
-    if (r < 0) { r += m; --q; }
-    dq = A / m; dr = A - dq * m;
-    if (dr < 0) { dr += m; --dq; }
+    if (B == 0) { q = k; r = 0; dq = A; dr = 0; return; }   // (k itself can be ~2^30: no division)
+    fdiv(k, m, q, r);
+    fdiv(A, m, dq, dr);
   }
   __device__ __forceinline__ void step() {
     q += dq; r += dr;
@@ -241,20 +269,32 @@ struct EdgeDda {   // floor((A y + C) / m), m = |B| (1 when B == 0), as quotient
   }
 };
 
-__global__ void __launch_bounds__(kRasThreads)
+__global__ void __launch_bounds__(kMarkThreads)
 raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
-                   const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ bits, int H, int W,
-                   int cap, int tcap) {
+                   const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ bits,
+                   unsigned* __restrict__ queue, int H, int W, int cap, int tcap) {
   const int b = blockIdx.y;
   const int T = ntri[b];
   if (T <= 0) return;  // no mesh for this frame: no starts, the row sweep leaves "no value" everywhere
   const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * kRasThreads + threadIdx.x;
+  const int t = blockIdx.x * kMarkThreads + threadIdx.x;
   if (t - lane >= T) return;
   const size_t img = static_cast<size_t>(b) * H * W;
   const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
                             trirec + static_cast<size_t>(b) * tcap, t, T);
-  const bool large = R.live && R.ymax - R.ymin + 1 > kMarkCoopRows;
+  // A warp's lanes walk their triangles in lockstep, so the tallest one sets the price (~45 instructions per row for
+  // the whole warp) -- while a queued triangle costs a warp of raster_mark_tall_kernel ~300.  The height limit above
+  // which triangles leave the lane path is the cheapest of a few candidates under that model.
+  const int bh = R.live ? R.ymax - R.ymin + 1 : 0;
+  int limit = kMarkCoopRows, best = 0x7fffffff;
+#pragma unroll
+  for (int cand = kMarkCoopRows; cand >= 8; cand = cand * 3 / 4) {   // 64, 48, 36, 27, 20, 15, 11, 8
+    const int above = __popc(__ballot_sync(0xffffffffu, bh > cand));
+    const int tallest = __reduce_max_sync(0xffffffffu, bh > cand ? 0 : bh);
+    const int cost = tallest * 45 + above * 300;
+    if (cost < best) { best = cost; limit = cand; }
+  }
+  const bool large = R.live && bh > limit;
   if (R.live && !large) {
     EdgeDda e0, e1, e2;
     e0.init(R.A0, R.B0, R.C0, R.ymin); e1.init(R.A1, R.B1, R.C1, R.ymin); e2.init(R.A2, R.B2, R.C2, R.ymin);
@@ -265,30 +305,49 @@ raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
       lo = max(lo, R.B0 > 0 ? -e0.q : lo); hi = min(hi, R.B0 < 0 ? e0.q : (R.B0 == 0 && e0.q < 0 ? -1 : hi));
       lo = max(lo, R.B1 > 0 ? -e1.q : lo); hi = min(hi, R.B1 < 0 ? e1.q : (R.B1 == 0 && e1.q < 0 ? -1 : hi));
       lo = max(lo, R.B2 > 0 ? -e2.q : lo); hi = min(hi, R.B2 < 0 ? e2.q : (R.B2 == 0 && e2.q < 0 ? -1 : hi));
-      if (lo <= hi) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
+      if (lo <= hi && !only_vertices(R, y, lo, hi)) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
       e0.step(); e1.step(); e2.step();
     }
   }
-  unsigned todo = __ballot_sync(0xffffffffu, large);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int A[3] = {__shfl_sync(0xffffffffu, R.A0, src), __shfl_sync(0xffffffffu, R.A1, src), __shfl_sync(0xffffffffu, R.A2, src)};
-    const int Bx[3] = {__shfl_sync(0xffffffffu, R.B0, src), __shfl_sync(0xffffffffu, R.B1, src), __shfl_sync(0xffffffffu, R.B2, src)};
-    const int Cc[3] = {__shfl_sync(0xffffffffu, R.C0, src), __shfl_sync(0xffffffffu, R.C1, src), __shfl_sync(0xffffffffu, R.C2, src)};
-    const int ymin = __shfl_sync(0xffffffffu, R.ymin, src), ymax = __shfl_sync(0xffffffffu, R.ymax, src);
-    const int xmin = __shfl_sync(0xffffffffu, R.xmin, src), xmax = __shfl_sync(0xffffffffu, R.xmax, src);
-    const unsigned id = static_cast<unsigned>(t - lane + src);
-    for (int y = ymin + lane; y <= ymax; y += 32) {
-      int lo = xmin, hi = xmax;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int k = A[i] * y + Cc[i];
-        if (Bx[i] > 0) lo = max(lo, -floor_div_pos(k, Bx[i]));
-        else if (Bx[i] < 0) hi = min(hi, floor_div_pos(k, -Bx[i]));
-        else if (k < 0) hi = -1;
+  // the tall ones go to a queue: raster_mark_tall_kernel spreads them over the whole device, one warp each (the corner
+  // fans -- dozens of consecutive triangles a thousand rows tall -- would otherwise be walked one after the other by
+  // the single warp that drew them)
+  const unsigned tall = __ballot_sync(0xffffffffu, large);
+  if (tall) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(queue, static_cast<unsigned>(__popc(tall)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (large) queue[4 + base + __popc(tall & ((1u << lane) - 1u))] = (static_cast<unsigned>(b) << 16) | static_cast<unsigned>(t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+raster_mark_tall_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
+                        const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ bits,
+                        const unsigned* __restrict__ queue, int H, int W, int cap, int tcap) {
+  const int lane = threadIdx.x & 31;
+  const unsigned n = queue[0];
+  for (unsigned i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const unsigned item = queue[4 + i];
+    const int b = static_cast<int>(item >> 16), t = static_cast<int>(item & 0xFFFFu);
+    const size_t img = static_cast<size_t>(b) * H * W;
+    const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
+                              trirec + static_cast<size_t>(b) * tcap, t, ntri[b]);   // (every lane the same triangle)
+    // lane l walks rows [ymin + l * per, ymin + (l + 1) * per) with the DDA
+    const int per = (R.ymax - R.ymin + 32) / 32;
+    const int y0 = R.ymin + lane * per, y1 = min(y0 + per - 1, R.ymax);
+    if (y0 <= y1) {
+      EdgeDda e0, e1, e2;
+      e0.init(R.A0, R.B0, R.C0, y0); e1.init(R.A1, R.B1, R.C1, y0); e2.init(R.A2, R.B2, R.C2, y0);
+      size_t rowoff = img + static_cast<size_t>(y0) * W;
+      for (int y = y0; y <= y1; ++y, rowoff += W) {
+        int lo = R.xmin, hi = R.xmax;
+        lo = max(lo, R.B0 > 0 ? -e0.q : lo); hi = min(hi, R.B0 < 0 ? e0.q : (R.B0 == 0 && e0.q < 0 ? -1 : hi));
+        lo = max(lo, R.B1 > 0 ? -e1.q : lo); hi = min(hi, R.B1 < 0 ? e1.q : (R.B1 == 0 && e1.q < 0 ? -1 : hi));
+        lo = max(lo, R.B2 > 0 ? -e2.q : lo); hi = min(hi, R.B2 < 0 ? e2.q : (R.B2 == 0 && e2.q < 0 ? -1 : hi));
+        if (lo <= hi && !only_vertices(R, y, lo, hi)) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
+        e0.step(); e1.step(); e2.step();
       }
-      if (lo <= hi) mark_start(loc, bits, img + static_cast<size_t>(y) * W + lo, id);
     }
   }
 }
@@ -375,8 +434,9 @@ __global__ void fill_none_kernel(uint4* __restrict__ loc, size_t n16, unsigned n
 
 using namespace fovea;
 
-extern "C" int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W) {
-  return (static_cast<int64_t>(B) * H * W + 31) / 32 * 4;   // one span-start bit per pixel
+extern "C" int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W, int tcap) {
+  // one span-start bit per pixel, then the queue of tall triangles (length + one word per triangle)
+  return (static_cast<int64_t>(B) * H * W + 31) / 32 * 4 + 16 + static_cast<int64_t>(B) * tcap * 4;
 }
 
 extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
@@ -406,14 +466,17 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
 #define FOVEA_RAS_SPAN(LPT)                                                                                      \
   raster_span_kernel<LPT><<<dim3(ceil_div(tcap, (32 / LPT) * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(       \
       pts, mesh4, recs, ntri, loc, hw, H, W, cap, tcap, tile_max)
-  if (mode == 64 && workspace && !prefill) {   // markers + row sweep (needs a canvas the mesh covers: every row starts a span)
-    const size_t npix = static_cast<size_t>(B) * H * W;
-    FOVEA_CUDA(cudaMemsetAsync(workspace, 0, (npix + 31) / 32 * 4, s));
-    raster_mark_kernel<<<dim3(ceil_div(tcap, kRasThreads), B), kRasThreads, 0, s>>>(
-        pts, mesh4, recs, ntri, loc, static_cast<unsigned*>(workspace), H, W, cap, tcap);
+  if (mode == 64 && workspace && !prefill && grid) {   // markers + row sweep (needs a canvas the mesh covers: every row starts a span)
+    const size_t npix = static_cast<size_t>(B) * H * W, bit_words = (npix + 31) / 32;
+    unsigned* bits = static_cast<unsigned*>(workspace);
+    unsigned* queue = bits + bit_words;     // [0] = length, [4 ...] = (frame << 16 | triangle) of the tall triangles
+    FOVEA_CUDA(cudaMemsetAsync(workspace, 0, (bit_words + 4) * 4, s));
+    raster_mark_kernel<<<dim3(ceil_div(tcap, kMarkThreads), B), kMarkThreads, 0, s>>>(pts, mesh4, recs, ntri, loc, bits, queue,
+                                                                                     H, W, cap, tcap);
+    raster_mark_tall_kernel<<<kNumSMs * 4, 256, 0, s>>>(pts, mesh4, recs, ntri, loc, bits, queue, H, W, cap, tcap);
     const long long rows = static_cast<long long>(B) * H;
     raster_fill_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
-        loc, static_cast<const unsigned char*>(workspace), rows, W, 0x8000u | static_cast<unsigned>(hw));
+        loc, reinterpret_cast<const unsigned char*>(bits), rows, W, 0x8000u | static_cast<unsigned>(hw));
   } else if (mode == 1) FOVEA_RAS_SPAN(1);
   else if (mode == 2) FOVEA_RAS_SPAN(2);
   else if (mode == 4) FOVEA_RAS_SPAN(4);

@@ -53,7 +53,7 @@ PROTOTYPES = {
     "fovea_locate_hints": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_triangle_setup": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "fovea_locate_raster_workspace_bytes": (_i64, [_i, _i, _i]),
+    "fovea_locate_raster_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "fovea_locate_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "fovea_inverse_mask_workspace_bytes": (_i64, [_i, _i, _i, _i]),

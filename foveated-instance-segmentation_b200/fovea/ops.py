@@ -394,7 +394,7 @@ def _locate_raster(pts, mesh, trirec, ntri, grid, winner, h, w, cap, tcap, prefi
     loc = torch.empty(B, H, W, device=winner.device, dtype=torch.int16)    # uint16 bit patterns
     ws = None
     if not prefill:                                                        # the span-start bitmap of the marker raster
-        nbytes = int(_lib.load().fovea_locate_raster_workspace_bytes(B, H, W))
+        nbytes = int(_lib.load().fovea_locate_raster_workspace_bytes(B, H, W, tcap))
         ws = torch.empty((nbytes + 3) // 4, device=winner.device, dtype=torch.int32)
     _lib.call("fovea_locate_raster", _ptr(pts), _ptr(mesh), _ptr(trirec), _ptr(ntri), _ptr(grid),
               _ptr(winner if grid is not None else None), B, h, w, H, W, cap, tcap, 1 if prefill else 0, _ptr(loc),

@@ -82,3 +82,32 @@ def test_width_not_multiple_of_8_uses_the_walker(ops):
     assert plan.hints is not None
     s, _ = ops.inverse_fill(plan, rp.synthetic_pred(1, 4, seed=2).cuda(), want_scores=True)
     assert torch.isfinite(s).all()
+
+
+@pytest.mark.parametrize("H,W,tri", [(256, 320, "device"), (1024, 1024, "device"), (4096, 4096, "device"), (520, 392, "host")])
+def test_raster_variants_write_the_same_map(ops, monkeypatch, H, W, tri):
+    """The three rasterisers of fovea_locate_raster -- span-start markers + row sweep (default), the per-pixel sweep and the
+    closed-form row spans -- evaluate one predicate and must agree bit for bit (the marker path additionally relies on
+    the spans of a row partitioning it, and on skipping spans made of vertex pixels only)."""
+    grid = _grid(2, seed=3 * H + W)
+    plan = ops.build_inverse_plan(grid, (H, W), nchan=51, triangulation=tri)
+    maps = {}
+    for mode in ("64", "0", "8"):
+        monkeypatch.setenv("FOVEA_RAS_MODE", mode)
+        maps[mode] = ops._locate_raster(plan.pts, plan.mesh, plan.trirec, plan.ntri, grid, plan.winner, plan.h, plan.w,
+                                        plan.cap, plan.tcap, False).clone()
+    assert torch.equal(maps["64"], plan.loc)
+    assert torch.equal(maps["64"], maps["0"]) and torch.equal(maps["8"], maps["0"])
+
+
+def test_marker_raster_leaves_unmeshed_frames_unset(ops, monkeypatch):
+    """A frame whose Delaunay run reported no mesh (ntri = 0) must come out "no value" everywhere (except its stamped nodes)."""
+    grid = _grid(2, seed=11)
+    plan = ops.build_inverse_plan(grid, (256, 256), nchan=51, triangulation="device")
+    ntri = plan.ntri.clone(); ntri[1] = 0
+    loc = ops._locate_raster(plan.pts, plan.mesh, plan.trirec, ntri, grid, plan.winner, plan.h, plan.w, plan.cap, plan.tcap, False)
+    l = loc.view(torch.int16).long() & 0xFFFF
+    assert torch.equal(l[0], plan.loc.view(torch.int16).long()[0] & 0xFFFF)
+    none = 0x8000 | (plan.h * plan.w)
+    unset = plan.winner[1] < 0
+    assert (l[1][unset] == none).all() and (l[1][~unset] != none).all()
