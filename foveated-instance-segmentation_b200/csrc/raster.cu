@@ -267,6 +267,40 @@ struct EdgeDda {   // floor((A y + C) / m), m = |B| (1 when B == 0), as quotient
     q += dq; r += dr;
     if (r >= m) { r -= m; ++q; }
   }
+  __device__ __forceinline__ void jump(int n) {   // n rows at once (n * dr < 2^10 * 2^14: the quotient below is <= n, exact)
+    int qq, rr;
+    fdiv(r + n * dr, m, qq, rr);
+    q += n * dq + qq; r = rr;
+  }
+};
+
+// The three edges of a triangle in roles: a counter-clockwise triangle of positive area has at least one edge that bounds
+// its rows from the LEFT (B > 0: x >= -floor(k / B)) and one from the RIGHT (B < 0: x <= floor(k / -B)); the third is
+// either kind or horizontal (B == 0: the row is inside iff k >= 0).
+struct SpanWalker {
+  EdgeDda L, Rr, X;
+  int xkind, xmin, xmax;
+  __device__ __forceinline__ void init(const RasTri& T, int y) {
+    const int iL = T.B0 > 0 ? 0 : (T.B1 > 0 ? 1 : 2);
+    const int iR = T.B0 < 0 ? 0 : (T.B1 < 0 ? 1 : 2);
+    const int iX = 3 - iL - iR;
+    auto pick = [&](int i, int& A, int& B, int& C) {
+      A = i == 0 ? T.A0 : (i == 1 ? T.A1 : T.A2); B = i == 0 ? T.B0 : (i == 1 ? T.B1 : T.B2); C = i == 0 ? T.C0 : (i == 1 ? T.C1 : T.C2);
+    };
+    int A, B, C;
+    pick(iL, A, B, C); L.init(A, B, C, y);
+    pick(iR, A, B, C); Rr.init(A, B, C, y);
+    pick(iX, A, B, C); X.init(A, B, C, y);
+    xkind = B > 0 ? 1 : (B < 0 ? -1 : 0);
+    xmin = T.xmin; xmax = T.xmax;
+  }
+  __device__ __forceinline__ void span(int& lo, int& hi) const {
+    lo = max(xmin, -L.q); hi = min(xmax, Rr.q);
+    lo = max(lo, xkind > 0 ? -X.q : lo);
+    hi = min(hi, xkind < 0 ? X.q : (xkind == 0 && X.q < 0 ? -1 : hi));
+  }
+  __device__ __forceinline__ void step() { L.step(); Rr.step(); X.step(); }
+  __device__ __forceinline__ void jump(int n) { L.jump(n); Rr.jump(n); X.jump(n); }
 };
 
 __global__ void __launch_bounds__(kMarkThreads)
@@ -296,17 +330,14 @@ raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
   }
   const bool large = R.live && bh > limit;
   if (R.live && !large) {
-    EdgeDda e0, e1, e2;
-    e0.init(R.A0, R.B0, R.C0, R.ymin); e1.init(R.A1, R.B1, R.C1, R.ymin); e2.init(R.A2, R.B2, R.C2, R.ymin);
+    SpanWalker w;
+    w.init(R, R.ymin);
     size_t rowoff = img + static_cast<size_t>(R.ymin) * W;
     for (int y = R.ymin; y <= R.ymax; ++y, rowoff += W) {
-      // B > 0: x >= -floor(k / B);  B < 0: x <= floor(k / -B);  B == 0: the row is inside iff k >= 0 (q = k)
-      int lo = R.xmin, hi = R.xmax;
-      lo = max(lo, R.B0 > 0 ? -e0.q : lo); hi = min(hi, R.B0 < 0 ? e0.q : (R.B0 == 0 && e0.q < 0 ? -1 : hi));
-      lo = max(lo, R.B1 > 0 ? -e1.q : lo); hi = min(hi, R.B1 < 0 ? e1.q : (R.B1 == 0 && e1.q < 0 ? -1 : hi));
-      lo = max(lo, R.B2 > 0 ? -e2.q : lo); hi = min(hi, R.B2 < 0 ? e2.q : (R.B2 == 0 && e2.q < 0 ? -1 : hi));
+      int lo, hi;
+      w.span(lo, hi);
       if (lo <= hi && !only_vertices(R, y, lo, hi)) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
-      e0.step(); e1.step(); e2.step();
+      w.step();
     }
   }
   // the tall ones go to a queue: raster_mark_tall_kernel spreads them over the whole device, one warp each (the corner
@@ -333,20 +364,20 @@ raster_mark_tall_kernel(const int32_t* __restrict__ pts, const uint4* __restrict
     const size_t img = static_cast<size_t>(b) * H * W;
     const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
                               trirec + static_cast<size_t>(b) * tcap, t, ntri[b]);   // (every lane the same triangle)
-    // lane l walks rows [ymin + l * per, ymin + (l + 1) * per) with the DDA
+    // lane l walks rows [ymin + l * per, ymin + (l + 1) * per): the walker is started at ymin by every lane alike (the
+    // only divisions with large operands: warp-uniform) and jumps to the lane's first row
     const int per = (R.ymax - R.ymin + 32) / 32;
     const int y0 = R.ymin + lane * per, y1 = min(y0 + per - 1, R.ymax);
+    SpanWalker w;
+    w.init(R, R.ymin);
     if (y0 <= y1) {
-      EdgeDda e0, e1, e2;
-      e0.init(R.A0, R.B0, R.C0, y0); e1.init(R.A1, R.B1, R.C1, y0); e2.init(R.A2, R.B2, R.C2, y0);
+      if (lane) w.jump(lane * per);
       size_t rowoff = img + static_cast<size_t>(y0) * W;
       for (int y = y0; y <= y1; ++y, rowoff += W) {
-        int lo = R.xmin, hi = R.xmax;
-        lo = max(lo, R.B0 > 0 ? -e0.q : lo); hi = min(hi, R.B0 < 0 ? e0.q : (R.B0 == 0 && e0.q < 0 ? -1 : hi));
-        lo = max(lo, R.B1 > 0 ? -e1.q : lo); hi = min(hi, R.B1 < 0 ? e1.q : (R.B1 == 0 && e1.q < 0 ? -1 : hi));
-        lo = max(lo, R.B2 > 0 ? -e2.q : lo); hi = min(hi, R.B2 < 0 ? e2.q : (R.B2 == 0 && e2.q < 0 ? -1 : hi));
+        int lo, hi;
+        w.span(lo, hi);
         if (lo <= hi && !only_vertices(R, y, lo, hi)) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
-        e0.step(); e1.step(); e2.step();
+        w.step();
       }
     }
   }

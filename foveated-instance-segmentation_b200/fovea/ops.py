@@ -391,6 +391,8 @@ def _locate_raster(pts, mesh, trirec, ntri, grid, winner, h, w, cap, tcap, prefi
     """interp2d.py:58 (find_simplex for every pixel) by rasterising the mesh, merged with the A7 winners (grid may be
     None: no pixel carries a node): the per-pixel source map `loc`."""
     B, H, W = winner.shape
+    if grid is not None:
+        grid = _req(grid, torch.float32, "grid", 4)                        # (the kernel reads it through the raw pointer)
     loc = torch.empty(B, H, W, device=winner.device, dtype=torch.int16)    # uint16 bit patterns
     ws = None
     if not prefill:                                                        # the span-start bitmap of the marker raster

@@ -89,7 +89,7 @@ def test_raster_variants_write_the_same_map(ops, monkeypatch, H, W, tri):
     """The three rasterisers of fovea_locate_raster -- span-start markers + row sweep (default), the per-pixel sweep and the
     closed-form row spans -- evaluate one predicate and must agree bit for bit (the marker path additionally relies on
     the spans of a row partitioning it, and on skipping spans made of vertex pixels only)."""
-    grid = _grid(2, seed=3 * H + W)
+    grid = _grid(2, seed=3 * H + W).float().contiguous()          # (_locate_raster takes the raw pointer)
     plan = ops.build_inverse_plan(grid, (H, W), nchan=51, triangulation=tri)
     maps = {}
     for mode in ("64", "0", "8"):
@@ -102,7 +102,7 @@ def test_raster_variants_write_the_same_map(ops, monkeypatch, H, W, tri):
 
 def test_marker_raster_leaves_unmeshed_frames_unset(ops, monkeypatch):
     """A frame whose Delaunay run reported no mesh (ntri = 0) must come out "no value" everywhere (except its stamped nodes)."""
-    grid = _grid(2, seed=11)
+    grid = _grid(2, seed=11).float().contiguous()
     plan = ops.build_inverse_plan(grid, (256, 256), nchan=51, triangulation="device")
     ntri = plan.ntri.clone(); ntri[1] = 0
     loc = ops._locate_raster(plan.pts, plan.mesh, plan.trirec, ntri, grid, plan.winner, plan.h, plan.w, plan.cap, plan.tcap, False)
