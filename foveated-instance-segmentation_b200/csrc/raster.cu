@@ -11,6 +11,8 @@
 // 6 400 nodes themselves (stamp_nodes_kernel) -- the 4-byte-per-pixel winner map is no longer read by stage 3's locate.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "fill.cuh"
 
@@ -215,30 +217,29 @@ raster_span_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
 }
 
 // ---- Marker raster.  On a canvas the triangulation covers (forced corners: the convex hull IS the canvas) the spans of
-// one row partition it, so the map is fixed by where every span STARTS: raster_mark_kernel stores the triangle id at the
-// first pixel of each (triangle, row) span and sets that pixel's bit in a start bitmap; raster_fill_rows_kernel then
-// sweeps every row once, carrying the last started id forward, with coalesced 16-byte loads and stores.  One lane takes
-// one triangle and walks its rows with an exact integer DDA (quotient + remainder of every edge's crossing, advanced by
-// one addition and one conditional carry per row -- two integer divisions per edge per TRIANGLE instead of one per
-// row); ~35 lane-instructions and one 2-byte store per (triangle, row), against ~8 per PIXEL tested by the sweep.
+// one row partition it, so the map is fixed by where every span STARTS: the map is cleared to "no start",
+// raster_mark_kernel stores the triangle id at the first pixel of each (triangle, row) span, and
+// raster_fill_rows_kernel sweeps every row once, carrying the last started id forward, with coalesced 16-byte loads and
+// stores.  One lane takes one triangle and walks its rows with an exact integer DDA (quotient + remainder of every
+// edge's crossing, advanced by one addition and one conditional carry per row -- two divisions per edge per TRIANGLE
+// instead of one per row); ~35 lane-instructions and one 2-byte store per (triangle, row), against ~8 per PIXEL tested by
+// the sweep.
 constexpr int kMarkCoopRows = 64;   // taller triangles are ALWAYS taken by the whole warp, rows strided by 32 (direct divisions)
-constexpr int kMarkThreads = 128;
+constexpr int kMarkThreads = 128;   // (<= 256: the sorted order is kept in bytes)
 
-__device__ __forceinline__ void mark_start(uint16_t* loc, unsigned* bits, size_t lin, unsigned id) {   // lin: pixel index in the batch
+__device__ __forceinline__ void mark_start(uint16_t* loc, unsigned lin, unsigned id) {   // lin: pixel index in the chunk (< 2^32)
   loc[lin] = static_cast<uint16_t>(id);
-  atomicOr(bits + (lin >> 5), 1u << (lin & 31));
 }
 
 // At a vertex the tie rule is not exclusive: several of the triangles around a site can own its pixel (harmless for the
 // sweep -- the pixel carries a node and is stamped afterwards -- but two span STARTS on one pixel would lose one).
-// A span made only of its triangle's own vertices (an apex, or a one-pixel horizontal edge) carries no information: skip.
-__device__ __forceinline__ bool only_vertices_pts(int p0, int p1, int p2, int y, int lo, int hi) {
-  if (hi - lo > 2) return false;
-  auto in = [&](int p) { return (p >> 16) == y && (p & 0xFFFF) >= lo && (p & 0xFFFF) <= hi ? 1 : 0; };
-  return in(p0) + in(p1) + in(p2) == hi - lo + 1;
-}
-__device__ __forceinline__ bool only_vertices(const RasTri& R, int y, int lo, int hi) {
-  return only_vertices_pts(R.p0, R.p1, R.p2, y, lo, hi);
+// A one-pixel span on the triangle's own vertex (an apex) carries no information and is skipped.  That is enough:
+// a longer span that starts on a vertex either continues onto pixels nobody else owns (its start is the only one
+// kept there), or is a one-pixel-long horizontal edge, whose two triangles tie for a start that only ever reaches the
+// edge's two vertex pixels -- both stamped.
+__device__ __forceinline__ bool apex_only(const RasTri& R, int y, int lo, int hi) {
+  const int pk = (y << 16) | lo;
+  return lo == hi && (pk == R.p0 || pk == R.p1 || pk == R.p2);
 }
 
 struct EdgeDda {   // floor((A y + C) / m), m = |B| (1 when B == 0), as quotient + remainder, advanced row by row
@@ -305,17 +306,51 @@ struct SpanWalker {
 
 __global__ void __launch_bounds__(kMarkThreads)
 raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
-                   const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ bits,
-                   unsigned* __restrict__ queue, int H, int W, int cap, int tcap) {
+                   const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ queue, int H,
+                   int W, int cap, int tcap) {
   const int b = blockIdx.y;
   const int T = ntri[b];
   if (T <= 0) return;  // no mesh for this frame: no starts, the row sweep leaves "no value" everywhere
   const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * kMarkThreads + threadIdx.x;
-  if (t - lane >= T) return;
-  const size_t img = static_cast<size_t>(b) * H * W;
-  const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
-                            trirec + static_cast<size_t>(b) * tcap, t, T);
+  const int tbase = blockIdx.x * kMarkThreads;
+  if (tbase >= T) return;
+  // The lanes of a warp walk their triangles in lockstep: hand the CTA's 128 triangles out SORTED BY HEIGHT (a counting
+  // sort on the row count, in shared memory), so that a warp's triangles are about equally tall.
+  __shared__ int s_hist[kMarkCoopRows + 2];
+  __shared__ unsigned char s_order[kMarkThreads];
+  __shared__ RasTri s_tri[kMarkThreads];                        // (17 words each: conflict-free)
+  if (threadIdx.x < kMarkCoopRows + 2) s_hist[threadIdx.x] = 0;
+  // every thread loads the record of ITS triangle (all global loads of the kernel, issued together) ...
+  const RasTri mine = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
+                               trirec + static_cast<size_t>(b) * tcap, tbase + threadIdx.x, T);
+  s_tri[threadIdx.x] = mine;
+  __syncthreads();
+  const bool past = tbase + static_cast<int>(threadIdx.x) >= T;
+  const int bin = past ? kMarkCoopRows + 1 : min(max(mine.ymax - mine.ymin, 0), kMarkCoopRows);   // (past the end: last)
+  const int pos = atomicAdd(&s_hist[bin], 1);
+  __syncthreads();
+  if (threadIdx.x < 32) {                                       // exclusive scan of the 66 bins by one warp
+    int carry = 0;
+    for (int i0 = 0; i0 < kMarkCoopRows + 2; i0 += 32) {
+      const int i = i0 + lane;
+      const int v = i < kMarkCoopRows + 2 ? s_hist[i] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (i < kMarkCoopRows + 2) s_hist[i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  s_order[s_hist[bin] + pos] = static_cast<unsigned char>(threadIdx.x);
+  __syncthreads();
+  // ... and walks the one the sort hands it
+  const int t = tbase + s_order[threadIdx.x];
+  const unsigned img = static_cast<unsigned>(b) * H * W;   // (a chunk holds < 2^32 pixels: checked by the launcher)
+  const RasTri R = s_tri[s_order[threadIdx.x]];
   // A warp's lanes walk their triangles in lockstep, so the tallest one sets the price (~45 instructions per row for
   // the whole warp) -- while a queued triangle costs a warp of raster_mark_tall_kernel ~300.  The height limit above
   // which triangles leave the lane path is the cheapest of a few candidates under that model.
@@ -332,11 +367,11 @@ raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
   if (R.live && !large) {
     SpanWalker w;
     w.init(R, R.ymin);
-    size_t rowoff = img + static_cast<size_t>(R.ymin) * W;
+    unsigned rowoff = img + static_cast<unsigned>(R.ymin) * W;
     for (int y = R.ymin; y <= R.ymax; ++y, rowoff += W) {
       int lo, hi;
       w.span(lo, hi);
-      if (lo <= hi && !only_vertices(R, y, lo, hi)) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
+      if (lo <= hi && !apex_only(R, y, lo, hi)) mark_start(loc, rowoff + lo, static_cast<unsigned>(t));
       w.step();
     }
   }
@@ -354,14 +389,22 @@ raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
 
 __global__ void __launch_bounds__(256)
 raster_mark_tall_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
-                        const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ bits,
-                        const unsigned* __restrict__ queue, int H, int W, int cap, int tcap) {
+                        const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ queue, int H,
+                        int W, int cap, int tcap) {
   const int lane = threadIdx.x & 31;
   const unsigned n = queue[0];
-  for (unsigned i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+  __shared__ unsigned s_next;
+  for (;;) {     // CTAs pull eight items at a time as they finish (a few are 1000 rows tall, most ~100): one atomic per eight
+    __syncthreads();                           // (one atomic per item on the one counter was the kernel's bottleneck)
+    if (threadIdx.x == 0) s_next = atomicAdd(queue + 1, 8u);
+    __syncthreads();
+    const unsigned first = s_next;
+    if (first >= n) break;
+    const unsigned i = first + (threadIdx.x >> 5);
+    if (i >= n) continue;
     const unsigned item = queue[4 + i];
     const int b = static_cast<int>(item >> 16), t = static_cast<int>(item & 0xFFFFu);
-    const size_t img = static_cast<size_t>(b) * H * W;
+    const unsigned img = static_cast<unsigned>(b) * H * W;
     const RasTri R = ras_load(pts + static_cast<size_t>(b) * cap, mesh + static_cast<size_t>(b) * tcap,
                               trirec + static_cast<size_t>(b) * tcap, t, ntri[b]);   // (every lane the same triangle)
     // lane l walks rows [ymin + l * per, ymin + (l + 1) * per): the walker is started at ymin by every lane alike (the
@@ -372,11 +415,11 @@ raster_mark_tall_kernel(const int32_t* __restrict__ pts, const uint4* __restrict
     w.init(R, R.ymin);
     if (y0 <= y1) {
       if (lane) w.jump(lane * per);
-      size_t rowoff = img + static_cast<size_t>(y0) * W;
+      unsigned rowoff = img + static_cast<unsigned>(y0) * W;
       for (int y = y0; y <= y1; ++y, rowoff += W) {
         int lo, hi;
         w.span(lo, hi);
-        if (lo <= hi && !only_vertices(R, y, lo, hi)) mark_start(loc, bits, rowoff + lo, static_cast<unsigned>(t));
+        if (lo <= hi && !apex_only(R, y, lo, hi)) mark_start(loc, rowoff + lo, static_cast<unsigned>(t));
         w.step();
       }
     }
@@ -384,47 +427,42 @@ raster_mark_tall_kernel(const int32_t* __restrict__ pts, const uint4* __restrict
 }
 
 // One warp per canvas row: 256 pixels per step (8 per lane, one 16-byte load + store), the id of the last span start
-// carried from lane to lane by a 5-step shuffle scan and from step to step in a register.
+// carried from lane to lane by a 5-step shuffle scan and from step to step in a register.  A pixel that is no span
+// start still holds the kNoStart the chunk was cleared to.
+constexpr unsigned kNoStart = 0xFFFFu;   // never a map value: node ids and triangle ids are < 32767 (checked on the host)
 __global__ void __launch_bounds__(256)
-raster_fill_rows_kernel(uint16_t* __restrict__ loc, const unsigned char* __restrict__ bits, long long rows, int W, unsigned none) {
+raster_fill_rows_kernel(uint16_t* __restrict__ loc, long long rows, int W, unsigned none) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   uint16_t* lr = loc + row * W;
-  const unsigned char* br = bits + row * (W / 8);
-  constexpr unsigned kNoVal = 0xFFFFFFFFu;
   unsigned carry = none;
   for (int x0 = 0; x0 < W; x0 += 256) {
     const int x = x0 + lane * 8;
     const bool act = x < W;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    unsigned f = 0;
-    if (act) {
-      f = br[x >> 3];
-      v = *reinterpret_cast<const uint4*>(lr + x);
-    }
+    uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (act) v = *reinterpret_cast<const uint4*>(lr + x);
     unsigned px[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
-    unsigned last = kNoVal;  // the id started last inside my 8 pixels
+    unsigned inc = kNoStart;   // the id started last inside my 8 pixels ...
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if ((f >> j) & 1u) last = px[j];
-    unsigned inc = last;    // inclusive scan: the last start at or before my pixels (within this step)
+      if (px[j] != kNoStart) inc = px[j];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < 32; o <<= 1) {   // ... then: the last start at or before my pixels (within this step)
       const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o && inc == kNoVal) inc = y;
+      if (lane >= o && inc == kNoStart) inc = y;
     }
     unsigned cur = __shfl_up_sync(0xffffffffu, inc, 1);   // the last start strictly before my pixels
-    if (lane == 0 || cur == kNoVal) cur = carry;
+    if (lane == 0 || cur == kNoStart) cur = carry;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if ((f >> j) & 1u) cur = px[j];
+      if (px[j] != kNoStart) cur = px[j];
       px[j] = cur;
     }
     if (act)
       *reinterpret_cast<uint4*>(lr + x) = make_uint4(px[0] | (px[1] << 16), px[2] | (px[3] << 16), px[4] | (px[5] << 16), px[6] | (px[7] << 16));
     const unsigned tail = __shfl_sync(0xffffffffu, inc, 31);
-    if (tail != kNoVal) carry = tail;
+    if (tail != kNoStart) carry = tail;
   }
 }
 
@@ -466,8 +504,8 @@ __global__ void fill_none_kernel(uint4* __restrict__ loc, size_t n16, unsigned n
 using namespace fovea;
 
 extern "C" int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W, int tcap) {
-  // one span-start bit per pixel, then the queue of tall triangles (length + one word per triangle)
-  return (static_cast<int64_t>(B) * H * W + 31) / 32 * 4 + 16 + static_cast<int64_t>(B) * tcap * 4;
+  (void)H; (void)W;
+  return 16 + static_cast<int64_t>(B) * tcap * 4;   // the queue of tall triangles: length, next, then one word per triangle
 }
 
 extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
@@ -498,16 +536,27 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
   raster_span_kernel<LPT><<<dim3(ceil_div(tcap, (32 / LPT) * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(       \
       pts, mesh4, recs, ntri, loc, hw, H, W, cap, tcap, tile_max)
   if (mode == 64 && workspace && !prefill && grid) {   // markers + row sweep (needs a canvas the mesh covers: every row starts a span)
-    const size_t npix = static_cast<size_t>(B) * H * W, bit_words = (npix + 31) / 32;
-    unsigned* bits = static_cast<unsigned*>(workspace);
-    unsigned* queue = bits + bit_words;     // [0] = length, [4 ...] = (frame << 16 | triangle) of the tall triangles
-    FOVEA_CUDA(cudaMemsetAsync(workspace, 0, (bit_words + 4) * 4, s));
-    raster_mark_kernel<<<dim3(ceil_div(tcap, kMarkThreads), B), kMarkThreads, 0, s>>>(pts, mesh4, recs, ntri, loc, bits, queue,
-                                                                                     H, W, cap, tcap);
-    raster_mark_tall_kernel<<<kNumSMs * 4, 256, 0, s>>>(pts, mesh4, recs, ntri, loc, bits, queue, H, W, cap, tcap);
-    const long long rows = static_cast<long long>(B) * H;
-    raster_fill_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(
-        loc, reinterpret_cast<const unsigned char*>(bits), rows, W, 0x8000u | static_cast<unsigned>(hw));
+    // Frame chunks small enough to stay in L2 from the clear to the sweep (the starts are scattered 2-byte stores: into
+    // lines that left L2 each one costs a 32-byte read-modify-write in DRAM -- measured, that was 40 % of the mark kernel)
+    unsigned* queue = static_cast<unsigned*>(workspace);   // [0] = length, [1] = next to take, [4 ...] = (frame << 16 | triangle)
+    const size_t frame_px = static_cast<size_t>(H) * W;
+    size_t chunk_mb = 48;
+    if (const char* e = getenv("FOVEA_RAS_CHUNK_MB")) chunk_mb = std::min<size_t>(std::max(atoi(e), 1), 4096);
+    const int per = static_cast<int>(std::max<size_t>(1, (chunk_mb << 20) / (frame_px * 2)));   // (per * frame_px < 2^32)
+    for (int b0 = 0; b0 < B; b0 += per) {
+      const int nb = std::min(per, B - b0);
+      uint16_t* lc = loc + b0 * frame_px;
+      FOVEA_CUDA(cudaMemsetAsync(lc, 0xFF, static_cast<size_t>(nb) * frame_px * 2, s));
+      FOVEA_CUDA(cudaMemsetAsync(queue, 0, 16, s));
+      raster_mark_kernel<<<dim3(ceil_div(tcap, kMarkThreads), nb), kMarkThreads, 0, s>>>(
+          pts + static_cast<size_t>(b0) * cap, mesh4 + static_cast<size_t>(b0) * tcap, recs + static_cast<size_t>(b0) * tcap,
+          ntri + b0, lc, queue, H, W, cap, tcap);
+      raster_mark_tall_kernel<<<kNumSMs * 4, 256, 0, s>>>(
+          pts + static_cast<size_t>(b0) * cap, mesh4 + static_cast<size_t>(b0) * tcap, recs + static_cast<size_t>(b0) * tcap,
+          ntri + b0, lc, queue, H, W, cap, tcap);
+      const long long rows = static_cast<long long>(nb) * H;
+      raster_fill_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(lc, rows, W, 0x8000u | static_cast<unsigned>(hw));
+    }
   } else if (mode == 1) FOVEA_RAS_SPAN(1);
   else if (mode == 2) FOVEA_RAS_SPAN(2);
   else if (mode == 4) FOVEA_RAS_SPAN(4);

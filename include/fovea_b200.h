@@ -241,7 +241,7 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
  *                  (Interp2D on an arbitrary point set)
  *   prefill != 0 : first mark every pixel "no value" -- required when the triangulation does not cover the canvas (no
  *                  forced corners: 'BI' sites, arbitrary point sets);  W must be a multiple of 8
- *   workspace    : fovea_locate_raster_workspace_bytes(B, H, W, tcap) bytes (span-start bitmap + queue of tall triangles), or NULL */
+ *   workspace    : fovea_locate_raster_workspace_bytes(B, H, W, tcap) bytes (the queue of tall triangles), or NULL */
 int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W, int tcap);
 int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
                         const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap, int tcap,
