@@ -42,7 +42,14 @@ WORKLOADS = {
     "b16_4096": dict(B=16, H=4096, W=4096, C=51, g=80, R=45),
     "tiny": dict(B=4, H=256, W=256, C=51, g=80, R=45),
 }
-KERNELS_PER_STEP = 10  # grid_fwd, grid_sample_fwd, scatter, select_points, delaunay, triangle_setup, raster_locate, stamp_nodes, box4_table, inverse_fill
+def kernels_per_step(cfg, interp="tri"):
+    """Kernels of this library launched per step (the `gpu_launches` claim): grid_fwd, grid_sample_fwd, select_points_sparse,
+    delaunay, triangle_setup, stamp_targets, box4_table, inverse_fill + the marker raster's three kernels (raster_mark,
+    raster_mark_tall, raster_fill_rows) per L2-sized chunk of frames (48 MB of the 2-byte map: csrc/raster.cu)."""
+    if interp != "tri":
+        return 10
+    per = max(1, (48 << 20) // (cfg["H"] * cfg["W"] * 2))
+    return 8 + 3 * -(-cfg["B"] // per)
 
 
 def peaks():
@@ -150,7 +157,8 @@ class Path:
         if self.interp == "nearest":
             plan = ops.build_nearest_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"])
         else:
-            plan = ops.build_inverse_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"], triangulation=self.tri)
+            plan = ops.build_inverse_plan(grid, (cfg["H"], cfg["W"]), nchan=cfg["C"], triangulation=self.tri,
+                                          dense_winner=False)        # (as the pipelines: no A7 winner map)
         table_ready = None
         if time_fill:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -711,7 +719,7 @@ def main():
                        "l2": "output per step (4*C*H*W*B bytes) exceeds the 126 MB L2; no flush needed"},
             "serial_ms_per_step": serial_ms / args.steps,
             "path_hbm_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
-            "gpu_launches": KERNELS_PER_STEP * args.steps,   # (host triangulation: locate_hints replaces delaunay)
+            "gpu_launches": kernels_per_step(cfg, args.interp) * args.steps,   # (host triangulation: locate_hints replaces delaunay)
             "clocks": clocks.summary(),
             "roofline": {"kernel": "inverse_fill_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -67,60 +67,65 @@ __global__ void grid_inv_canvas_kernel(const int32_t* __restrict__ winner, float
 
 // ------------------------------------------------------------------------------------------------ A8
 // table[b][node][c] = grid_sample(pred, grid_inv)[node]: the bilinear sample of pred at the coordinate the
-// reference stores for node (i,j).  One warp handles 32 consecutive nodes of one image; channel values are
-// transposed through shared memory so that both the pred reads and the table writes are coalesced.
-constexpr int kTabNodes = 32;
+// reference stores for node (i,j).  One CTA handles 64 consecutive nodes of one image: a thread gathers FOUR channels of
+// its node (the lanes of a warp along the nodes: coalesced plane reads), parks them as one float4 in a shared-memory tile
+// and the tile leaves as whole 16-byte pieces of the channel-contiguous rows.
+constexpr int kTabNodes = 64;
 constexpr int kTabThreads = 256;
+constexpr int kTabQuads = 16;    // channel quads per pass (64 channels)
+constexpr int kTabStride = 17;   // float4 per tile row: odd, so a quarter-warp's rows land in distinct bank groups
 
 // kBox = false: the plain transpose table[b][node][c] = pred[b][c][node] (DynamicFocus deformed_unsampler scatters the
 // low-resolution labels themselves, nn_B0_deformed_sampler.py:137)
 template <bool kBox>
-__global__ void __launch_bounds__(kTabThreads)
+__global__ void __launch_bounds__(kTabThreads, 8)
 box4_table_kernel(const float* __restrict__ pred, float* __restrict__ table, int C, int Cs, int h, int w) {
-  __shared__ float tile[kTabNodes][65];  // [node][channel chunk of 64] (+1: bank-conflict-free transpose)
+  __shared__ float4 tile[kTabNodes * kTabStride];
   const int hw = h * w;
   const int b = blockIdx.y;
   const int node0 = blockIdx.x * kTabNodes;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps: 2 node halves x 4 channel-quad groups
+  const int nl = (warp & 1) * 32 + lane, qg = warp >> 1;
   const float* pb = pred + static_cast<size_t>(b) * C * hw;
   float* tb = table + static_cast<size_t>(b) * (hw + 2) * Cs;
 
-  const int node = node0 + lane;
+  const int node = node0 + nl;
   Taps t;
-  bool valid = node < hw;
+  const bool valid = node < hw;
+  // The four tap addresses of a node differ from channel to channel only by the plane offset: formed once, as 32-bit
+  // indices into pred[b] (an out-of-range tap reads element 0 and is replaced by 0 -- the zeros padding of grid_sample,
+  // exactly: the VALUE is dropped, not weighted by 0).
+  unsigned o_nw = 0, o_ne = 0, o_sw = 0, o_se = 0;
   if (valid) {
     const int i = node / w, j = node - i * w;
     const float gx = __fadd_rn(__fmul_rn(__fdiv_rn(static_cast<float>(j), static_cast<float>(w)), 2.f), -1.f);
     const float gy = __fadd_rn(__fmul_rn(__fdiv_rn(static_cast<float>(i), static_cast<float>(h)), 2.f), -1.f);
     t = make_taps(gx, gy, h, w);
+    const int base = t.y0 * w + t.x0;
+    o_nw = t.ok_nw ? base : 0; o_ne = t.ok_ne ? base + 1 : 0; o_sw = t.ok_sw ? base + w : 0; o_se = t.ok_se ? base + w + 1 : 0;
   }
-  for (int c0 = 0; c0 < Cs; c0 += 64) {
-    // gather: warp `warp` handles channels c0 + warp, c0 + warp + 8, ...
-    for (int cc = warp; cc < 64; cc += 8) {
-      const int c = c0 + cc;
-      float acc = 0.f;
-      if (!kBox) {
-        if (valid && c < C) acc = __ldg(pb + static_cast<size_t>(c) * hw + node);
-      } else if (valid && c < C) {
-        const float* s = pb + static_cast<size_t>(c) * hw + t.y0 * w + t.x0;
-        const float v_nw = t.ok_nw ? __ldg(s) : 0.f;
-        const float v_ne = t.ok_ne ? __ldg(s + 1) : 0.f;
-        const float v_sw = t.ok_sw ? __ldg(s + w) : 0.f;
-        const float v_se = t.ok_se ? __ldg(s + w + 1) : 0.f;
-        acc = v_nw * t.nw;
-        acc = fmaf(v_ne, t.ne, acc);
-        acc = fmaf(v_sw, t.sw, acc);
-        acc = fmaf(v_se, t.se, acc);
-      }
-      tile[lane][cc] = acc;
+  auto sample = [&](int c) -> float {
+    if (!valid || c >= C) return 0.f;
+    const float* pc = pb + static_cast<size_t>(c) * hw;
+    if (!kBox) return __ldg(pc + node);
+    const float v_nw = __ldg(pc + o_nw), v_ne = __ldg(pc + o_ne), v_sw = __ldg(pc + o_sw), v_se = __ldg(pc + o_se);
+    float acc = (t.ok_nw ? v_nw : 0.f) * t.nw;
+    acc = fmaf(t.ok_ne ? v_ne : 0.f, t.ne, acc);
+    acc = fmaf(t.ok_sw ? v_sw : 0.f, t.sw, acc);
+    return fmaf(t.ok_se ? v_se : 0.f, t.se, acc);
+  };
+  for (int c0 = 0; c0 < Cs; c0 += 4 * kTabQuads) {
+    const int nq = min(kTabQuads, (Cs - c0) / 4);   // (Cs is a multiple of 4)
+    for (int q = qg; q < nq; q += 4) {
+      const int c = c0 + 4 * q;
+      tile[nl * kTabStride + q] = make_float4(sample(c), sample(c + 1), sample(c + 2), sample(c + 3));
     }
     __syncthreads();
-    // scatter rows: 256 threads write 32 nodes x min(64, Cs-c0) channels, channel-contiguous
-    const int nch = min(64, Cs - c0);
-    for (int e = threadIdx.x; e < kTabNodes * nch; e += kTabThreads) {
-      const int n = e / nch, cc = e - n * nch;
-      if (node0 + n < hw) tb[static_cast<size_t>(node0 + n) * Cs + c0 + cc] = tile[n][cc];
-    }
+    // rows leave 16 bytes per thread: 16 threads along a row's quads, 16 rows per pass
+    const int q = threadIdx.x & 15;
+    if (q < nq)
+      for (int n = threadIdx.x >> 4; n < kTabNodes && node0 + n < hw; n += 16)
+        reinterpret_cast<float4*>(tb + static_cast<size_t>(node0 + n) * Cs + c0)[q] = tile[n * kTabStride + q];
     __syncthreads();
   }
   if (blockIdx.x == 0)  // row hw: NaN (an image corner no node landed on); row hw+1: zeros (NaN after NaN -> 0)
@@ -157,7 +162,7 @@ select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict_
     if (win[static_cast<size_t>(v) * p.W + u] != node) continue;  // lost a collision
     const bool corner = (v == 0 || v == p.H - 1) && (u == 0 || u == p.W - 1);
     if (!kNB && corner) continue;  // corners are appended below, exactly once
-    if (!dilation_covers<kNB>(win, p, v, u)) continue;
+    if (!dilation_covers<kNB>(DenseWinners{win, p.W}, p, v, u)) continue;
     const int slot = atomicAdd(&count, 1);
     keys[slot] = (static_cast<unsigned long long>((v << 16) | u) << 32) | static_cast<unsigned>(node);
   }
@@ -193,6 +198,87 @@ select_points_kernel(const float2* __restrict__ grid, const int32_t* __restrict_
     src[static_cast<size_t>(b) * p.cap + i] = static_cast<int32_t>(keys[i] & 0xFFFFFFFFull);
   }
   if (tid == 0) npts[b] = n;
+}
+
+// The same sites WITHOUT the dense winner map (4 bytes per canvas pixel to clear, scatter into and probe): the frame's
+// <= 6 400 node targets are sorted in shared memory by (pixel, node); the last entry of a run of equal pixels is the
+// node that wins the pixel (atomicMax of the A7 scatter), "is this pixel filled" is a binary search, and the sites come
+// out already in row-major order.  Also written: targets[b][n] = (row << 16 | column) of node n if it won its pixel,
+// else -1 -- what the raster needs to stamp the node pixels -- with four more entries for image corners nobody landed on.
+__global__ void __launch_bounds__(kSelThreads, 1)
+select_points_sparse_kernel(const float2* __restrict__ grid, int32_t* __restrict__ pts, int32_t* __restrict__ src,
+                            int32_t* __restrict__ npts, int32_t* __restrict__ targets, SelectParams p) {
+  extern __shared__ unsigned long long keys[];  // (row<<16|col) << 32 | node + 1   (0: a corner's place holder)
+  __shared__ int s_warp[kSelThreads / 32];
+  __shared__ int s_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hw = p.h * p.w;
+  const int n = hw + 4;
+  int32_t* tg = targets + static_cast<size_t>(b) * n;
+  for (int node = tid; node < n; node += kSelThreads) {
+    tg[node] = -1;
+    unsigned long long key = ~0ull;   // targets outside the canvas sort last and win nothing
+    if (node < hw) {
+      const float2 g = grid[static_cast<size_t>(b) * hw + node];
+      const int u = target_coord(g.x, p.W), v = target_coord(g.y, p.H);
+      if (u >= 0 && u < p.W && v >= 0 && v < p.H)
+        key = (static_cast<unsigned long long>((v << 16) | u) << 32) | static_cast<unsigned>(node + 1);
+    } else {                          // models/models.py:202-209: the four corners are always interpolation points
+      const int c = node - hw, v = (c & 2) ? p.H - 1 : 0, u = (c & 1) ? p.W - 1 : 0;
+      key = static_cast<unsigned long long>((v << 16) | u) << 32;
+    }
+    keys[node] = key;
+  }
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + tid; i < n2; i += kSelThreads) keys[i] = ~0ull;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {   // bitonic sort, ascending
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += kSelThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], c = keys[l];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const SortedTargets filled{keys, n};
+  // 1024 entries at a time: winners of their pixel decide whether they are sites; a block-wide scan keeps the order
+  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+    const int i = i0 + tid;
+    const unsigned long long key = i < n ? keys[i] : ~0ull;
+    const unsigned pix = static_cast<unsigned>(key >> 32), tag = static_cast<unsigned>(key);
+    const bool live = key != ~0ull;
+    const bool wins = live && (i + 1 >= n || static_cast<unsigned>(keys[i + 1] >> 32) != pix);   // last of its run
+    bool site = false;
+    int source = hw;
+    if (wins) {
+      const int v = static_cast<int>(pix >> 16), u = static_cast<int>(pix & 0xFFFFu);
+      const bool corner = (v == 0 || v == p.H - 1) && (u == 0 || u == p.W - 1);
+      if (tag) { source = static_cast<int>(tag) - 1; tg[source] = static_cast<int32_t>(pix); }
+      else tg[hw + ((v ? 2 : 0) | (u ? 1 : 0))] = static_cast<int32_t>(pix);   // an unfilled corner: "no value" is stamped there
+      site = corner || dilation_covers<false>(filled, p, v, u);
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, site);
+    if (lane == 0) s_warp[warp] = __popc(ball);
+    __syncthreads();
+    int before = s_base;
+    for (int wq = 0; wq < warp; ++wq) before += s_warp[wq];
+    const int slot = before + __popc(ball & ((1u << lane) - 1u));
+    if (site) {
+      pts[static_cast<size_t>(b) * p.cap + slot] = static_cast<int32_t>(pix);
+      src[static_cast<size_t>(b) * p.cap + slot] = source;
+    }
+    __syncthreads();
+    if (tid == kSelThreads - 1) s_base = slot + (site ? 1 : 0);
+    __syncthreads();
+  }
+  if (tid == 0) npts[b] = s_base;
 }
 
 // ------------------------------------------------------------------------------------------------ hints
@@ -862,6 +948,28 @@ extern "C" int fovea_select_points(const float* grid, const int32_t* winner, int
                                    int nchan, int cap, int32_t* pts, int32_t* src, int32_t* npts,
                                    fovea_stream_t stream) {
   return launch_select<false>(grid, winner, B, h, w, H, W, nchan, cap, pts, src, npts, stream, "fovea_select_points");
+}
+
+extern "C" int fovea_select_points_sparse(const float* grid, int B, int h, int w, int H, int W, int nchan, int cap,
+                                          int32_t* pts, int32_t* src, int32_t* npts, int32_t* targets,
+                                          fovea_stream_t stream) {
+  const char* who = "fovea_select_points_sparse";
+  FOVEA_REQUIRE(grid && pts && src && npts && targets, "%s: null pointer", who);
+  FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && nchan > 0, "%s: bad sizes", who);
+  FOVEA_REQUIRE(H <= 32768 && W <= 65536, "%s: pixel keys are (row << 16 | column) in 31 bits", who);
+  if (cap < h * w + 4 || cap > kSelMax) {
+    set_error("%s: cap=%d must satisfy h*w+4=%d <= cap <= %d", who, cap, h * w + 4, kSelMax);
+    return FOVEA_ERR_CAPACITY;
+  }
+  SelectParams p;
+  if (int rc = make_select_params(p, h, w, H, W, nchan, cap, who)) return rc;
+  int n2 = 1;
+  while (n2 < h * w + 4) n2 <<= 1;
+  const int smem = n2 * static_cast<int>(sizeof(unsigned long long));
+  FOVEA_CUDA(cudaFuncSetAttribute(select_points_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  select_points_sparse_kernel<<<B, kSelThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(grid), pts, src, npts, targets, p);
+  return check_launch(who);
 }
 
 extern "C" int fovea_select_points_nb(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W,

@@ -45,7 +45,7 @@ nearest_columns_kernel(const int32_t* __restrict__ winner, short* __restrict__ g
     for (int k = 0; k < U; ++k) {
       const int y = y0 + k;
       if (y >= p.H) break;
-      if (wv[k] >= 0 && (kAllSites || dilation_covers<true>(win, p, y, x))) last = y;
+      if (wv[k] >= 0 && (kAllSites || dilation_covers<true>(DenseWinners{win, p.W}, p, y, x))) last = y;
       gb[static_cast<size_t>(y) * p.W + x] = last >= 0 ? static_cast<short>(last - y) : kNoSite;
     }
   }
@@ -234,7 +234,7 @@ nearest_sites_kernel(const int32_t* __restrict__ winner, SelectParams p, TileGeo
   for (int k = 0; k < 4; ++k) {
     const int x = x0 + k;
     node[k] = (y < g.H && x < g.W) ? __ldg(win + static_cast<size_t>(y) * g.W + x) : -1;
-    if (node[k] >= 0 && (kAllSites || dilation_covers<true>(win, p, y, x))) mask |= 1u << k;
+    if (node[k] >= 0 && (kAllSites || dilation_covers<true>(DenseWinners{win, p.W}, p, y, x))) mask |= 1u << k;
   }
   const int cnt = __popc(mask);
   int incl = cnt;

@@ -493,6 +493,18 @@ __global__ void stamp_nodes_kernel(const float2* __restrict__ grid, const int32_
   }
 }
 
+// The same stamps from fovea_select_points_sparse's per-node targets (no winner map): targets[b][n] = (row << 16 | column)
+// of node n if it won its pixel, else -1; entries hw .. hw+3 name image corners no node landed on.
+__global__ void stamp_targets_kernel(const int32_t* __restrict__ targets, uint16_t* __restrict__ loc, int B, int hw, int H, int W) {
+  const int total = B * (hw + 4);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int t = targets[idx];
+    if (t < 0) continue;
+    const int b = idx / (hw + 4), node = idx - b * (hw + 4);
+    loc[(static_cast<size_t>(b) * H + (t >> 16)) * W + (t & 0xFFFF)] = static_cast<uint16_t>(0x8000u | min(node, hw));
+  }
+}
+
 __global__ void fill_none_kernel(uint4* __restrict__ loc, size_t n16, unsigned none2) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -508,9 +520,9 @@ extern "C" int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W, int 
   return 16 + static_cast<int64_t>(B) * tcap * 4;   // the queue of tall triangles: length, next, then one word per triangle
 }
 
-extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
-                                   const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap,
-                                   int tcap, int prefill, uint16_t* loc, void* workspace, fovea_stream_t stream) {
+static int locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
+                         const float* grid, const int32_t* winner, const int32_t* targets, int B, int h, int w, int H,
+                         int W, int cap, int tcap, int prefill, uint16_t* loc, void* workspace, fovea_stream_t stream) {
   FOVEA_REQUIRE(pts && mesh && trirec && ntri && loc, "fovea_locate_raster: null pointer");
   FOVEA_REQUIRE((grid == nullptr) == (winner == nullptr), "fovea_locate_raster: grid and winner go together");
   FOVEA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 1 && W > 1 && cap > 0 && tcap > 0, "fovea_locate_raster: bad sizes");
@@ -535,7 +547,7 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
 #define FOVEA_RAS_SPAN(LPT)                                                                                      \
   raster_span_kernel<LPT><<<dim3(ceil_div(tcap, (32 / LPT) * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(       \
       pts, mesh4, recs, ntri, loc, hw, H, W, cap, tcap, tile_max)
-  if (mode == 64 && workspace && !prefill && grid) {   // markers + row sweep (needs a canvas the mesh covers: every row starts a span)
+  if (mode == 64 && workspace && !prefill && (grid || targets)) {   // markers + row sweep (needs a canvas the mesh covers: every row starts a span)
     // Frame chunks small enough to stay in L2 from the clear to the sweep (the starts are scattered 2-byte stores: into
     // lines that left L2 each one costs a 32-byte read-modify-write in DRAM -- measured, that was 40 % of the mark kernel)
     unsigned* queue = static_cast<unsigned*>(workspace);   // [0] = length, [1] = next to take, [4 ...] = (frame << 16 | triangle)
@@ -567,10 +579,24 @@ extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, con
     raster_locate_kernel<<<dim3(ceil_div(tcap, 4 * (kRasThreads / 32)), B), kRasThreads, 0, s>>>(
         pts, mesh4, recs, ntri, loc, hw, H, W, cap, tcap, tile_max);
 #undef FOVEA_RAS_SPAN
-  if (grid) {
-    const int total = B * (hw + 4);
+  const int total = B * (hw + 4);
+  if (targets)
+    stamp_targets_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(targets, loc, B, hw, H, W);
+  else if (grid)
     stamp_nodes_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s>>>(reinterpret_cast<const float2*>(grid), winner,
                                                                              loc, B, hw, H, W);
-  }
   return check_launch("fovea_locate_raster");
+}
+
+extern "C" int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
+                                   const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap,
+                                   int tcap, int prefill, uint16_t* loc, void* workspace, fovea_stream_t stream) {
+  return locate_raster(pts, mesh, trirec, ntri, grid, winner, nullptr, B, h, w, H, W, cap, tcap, prefill, loc, workspace, stream);
+}
+
+extern "C" int fovea_locate_raster_targets(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
+                                           const int32_t* targets, int B, int h, int w, int H, int W, int cap, int tcap,
+                                           uint16_t* loc, void* workspace, fovea_stream_t stream) {
+  FOVEA_REQUIRE(targets, "fovea_locate_raster_targets: null pointer");
+  return locate_raster(pts, mesh, trirec, ntri, nullptr, nullptr, targets, B, h, w, H, W, cap, tcap, 0, loc, workspace, stream);
 }

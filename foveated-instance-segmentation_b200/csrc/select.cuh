@@ -32,8 +32,31 @@ inline int make_select_params(SelectParams& p, int h, int w, int H, int W, int n
   return FOVEA_OK;
 }
 
-__device__ __forceinline__ bool invalid_at(const int32_t* win, int H, int W, int y, int x) {
-  return y >= 0 && y < H && x >= 0 && x < W && win[static_cast<size_t>(y) * W + x] < 0;
+// "Is pixel (y,x) unfilled?" -- answered from the dense A7 winner map ...
+struct DenseWinners {
+  const int32_t* win;
+  int W;
+  __device__ __forceinline__ bool unfilled(int y, int x) const { return win[static_cast<size_t>(y) * W + x] < 0; }
+};
+// ... or from the frame's node targets themselves, sorted in shared memory as (row << 16 | column) << 32 | node + 1
+// (entries with a zero low word are the forced corners' place holders, not nodes): a binary search, no dense map.
+struct SortedTargets {
+  const unsigned long long* keys;
+  int n;
+  __device__ __forceinline__ bool unfilled(int y, int x) const {
+    const unsigned long long want = (static_cast<unsigned long long>((y << 16) | x) << 32) | 1ull;
+    int lo = 0, hi = n;   // first entry >= want
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (keys[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    return lo >= n || static_cast<unsigned>(keys[lo] >> 32) != static_cast<unsigned>((y << 16) | x);
+  }
+};
+
+template <class Winners>
+__device__ __forceinline__ bool invalid_at(const Winners& win, int H, int W, int y, int x) {
+  return y >= 0 && y < H && x >= 0 && x < W && win.unfilled(y, x);
 }
 
 // dilated(y,x): does the structuring element around (y,x) touch an invalid pixel?
@@ -41,8 +64,8 @@ __device__ __forceinline__ bool invalid_at(const int32_t* win, int H, int W, int
 //   kVerticalOnly = true : getPixelsForInterp_NB ('nearest'/'BI', :213-239) hands the [C,H,W] array to cv2.dilate, which
 //                          reads it as rows=C, cols=H, channels=W -- the cross then spans the CLASS and ROW axes; the
 //                          NaN pattern is identical in every class, so what is left is (y-1, y, y+1) in the same column.
-template <bool kVerticalOnly>
-__device__ bool dilation_covers(const int32_t* win, const SelectParams& p, int y, int x) {
+template <bool kVerticalOnly, class Winners>
+__device__ bool dilation_covers(const Winners& win, const SelectParams& p, int y, int x) {
   if (!p.scaled) {
     bool c = invalid_at(win, p.H, p.W, y - 1, x) || invalid_at(win, p.H, p.W, y + 1, x) || invalid_at(win, p.H, p.W, y, x);
     if (!kVerticalOnly) c = c || invalid_at(win, p.H, p.W, y, x - 1) || invalid_at(win, p.H, p.W, y, x + 1);
@@ -59,7 +82,7 @@ __device__ bool dilation_covers(const int32_t* win, const SelectParams& p, int y
     // nearest downscale: scaled[yy][xx] = invalid[min(floor(yy*H/hs), H-1)][...]
     const int sy = min(static_cast<int>(floorf(static_cast<float>(yy) * p.dn_y)), p.H - 1);
     const int sx = min(static_cast<int>(floorf(static_cast<float>(xx) * p.dn_x)), p.W - 1);
-    if (win[static_cast<size_t>(sy) * p.W + sx] < 0) return true;
+    if (win.unfilled(sy, sx)) return true;
   }
   return false;
 }

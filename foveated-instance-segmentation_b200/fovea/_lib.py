@@ -15,7 +15,7 @@ FOVEA_OK = 0
 PAD_NONE, PAD_REPLICATION, PAD_REFLECT, PAD_ZERO = 0, 1, 2, 3
 PAD_MODES = {"none": PAD_NONE, "replication": PAD_REPLICATION, "reflect": PAD_REFLECT, "zero": PAD_ZERO}
 HINT_CELL_W, HINT_CELL_H = 32, 8
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 class FoveaError(RuntimeError):
@@ -45,6 +45,7 @@ PROTOTYPES = {
     "fovea_box4_table": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_select_points": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_select_points_nb": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fovea_select_points_sparse": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "fovea_delaunay_workspace_bytes": (_i64, [_i, _i]),
     "fovea_delaunay": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fovea_delaunay_hints_fused": (_i, [_i, _i, _i]),
@@ -55,6 +56,7 @@ PROTOTYPES = {
     "fovea_locate_pixels": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fovea_locate_raster_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "fovea_locate_raster": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fovea_locate_raster_targets": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fovea_inverse_fill": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "fovea_inverse_mask_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "fovea_inverse_mask": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),

@@ -281,7 +281,7 @@ def grid_inv_canvas(winner, h, w):
 @dataclass
 class InversePlan:
     """Everything stage 3 needs that depends only on the sampling grid (not on the scores being warped)."""
-    winner: torch.Tensor   # [B,H,W] int32
+    winner: torch.Tensor   # [B,H,W] int32 (None for a plan built with dense_winner=False)
     pts: torch.Tensor      # [B,cap] int32 (row<<16|col), row-major sorted
     src: torch.Tensor      # [B,cap] int32 row of the value table
     npts: torch.Tensor     # [B] int32
@@ -333,7 +333,7 @@ def _triangulate_host(pts, npts, cap, tcap, pool=None):
     return torch.from_numpy(mesh).to(dev), torch.from_numpy(ntri).to(dev)
 
 
-def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, sites="tri") -> InversePlan:
+def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, sites="tri", dense_winner=True) -> InversePlan:
     """A7 scatter + A9 point selection + triangulation + walk hints for a batch of sampling grids.
 
     triangulation='host'  : stock SciPy Qhull on the host, exactly what the reference does (parity mode);
@@ -342,6 +342,9 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, si
     sites='tri': interpolation sites of rev_deform_interp='tri' (getPixelsForInterp, models/models.py:169-211);
     sites='nb' : the sites of 'BI' / 'nearest' (getPixelsForInterp_NB, :213-242; no forced corners: pixels outside the
                  sites' convex hull stay NaN, as scipy's LinearNDInterpolator leaves them).
+    dense_winner=False (sites='tri' on the raster path): never materialise the A7 winner map [B,H,W] int32 -- the
+                 sites and the node stamps come from the sorted node targets (fovea_select_points_sparse); same plan,
+                 bit for bit, with plan.winner = None.  The pipelines use it; the reference-facing mirrors keep the map.
     """
     if sites not in ("tri", "nb"):
         raise FoveaError(f"unknown site rule {sites!r}")
@@ -349,16 +352,23 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, si
     B, h, w, _ = g.shape
     H, W = int(segSize[0]), int(segSize[1])
     dev = g.device
-    winner = grid_inv_scatter(g, (H, W))
     cap = h * w + 4
     tcap = 2 * cap
     pts = torch.empty(B, cap, device=dev, dtype=torch.int32)
     src = torch.empty(B, cap, device=dev, dtype=torch.int32)
     npts = torch.empty(B, device=dev, dtype=torch.int32)
-    _lib.call("fovea_select_points" if sites == "tri" else "fovea_select_points_nb", _ptr(g), _ptr(winner), B, h, w, H,
-              W, int(nchan), cap, _ptr(pts), _ptr(src), _ptr(npts), _stream())
-    hints = rounds = None
     raster = _use_raster(W)
+    sparse = not dense_winner and sites == "tri" and raster
+    winner = targets = None
+    if sparse:
+        targets = torch.empty(B, cap, device=dev, dtype=torch.int32)
+        _lib.call("fovea_select_points_sparse", _ptr(g), B, h, w, H, W, int(nchan), cap, _ptr(pts), _ptr(src),
+                  _ptr(npts), _ptr(targets), _stream())
+    else:
+        winner = grid_inv_scatter(g, (H, W))
+        _lib.call("fovea_select_points" if sites == "tri" else "fovea_select_points_nb", _ptr(g), _ptr(winner), B, h, w,
+                  H, W, int(nchan), cap, _ptr(pts), _ptr(src), _ptr(npts), _stream())
+    hints = rounds = None
     if triangulation == "host":
         mesh, ntri = _triangulate_host(pts, npts, cap, tcap, pool)
     elif triangulation == "device":
@@ -370,7 +380,9 @@ def build_inverse_plan(grid, segSize, nchan, triangulation="host", pool=None, si
     else:
         raise FoveaError(f"unknown triangulation mode {triangulation!r}")
     trirec = _triangle_setup(pts, src, mesh, ntri, cap, tcap, max(H, W), h * w)
-    if raster:   # sites='nb' has no forced corners: the hull does not cover the canvas, start from "no value"
+    if sparse:
+        loc = _locate_raster_targets(pts, mesh, trirec, ntri, targets, h, w, H, W, cap, tcap)
+    elif raster:   # sites='nb' has no forced corners: the hull does not cover the canvas, start from "no value"
         loc = _locate_raster(pts, mesh, trirec, ntri, g, winner, h, w, cap, tcap, prefill=sites != "tri")
     else:
         if hints is None:
@@ -385,6 +397,17 @@ def _use_raster(W):
     (fovea_locate_hints + fovea_locate_pixels) or the canvas width is not a multiple of 8 (its 16-byte span stores)."""
     import os
     return os.environ.get("FOVEA_LOCATE", "raster") != "walk" and W % 8 == 0
+
+
+def _locate_raster_targets(pts, mesh, trirec, ntri, targets, h, w, H, W, cap, tcap):
+    """_locate_raster with the node pixels stamped from fovea_select_points_sparse's targets (no winner map)."""
+    B = pts.shape[0]
+    loc = torch.empty(B, H, W, device=pts.device, dtype=torch.int16)       # uint16 bit patterns
+    nbytes = int(_lib.load().fovea_locate_raster_workspace_bytes(B, H, W, tcap))
+    ws = torch.empty((nbytes + 3) // 4, device=pts.device, dtype=torch.int32)
+    _lib.call("fovea_locate_raster_targets", _ptr(pts), _ptr(mesh), _ptr(trirec), _ptr(ntri), _ptr(targets), B, h, w, H, W,
+              cap, tcap, _ptr(loc), _ptr(ws), _stream())
+    return loc
 
 
 def _locate_raster(pts, mesh, trirec, ntri, grid, winner, h, w, cap, tcap, prefill):
@@ -653,7 +676,7 @@ def inverse_fill(plan: InversePlan, pred, want_scores=True, want_mask=False, zer
     Differentiable w.r.t. `pred` (scores only) when it requires grad: models/models.py:933-940."""
     p = _req(pred, torch.float32, "pred", 4)
     B, Cc, h, w = p.shape
-    if (h, w) != (plan.h, plan.w) or B != plan.winner.shape[0]:
+    if (h, w) != (plan.h, plan.w) or B != plan.loc.shape[0]:
         raise FoveaError(f"inverse_fill: pred {tuple(p.shape)} does not match the plan ({B}x{plan.h}x{plan.w})")
     scores = None
     if want_scores:
@@ -695,7 +718,7 @@ def inverse_mask_c1(plan: InversePlan, cls_pred, x, mask_out=None):
     B, K = cp.shape
     if K < 2 or xm.shape[0] != B or xm.shape[1] != 1 or tuple(xm.shape[-2:]) != (plan.h, plan.w):
         raise FoveaError(f"inverse_mask_c1: cls_pred {tuple(cp.shape)} / x {tuple(xm.shape)} do not match the plan "
-                         f"({plan.winner.shape[0]}x{plan.h}x{plan.w})")
+                         f"({plan.loc.shape[0]}x{plan.h}x{plan.w})")
     kstar = torch.argmax(cp[:, :K - 1], dim=1)
     pred3 = torch.empty(B, 3, plan.h, plan.w, device=cp.device, dtype=torch.float32)
     pred3[:, 0] = -1e30                                            # sentinel: never the maximum of a valid pixel

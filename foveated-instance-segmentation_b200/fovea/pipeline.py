@@ -98,7 +98,8 @@ class ResamplePipeline:
         torch.cuda.current_stream(self.dev).wait_event(s.h2d_done)
         with torch.cuda.stream(self.plan_stream):            # saliency-only half of the inverse stage, high priority:
             self.plan_stream.wait_event(s.h2d_done)          # it overlaps the HBM-bound fill of the previous batch
-            plan = ops.build_inverse_plan(s.grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
+            plan = ops.build_inverse_plan(s.grid, (self.H, self.W), nchan=self.C, triangulation=self.tri,
+                                          dense_winner=False)
             planned = torch.cuda.Event()
             planned.record(self.plan_stream)
         with torch.cuda.stream(self.compute):                # fill (+ fused argmax)
@@ -194,7 +195,8 @@ class DevicePipeline:
             if self.interp == "nearest":
                 plan = ops.build_nearest_plan(grid, (self.H, self.W), nchan=self.C)
             else:
-                plan = ops.build_inverse_plan(grid, (self.H, self.W), nchan=self.C, triangulation=self.tri)
+                plan = ops.build_inverse_plan(grid, (self.H, self.W), nchan=self.C, triangulation=self.tri,
+                                              dense_winner=False)
             table = ops.box4_table(pred)                     # A8 at the nodes: also off the fill stream, which then
             planned = torch.cuda.Event()                     # carries nothing but back-to-back fills
             planned.record(self.plan_stream)

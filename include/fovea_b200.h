@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FOVEA_ABI_VERSION 12
+#define FOVEA_ABI_VERSION 13
 
 enum fovea_status {
   FOVEA_OK = 0,
@@ -168,6 +168,14 @@ int fovea_select_points(const float* grid, const int32_t* winner, int B, int h, 
                         int cap, int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream);
 int fovea_select_points_nb(const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int nchan,
                            int cap, int32_t* pts, int32_t* src, int32_t* npts, fovea_stream_t stream);
+/* fovea_select_points WITHOUT the dense winner map of fovea_grid_inv_scatter (A7 + A9 in one launch; nothing of 4*H*W
+ * bytes per frame is cleared, scattered into or probed): the frame's node targets are sorted in shared memory by
+ * (pixel, node), the last node of a run of equal pixels wins the pixel (the scatter's atomicMax), "is this pixel filled"
+ * is a binary search.  Same pts / src / npts, bit for bit.  Also written:
+ *   targets [B, h*w + 4] int32: (row<<16 | col) of node n if it won its pixel, else -1; entries h*w .. h*w+3 name image
+ *                               corners no node landed on (fovea_locate_raster_targets stamps the node pixels from it) */
+int fovea_select_points_sparse(const float* grid, int B, int h, int w, int H, int W, int nchan, int cap, int32_t* pts,
+                               int32_t* src, int32_t* npts, int32_t* targets, fovea_stream_t stream);
 
 /* Triangle mesh layout shared by the entry points below:
  *   mesh [B,tcap,8] uint16, one 16-byte record per triangle: (v0, v1, v2, 0, n0, n1, n2, 0)
@@ -243,6 +251,11 @@ int fovea_locate_pixels(const int32_t* winner, const void* trirec, const int32_t
  *                  forced corners: 'BI' sites, arbitrary point sets);  W must be a multiple of 8
  *   workspace    : fovea_locate_raster_workspace_bytes(B, H, W, tcap) bytes (the queue of tall triangles), or NULL */
 int64_t fovea_locate_raster_workspace_bytes(int B, int H, int W, int tcap);
+/* The same with the node pixels stamped from fovea_select_points_sparse's `targets` [B, h*w + 4] instead of the sampling
+ * grid + the dense winner map (a canvas the triangulation covers: 'tri' sites). */
+int fovea_locate_raster_targets(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
+                                const int32_t* targets, int B, int h, int w, int H, int W, int cap, int tcap,
+                                uint16_t* loc, void* workspace, fovea_stream_t stream);
 int fovea_locate_raster(const int32_t* pts, const uint16_t* mesh, const void* trirec, const int32_t* ntri,
                         const float* grid, const int32_t* winner, int B, int h, int w, int H, int W, int cap, int tcap,
                         int prefill, uint16_t* loc, void* workspace, fovea_stream_t stream);

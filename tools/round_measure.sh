@@ -16,7 +16,7 @@ python tools/probe_delaunay_frames.py b64_1024 > $out/${tag}_delaunay_frames.txt
 python tools/probe_mask.py > $out/${tag}_probe_mask.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-extras --no-cpu-baseline > $out/ncu_$tag.log 2>&1
-for k in inverse_fill_kernel raster_locate_kernel delaunay_kernel inverse_mask_kernel triangle_candidates_kernel inverse_fill_bwd_kernel; do
+for k in inverse_fill_kernel raster_mark_kernel raster_fill_rows_kernel delaunay_kernel inverse_mask_kernel triangle_candidates_kernel inverse_fill_bwd_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o $out/${tag}_$k \
       python tools/probe_kernels.py > $out/ncu_${tag}_$k.log 2>&1
   ncu -i $out/${tag}_$k.ncu-rep --page raw --csv > $out/${tag}_${k}_ncu_raw.csv 2>/dev/null
