@@ -618,19 +618,23 @@ __device__ __forceinline__ void ldg3_if<8>(Rows<8>& r, unsigned long long pa, un
       : "l"(pa), "l"(pb), "l"(pc), "r"(p));
 }
 
+__device__ __forceinline__ uint2 fill_loc(const uint16_t* __restrict__ loc, const FillParams& p, int b, int x0, int y) {
+  return __ldcs(reinterpret_cast<const uint2*>(loc + (static_cast<size_t>(b) * p.H + y) * p.W + x0));
+}
+
 // Each thread owns 4 consecutive pixels of one row: resolve their table rows + barycentric weights from `loc`
 // (exact integer edge functions, stepped in registers while the triangle does not change), then stream all channels
 // with 128-bit stores.  Table rows are re-loaded only where they differ from the previous pixel's.
 template <bool kScores, bool kMask, int G>
 __device__ __forceinline__ void fill_tile(const uint16_t* __restrict__ loc, const TriRec* __restrict__ trirec,
                                           const float* __restrict__ table, float* __restrict__ scores,
-                                          long long* __restrict__ mask, const FillParams& p, int b, int x0, int y) {
+                                          long long* __restrict__ mask, const FillParams& p, int b, int x0, int y,
+                                          const uint2 l2) {   // l2: the tile's 4 x 16 bits of `loc` (fill_loc)
   const int hw = p.h * p.w;
   const unsigned pixoff = static_cast<unsigned>(y) * p.W + x0;  // H*W < 2^32 is checked on the host
   const size_t plane = static_cast<size_t>(p.H) * p.W;
   const TriRec* recs = trirec + static_cast<size_t>(b) * p.tcap;
 
-  const uint2 l2 = __ldcs(reinterpret_cast<const uint2*>(loc + static_cast<size_t>(b) * plane + pixoff));  // 4 x 16 bit
   const int lc[4] = {decode_loc(l2.x & 0xFFFFu), decode_loc(l2.x >> 16), decode_loc(l2.y & 0xFFFFu), decode_loc(l2.y >> 16)};
   unsigned nd0[4], nd1[4], nd2[4];  // table rows (node ids) of the three vertices of each pixel
   float w0[4], w1[4], w2[4];        // barycentric weights ((1,0,0) for a pixel that received a node)
@@ -760,10 +764,18 @@ inverse_fill_kernel(const uint16_t* __restrict__ loc, const TriRec* __restrict__
   constexpr int kTileH = kWarpH * (kFillThreads / 32 / WX);
   const int x0 = blockIdx.x * (kWarpW * WX) + (warp % WX) * kWarpW + (lane % WL) * 4;
   if (x0 >= p.W) return;
+  // the next tile's slice of `loc` (the one DRAM read at the head of a tile's dependent loads) is requested before this
+  // tile's channel loop
+  const int ybase = blockIdx.y * kFillTilesY * kTileH + (warp / WX) * kWarpH + (lane / WL);
+  if (ybase >= p.H) return;
+  uint2 l2 = fill_loc(loc, p, b, x0, ybase);
   for (int ty = 0; ty < kFillTilesY; ++ty) {
-    const int y = (blockIdx.y * kFillTilesY + ty) * kTileH + (warp / WX) * kWarpH + (lane / WL);
-    if (y >= p.H) return;
-    fill_tile<kScores, kMask, G>(loc, trirec, table, scores, mask, p, b, x0, y);
+    const int y = ybase + ty * kTileH;
+    const uint2 cur = l2;
+    const bool more = ty + 1 < kFillTilesY && y + kTileH < p.H;
+    if (more) l2 = fill_loc(loc, p, b, x0, y + kTileH);
+    fill_tile<kScores, kMask, G>(loc, trirec, table, scores, mask, p, b, x0, y, cur);
+    if (!more) return;
   }
 }
 

@@ -307,7 +307,7 @@ struct SpanWalker {
 __global__ void __launch_bounds__(kMarkThreads)
 raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ mesh, const TriRec* __restrict__ trirec,
                    const int32_t* __restrict__ ntri, uint16_t* __restrict__ loc, unsigned* __restrict__ queue, int H,
-                   int W, int cap, int tcap) {
+                   int W, int cap, int tcap, int tall_cost) {
   const int b = blockIdx.y;
   const int T = ntri[b];
   if (T <= 0) return;  // no mesh for this frame: no starts, the row sweep leaves "no value" everywhere
@@ -360,7 +360,7 @@ raster_mark_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
   for (int cand = kMarkCoopRows; cand >= 8; cand = cand * 3 / 4) {   // 64, 48, 36, 27, 20, 15, 11, 8
     const int above = __popc(__ballot_sync(0xffffffffu, bh > cand));
     const int tallest = __reduce_max_sync(0xffffffffu, bh > cand ? 0 : bh);
-    const int cost = tallest * 45 + above * 300;
+    const int cost = tallest * 45 + above * tall_cost;
     if (cost < best) { best = cost; limit = cand; }
   }
   const bool large = R.live && bh > limit;
@@ -552,6 +552,7 @@ static int locate_raster(const int32_t* pts, const uint16_t* mesh, const void* t
     // lines that left L2 each one costs a 32-byte read-modify-write in DRAM -- measured, that was 40 % of the mark kernel)
     unsigned* queue = static_cast<unsigned*>(workspace);   // [0] = length, [1] = next to take, [4 ...] = (frame << 16 | triangle)
     const size_t frame_px = static_cast<size_t>(H) * W;
+    static const int tall_cost = [] { const char* e = getenv("FOVEA_RAS_TALL_COST"); return e ? atoi(e) : 300; }();
     size_t chunk_mb = 48;
     if (const char* e = getenv("FOVEA_RAS_CHUNK_MB")) chunk_mb = std::min<size_t>(std::max(atoi(e), 1), 4096);
     const int per = static_cast<int>(std::max<size_t>(1, (chunk_mb << 20) / (frame_px * 2)));   // (per * frame_px < 2^32)
@@ -562,7 +563,7 @@ static int locate_raster(const int32_t* pts, const uint16_t* mesh, const void* t
       FOVEA_CUDA(cudaMemsetAsync(queue, 0, 16, s));
       raster_mark_kernel<<<dim3(ceil_div(tcap, kMarkThreads), nb), kMarkThreads, 0, s>>>(
           pts + static_cast<size_t>(b0) * cap, mesh4 + static_cast<size_t>(b0) * tcap, recs + static_cast<size_t>(b0) * tcap,
-          ntri + b0, lc, queue, H, W, cap, tcap);
+          ntri + b0, lc, queue, H, W, cap, tcap, tall_cost);
       raster_mark_tall_kernel<<<kNumSMs * 4, 256, 0, s>>>(
           pts + static_cast<size_t>(b0) * cap, mesh4 + static_cast<size_t>(b0) * tcap, recs + static_cast<size_t>(b0) * tcap,
           ntri + b0, lc, queue, H, W, cap, tcap);
