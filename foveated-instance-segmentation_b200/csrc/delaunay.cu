@@ -504,13 +504,10 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     }
     const int excl = incl - mycnt;
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned cand = 0;  // 2 bits per iteration: 0 = none, else illegal edge slot + 1
-    bool any = deferred;
-    int it = 0;
-    for (int base = 0; base < total; base += 32, ++it) {
-      // triangle of rank base+lane among this warp's dirty bits
-      const int rank = base + lane;
-      // word holding the rank-th dirty bit: smallest lane j with incl_j > rank (binary search by shuffles)
+    // triangle of rank r + lane among this warp's dirty bits: the word holding the rank-th bit is the smallest lane j with
+    // incl_j > rank (binary search by shuffles -- every lane must take part)
+    auto ranked = [&](int r) -> int {
+      const int rank = r + lane;
       int jsel = 0;
 #pragma unroll
       for (int sstep = 16; sstep > 0; sstep >>= 1) {
@@ -520,7 +517,17 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       jsel = min(jsel, 31);
       const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
       const int ex = __shfl_sync(0xffffffffu, excl, jsel);
-      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      return rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+    };
+    int tc0 = -1, tc1 = -1;
+    unsigned cand = 0;  // 2 bits per iteration: 0 = none, else illegal edge slot + 1
+    bool any = deferred;
+    int it = 0;
+    for (int base = 0; base < total; base += 32, ++it) {
+      // triangle of rank base+lane among this warp's dirty bits (kept for the two later passes of this round while it
+      // fits the two cache registers: most rounds have at most 64 dirty triangles per warp)
+      const int t = ranked(base);
+      if (it == 0) tc0 = t; else if (it == 1) tc1 = t;
       if (t < 0) continue;
       const int pa = pts[DT_V(t, 0)], pb = pts[DT_V(t, 1)], pc = pts[DT_V(t, 2)];
       // all three neighbours are fetched and tested together (no early exit): the round's critical path is this
@@ -574,25 +581,16 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     for (int base = 0; base < total; base += 32, ++it) {
       const int sel = (cand >> (2 * it)) & 3;
       if (!__any_sync(0xffffffffu, sel != 0)) continue;  // warp-uniform: the shuffles below need every lane
-      const int rank = base + lane;
-      int jsel = 0;
-#pragma unroll
-      for (int sstep = 16; sstep > 0; sstep >>= 1) {
-        const int v = __shfl_sync(0xffffffffu, incl, jsel + sstep - 1);
-        if (v <= rank) jsel += sstep;
-      }
-      jsel = min(jsel, 31);
-      const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
-      const int ex = __shfl_sync(0xffffffffu, excl, jsel);
-      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      const int t = it == 0 ? tc0 : (it == 1 ? tc1 : ranked(base));
       if (!sel) continue;
       const int k = sel - 1;
-      const unsigned pri = claim_word(tag, t, round);
       const unsigned lt = A.lock[t];
       const unsigned ucode = DT_N(t, k);
       const int u = ucode < kPendingCode ? static_cast<int>(ucode >> 2) : t, ku = ucode & 3;  // (a hull marker is no index)
       const unsigned lu = A.lock[u];
-      if (lt != pri || ucode >= kPendingCode || lu != pri) continue;
+      // both words hold MY claim of this round (the priority bits need not be recomputed: a claim names its proposer)
+      const bool mine = (lt & 0x3FFFu) == static_cast<unsigned>(t) && (lt & (0xFC000000u | kClaimBit)) == (tag | kClaimBit);
+      if (!mine || ucode >= kPendingCode || lu != lt) continue;
       wins |= 1u << it;
       A.lock[t] = tag | static_cast<unsigned>(k << 14) | static_cast<unsigned>(u);
       A.lock[u] = tag | kPostIsU | static_cast<unsigned>(ku << 14) | static_cast<unsigned>(t);
@@ -646,17 +644,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       const bool win = (wins >> it) & 1u;
       const unsigned wm = __ballot_sync(0xffffffffu, win);
       if (!wm) continue;
-      const int rank = base + lane;
-      int jsel = 0;
-#pragma unroll
-      for (int sstep = 16; sstep > 0; sstep >>= 1) {
-        const int v = __shfl_sync(0xffffffffu, incl, jsel + sstep - 1);
-        if (v <= rank) jsel += sstep;
-      }
-      jsel = min(jsel, 31);
-      const unsigned wsel = __shfl_sync(0xffffffffu, myword, jsel);
-      const int ex = __shfl_sync(0xffffffffu, excl, jsel);
-      const int t = rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
+      const int t = it == 0 ? tc0 : (it == 1 ? tc1 : ranked(base));
       const int mine = win ? ((t << 2) | (static_cast<int>((cand >> (2 * it)) & 3) - 1)) : -1;
       const int cnt = __popc(wm);
       const int j = lane - npend;                                   // lanes npend.. take this iteration's winners in order
