@@ -11,10 +11,14 @@
 //                  monotone mountains; they are closed by PARALLEL ear clipping (independent sets of convex chain
 //                  vertices per round), which also yields the hull edges.
 //   4. Lawson    : parallel edge flips with exact int64 in-circle tests until every interior edge is locally
-//                  Delaunay.  Each round every dirty triangle proposes one illegal edge; proposals claim their two
-//                  triangles and the four outer neighbours with a random-priority atomicMin, winners flip.
+//                  Delaunay.  Each round every dirty triangle proposes one illegal edge; proposals claim the two
+//                  triangles the flip rewrites with a random-priority atomicMin, winners flip.  The back links of the
+//                  four outer neighbours -- which a flip re-points and which may be flipping themselves in the same
+//                  round -- go through postings the winners leave in their own lock words (DT_CLAIM2 below; the first
+//                  version claimed all six triangles instead: twice the rounds).
 //                  Random priorities matter: with index priorities the skinny strips serialise (~10^4 rounds on a
-//                  1024^2 frame, ~150 with random ones; measured in the NumPy prototype of this algorithm).
+//                  1024^2 frame, ~150 with random ones and six-triangle claims, ~75 with two; measured in the NumPy
+//                  prototypes of this algorithm, tools/prototypes/dt_claims.py).
 //
 // Exactness: coordinates < 8192 keep the 4th-order in-circle determinant inside int64 (checked on the host).
 // Co-circular point sets (ubiquitous on a pixel lattice) have no unique Delaunay triangulation; any locally
