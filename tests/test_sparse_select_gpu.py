@@ -59,3 +59,19 @@ def test_sparse_plan_with_nan_and_out_of_range_targets(ops):
         n = int(dense.npts[b])
         assert torch.equal(dense.pts[b, :n], sparse.pts[b, :n]) and torch.equal(dense.src[b, :n], sparse.src[b, :n])
     assert torch.equal(dense.loc, sparse.loc)
+
+
+def test_sparse_plan_on_the_yaml_lattice_64x128(ops):
+    """config/deform.yaml:42's (64,128) saliency = 8 196 keys per frame: the 16 384-key sort, the Delaunay kernel's large
+    layout and the marker raster on a 1024 x 2048 canvas, sparse against dense."""
+    B, gh, gw, Rx, Ry, H, W = 2, 64, 128, 15, 30, 1024, 2048
+    xs, _ = rp.synthetic_saliency(B, gh, gw, seed=64)
+    filt, P = rp.gaussian_filter_weight(Rx, Ry, Rx), rp.p_basis(gh, gw, Rx, Ry)
+    grid = rp.create_grid(rp.pad_saliency(xs, Rx, Ry), filt, P, gh, gw, (gh, gw))[0].cuda().float().contiguous()
+    dense = ops.check_plan(ops.build_inverse_plan(grid, (H, W), nchan=3, triangulation="device"))
+    sparse = ops.check_plan(ops.build_inverse_plan(grid, (H, W), nchan=3, triangulation="device", dense_winner=False))
+    assert torch.equal(dense.npts, sparse.npts) and (dense.npts > 6600).all()
+    for b in range(B):
+        n = int(dense.npts[b])
+        assert torch.equal(dense.pts[b, :n], sparse.pts[b, :n]) and torch.equal(dense.src[b, :n], sparse.src[b, :n])
+    assert torch.equal(dense.loc, sparse.loc)
