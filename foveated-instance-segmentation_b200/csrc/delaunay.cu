@@ -523,15 +523,15 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       const int ex = __shfl_sync(0xffffffffu, excl, jsel);
       return rank < total ? DT_WORD(jsel) * 32 + nth_set_bit(wsel, rank - ex) : -1;
     };
-    int tc0 = -1, tc1 = -1;
+    int tc0 = -1, tc1 = -1, tc2 = -1, tc3 = -1;
     unsigned cand = 0;  // 2 bits per iteration: 0 = none, else illegal edge slot + 1
     bool any = deferred;
     int it = 0;
     for (int base = 0; base < total; base += 32, ++it) {
       // triangle of rank base+lane among this warp's dirty bits (kept for the two later passes of this round while it
-      // fits the two cache registers: most rounds have at most 64 dirty triangles per warp)
+      // fits the four cache registers: most rounds have at most 128 dirty triangles per warp)
       const int t = ranked(base);
-      if (it == 0) tc0 = t; else if (it == 1) tc1 = t;
+      if (it == 0) tc0 = t; else if (it == 1) tc1 = t; else if (it == 2) tc2 = t; else if (it == 3) tc3 = t;
       if (t < 0) continue;
       const int pa = pts[DT_V(t, 0)], pb = pts[DT_V(t, 1)], pc = pts[DT_V(t, 2)];
       // all three neighbours are fetched and tested together (no early exit): the round's critical path is this
@@ -585,7 +585,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     for (int base = 0; base < total; base += 32, ++it) {
       const int sel = (cand >> (2 * it)) & 3;
       if (!__any_sync(0xffffffffu, sel != 0)) continue;  // warp-uniform: the shuffles below need every lane
-      const int t = it == 0 ? tc0 : (it == 1 ? tc1 : ranked(base));
+      const int t = it < 4 ? (it == 0 ? tc0 : (it == 1 ? tc1 : (it == 2 ? tc2 : tc3))) : ranked(base);
       if (!sel) continue;
       const int k = sel - 1;
       const unsigned lt = A.lock[t];
@@ -648,7 +648,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       const bool win = (wins >> it) & 1u;
       const unsigned wm = __ballot_sync(0xffffffffu, win);
       if (!wm) continue;
-      const int t = it == 0 ? tc0 : (it == 1 ? tc1 : ranked(base));
+      const int t = it < 4 ? (it == 0 ? tc0 : (it == 1 ? tc1 : (it == 2 ? tc2 : tc3))) : ranked(base);
       const int mine = win ? ((t << 2) | (static_cast<int>((cand >> (2 * it)) & 3) - 1)) : -1;
       const int cnt = __popc(wm);
       const int j = lane - npend;                                   // lanes npend.. take this iteration's winners in order
