@@ -60,24 +60,46 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks + throttle reasons during the timed region."""
+    """Samples SM clocks + throttle reasons during the timed region: through NVML every 2 ms (a timed region is tens of
+    milliseconds), or -- if NVML cannot be loaded -- through nvidia-smi (one query takes ~50 ms)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits: HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+    BITS = (0x8, 0x40, 0x20, 0x4)
 
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.handle))
+        self.samples.append([str(sm), str(self.max_sm)] + ["Active" if mask & b else "Not Active" for b in self.BITS])
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
-                pass
-            self.stop.wait(0.1)
+                if self.nvml is not None:
+                    self.nvml = None      # fall back to nvidia-smi for the rest of the region
+            self.stop.wait(0.002 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.t.start()
@@ -95,7 +117,7 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self.handle is not None and self.nvml is not None else "nvidia-smi"}
 
 
 def synthetic_saliency(B, gh=80, gw=80, seed=0):
