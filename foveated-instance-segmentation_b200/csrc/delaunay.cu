@@ -161,6 +161,9 @@ __device__ __forceinline__ unsigned claim_word(unsigned tag, int t, int round) {
 #ifndef DT_MAXNREG
 #define DT_MAXNREG 64   // (48 would let one inverse_fill CTA co-reside per SM under the pipelined schedule: measured, no gain)
 #endif
+// kBig: claims and dirty bits in global memory (lock_g); otherwise everything is shared memory and the template keeps
+// the compiler's address-space inference intact (LDS / STS / ATOMS instead of generic LD / ST / ATOM).
+template <bool kBig>
 __global__ void __maxnreg__(DT_MAXNREG)
 delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ npts, int cap, int tcap,
                 uint16_t* __restrict__ mesh_out, int32_t* __restrict__ ntri_out, int32_t* __restrict__ rounds_out,
@@ -185,7 +188,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     A.n0 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
     A.n1 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
     A.n2 = reinterpret_cast<unsigned short*>(p); p += 2 * tcap;
-    if (lock_g) {  // large site sets (e.g. the 64 x 128 lattice): claims and dirty bits live in global memory (L2), the
+    if (kBig) {  // large site sets (e.g. the 64 x 128 lattice): claims and dirty bits live in global memory (L2), the
                    // mesh itself and the points still fit one CTA's shared memory
       A.lock = lock_g + static_cast<size_t>(b) * (tcap + (tcap + 31) / 32);
       A.dirty = A.lock + tcap;
@@ -240,6 +243,15 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     return;
   }
 
+  // The row starts are read by every binary search of the strips and every ear test of the pockets: when they fit, they
+  // move from the global workspace into the unused upper half of a scratch array (each array holds `cap` entries, the
+  // construction uses the first R of them).
+  if (!kBig && R + 1 <= cap - cap / 2) {
+    unsigned short* rs = A.stripBase + cap / 2;
+    for (int i = tid; i <= R; i += kDtThreads) rs[i] = A.rowStart[i];
+    __syncthreads();
+    A.rowStart = rs;
+  }
   if (dbg && tid == 0) dbg[b * 8 + 1] = (int)((clock64() - clk0) >> 4);
   // ------------------------------------------------------------------ 2. strips
   const int nstrips = R - 1;
@@ -334,8 +346,8 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
 
   if (dbg && tid == 0) dbg[b * 8 + 2] = (int)((clock64() - clk0) >> 4);
   // ------------------------------------------------------------------ 3. pockets (left, then right)
-  // cprev[m]: bits 0..12 = previous alive chain vertex (kCNone = chain start), bit 13 DEAD, bit 14 SELECTED, bit 15 EAR
-  constexpr unsigned kCIdx = 0x1FFFu, kCNone = 0x1FFFu, kCDead = 0x2000u, kCSel = 0x4000u, kCEar = 0x8000u;
+  // cprev[m]: bits 0..12 = previous alive chain vertex (kCNone = chain start), bit 13 DEAD
+  constexpr unsigned kCIdx = 0x1FFFu, kCNone = 0x1FFFu, kCDead = 0x2000u;
   int ntri_run = nstrip_tris;  // triangles so far (identical in every thread)
   bool converged = true;       // false: a safety bound ended a loop early (block-uniform) -> the frame reports no mesh
   for (int side = 0; side < 2; ++side) {
@@ -353,47 +365,40 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
     bool closed = false;
     for (int round = 0; round < 4 * R + 64; ++round) {
       if (dbg && tid == 0) dbg[b * 8 + 4 + side] = round;
-      // phase 1: which alive interior chain vertices are ears (strictly convex towards the pocket)?
-      for (int m = tid; m < R; m += kDtThreads) {
+      // phase 1: an alive interior chain vertex is an EAR if it is strictly convex towards the pocket; an ear is selected
+      // iff it beats both neighbouring ears (random priority: an independent set).  One pass: every thread also tests
+      // its two neighbours (two more orientation tests, but no barrier between "which are ears" and "who wins"), and
+      // keeps its selections in registers.  Nothing is written in this phase.
+      auto is_ear = [&](unsigned pv, unsigned m, unsigned nx) {
+        if (pv == kCNone || nx == kCNone) return false;
+        const long long o = orient_pts(pts[cpt(pv)], pts[cpt(m)], pts[cpt(nx)]);
+        return side == 0 ? (o > 0) : (o < 0);
+      };
+      unsigned selmask = 0;   // bit i: my i-th chain vertex (m = tid + i * kDtThreads) is clipped this round
+      int mysel = 0, si = 0;
+      for (int m = tid; m < R; m += kDtThreads, ++si) {
         const unsigned cp = A.cprev[m];
         if (cp & kCDead) continue;
         const unsigned pv = cp & kCIdx, nx = A.cnext[m];
-        bool ear = false;
-        if (pv != kCNone && nx != kCNone) {
-          const long long o = orient_pts(pts[cpt(pv)], pts[cpt(m)], pts[cpt(nx)]);
-          ear = side == 0 ? (o > 0) : (o < 0);
-        }
-        A.cprev[m] = static_cast<unsigned short>(pv | (ear ? kCEar : 0u));
-      }
-      __syncthreads();
-      // phase 2a: independent set -- an ear is selected iff it beats both neighbouring ears (random priority)
-      bool selected_any = false;
-      for (int m = tid; m < R; m += kDtThreads) {
-        const unsigned cp = A.cprev[m];
-        if ((cp & kCDead) || !(cp & kCEar)) continue;
-        const unsigned pv = cp & kCIdx, nx = A.cnext[m];
+        if (!is_ear(pv, m, nx)) continue;
         const unsigned pri = cpri(m, round);
-        const unsigned cpp = A.cprev[pv], cpn = A.cprev[nx];
-        if ((cpp & kCEar) && cpri(pv, round) < pri) continue;
-        if ((cpn & kCEar) && cpri(nx, round) < pri) continue;
-        selected_any = true;
-        A.cprev[m] = static_cast<unsigned short>(cp | kCSel);
+        if (cpri(pv, round) < pri && is_ear(A.cprev[pv] & kCIdx, pv, m)) continue;
+        if (cpri(nx, round) < pri && is_ear(m, nx, A.cnext[nx])) continue;
+        selmask |= 1u << si;
+        ++mysel;
       }
-      if (!__syncthreads_or(selected_any)) { closed = true; break; }
-      // phase 2b: clip the selected ears (their neighbours are not selected, so the list surgery is race-free).
+      // phase 2: clip the selected ears (their neighbours are not selected, so the list surgery is race-free).
       // Triangle ids come from a block scan over the selected ears, not from an atomic counter: the numbering -- and
       // with it the flip priorities and the final choice among co-circular alternatives -- is the same on every run.
-      int mysel = 0;
-      for (int m = tid; m < R; m += kDtThreads) {
-        const unsigned cp = A.cprev[m];
-        if (!(cp & kCDead) && (cp & kCSel)) ++mysel;
-      }
+      // (The scan's barriers also separate the reads above from the writes below.)
       int nsel;
       int E_next = ntri_run + block_scan_excl(mysel, warp_sums, nsel);
+      if (nsel == 0) { closed = true; break; }
       ntri_run += nsel;
-      for (int m = tid; m < R; m += kDtThreads) {
+      si = 0;
+      for (int m = tid; m < R; m += kDtThreads, ++si) {
+        if (!((selmask >> si) & 1u)) continue;
         const unsigned cp = A.cprev[m];
-        if ((cp & kCDead) || !(cp & kCSel)) continue;
         const int pv = cp & kCIdx, nx = A.cnext[m];
         const int E = E_next++;
         const int P = cpt(pv), M = cpt(m), N = cpt(nx);
@@ -955,7 +960,8 @@ static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int c
     set_error("%s: %zu B of shared memory needed for cap=%d (> 227 KB); use the host triangulation", who, smem, cap);
     return FOVEA_ERR_CAPACITY;
   }
-  FOVEA_CUDA(cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  FOVEA_CUDA(cudaFuncSetAttribute(big ? delaunay_kernel<true> : delaunay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
   // safety bound on the flip rounds (worst frame seen: ~310); FOVEA_DT_MAX_ROUNDS lowers it to exercise the
   // non-convergence report in the tests
   int max_rounds = 20000;
@@ -963,7 +969,11 @@ static int launch_delaunay(const int32_t* pts, const int32_t* npts, int B, int c
   int32_t* ws32 = static_cast<int32_t*>(workspace);
   unsigned short* row_ws = reinterpret_cast<unsigned short*>(ws32 + 9 * B);
   unsigned* lock_g = big ? reinterpret_cast<unsigned*>(ws32 + 9 * B + (static_cast<size_t>(B) * (cap + 2) * 2 + 3) / 4) : nullptr;
-  delaunay_kernel<<<B, kDtThreads, smem, stream>>>(pts, npts, cap, tk, mesh, ntri, ws32, max_rounds, ws32 + B, row_ws, hints, H,
+  if (big)
+    delaunay_kernel<true><<<B, kDtThreads, smem, stream>>>(pts, npts, cap, tk, mesh, ntri, ws32, max_rounds, ws32 + B, row_ws, hints, H,
+                                                   W, tcap, lock_g);
+  else
+    delaunay_kernel<false><<<B, kDtThreads, smem, stream>>>(pts, npts, cap, tk, mesh, ntri, ws32, max_rounds, ws32 + B, row_ws, hints, H,
                                                    W, tcap, lock_g);
   return check_launch(who);
 }

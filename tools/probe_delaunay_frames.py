@@ -35,6 +35,8 @@ for b in list(order[:6]) + list(order[-3:]):
     print(f"{b:5d} {npts[b]:6d} {rounds[b]:6d} {rows[b]:6.1f} {strips[b]-rows[b]:6.1f} {pockets[b]-strips[b]:7.1f} {tot[b]-pockets[b]:7.1f} {tot[b]:7.1f}")
 print(f"mean: rounds {rounds.mean():.1f}  construction {pockets.mean():.1f} us  flips {(tot-pockets).mean():.1f} us  total {tot.mean():.1f} us;"
       f"  sum over frames {tot.sum()/1e3:.2f} SM-ms; max {tot.max():.1f} us")
+print(f"pocket rounds (ear-clipping rounds of the left / right side): mean {dbg[:, 4].mean():.1f} / {dbg[:, 5].mean():.1f}, max {dbg[:, 4].max()} / {dbg[:, 5].max()};"
+      f"  pockets {(pockets - strips).mean():.1f} us on average")
 if prof:
     b = int(np.argmax(rounds))
     o = 9 * B + B * (plan.cap + 2) // 2
