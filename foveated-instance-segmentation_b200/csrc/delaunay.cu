@@ -85,6 +85,24 @@ __device__ __forceinline__ int nth_set_bit(unsigned w, int n) {
   return pos;
 }
 
+// The same scan with ONE barrier: every warp sums the totals of the warps before it itself (and all 32 for `total`).
+// The caller must put a barrier between two calls (warp_sums is rewritten by the next one).
+__device__ __forceinline__ int block_scan_excl_1bar(int v, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  const int w = warp_sums[lane];                       // (kDtThreads = 1024: exactly 32 warps)
+  total = __reduce_add_sync(0xffffffffu, w);
+  const int before = __reduce_add_sync(0xffffffffu, lane < warp ? w : 0);
+  return before + incl - v;
+}
+
 // exclusive block scan of one int per thread; returns the exclusive prefix, `total` = block sum
 __device__ int block_scan_excl(int v, int* warp_sums, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -392,7 +410,7 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
       // with it the flip priorities and the final choice among co-circular alternatives -- is the same on every run.
       // (The scan's barriers also separate the reads above from the writes below.)
       int nsel;
-      int E_next = ntri_run + block_scan_excl(mysel, warp_sums, nsel);
+      int E_next = ntri_run + block_scan_excl_1bar(mysel, warp_sums, nsel);   // (the round ends with a barrier)
       if (nsel == 0) { closed = true; break; }
       ntri_run += nsel;
       si = 0;
