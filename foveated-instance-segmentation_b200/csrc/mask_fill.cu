@@ -179,7 +179,10 @@ triangle_candidates_kernel(const TriRec* __restrict__ trirec, const int32_t* __r
 }
 
 constexpr int kMaskThreads = 256;
-constexpr int kMaskWL = 16;  // the fill's mapping: a warp covers 64 px x 2 rows, a thread 4 consecutive pixels
+#ifndef FOVEA_MASK_WL
+#define FOVEA_MASK_WL 16
+#endif
+constexpr int kMaskWL = FOVEA_MASK_WL;  // lanes of a warp across a row (x 4 pixels each): 16 = the fill's mapping, 64 px x 2 rows
 
 __device__ __forceinline__ float interp3(float a, float b, float c, float w0, float w1, float w2) {
   // interp2d.py:85-89 as fill_tile evaluates it: three products, summed in vertex order, every step rounded
