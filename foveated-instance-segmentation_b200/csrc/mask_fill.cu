@@ -179,10 +179,14 @@ triangle_candidates_kernel(const TriRec* __restrict__ trirec, const int32_t* __r
 }
 
 constexpr int kMaskThreads = 256;
+// Lanes of a warp across a row (x 4 pixels each).  The candidate loop runs to the longest list among the warp's
+// triangles, so a compact footprint (fewer triangles per warp) is worth more here than the long row segments the
+// store-bound score fill wants: pruned mask fill on N(0,1) predictions 1.197 / 1.155 / 1.099 / 1.122 ms for
+// WL = 16 / 8 / 4 / 2 (64 x 2, 32 x 4, 16 x 8, 8 x 16 pixels per warp).
 #ifndef FOVEA_MASK_WL
-#define FOVEA_MASK_WL 16
+#define FOVEA_MASK_WL 4
 #endif
-constexpr int kMaskWL = FOVEA_MASK_WL;  // lanes of a warp across a row (x 4 pixels each): 16 = the fill's mapping, 64 px x 2 rows
+constexpr int kMaskWL = FOVEA_MASK_WL;
 
 __device__ __forceinline__ float interp3(float a, float b, float c, float w0, float w1, float w2) {
   // interp2d.py:85-89 as fill_tile evaluates it: three products, summed in vertex order, every step rounded
