@@ -174,6 +174,7 @@ __device__ __forceinline__ void link_back(const DtArrays& A, unsigned code, unsi
 // of the pair, [15:14] this triangle's slot of the old diagonal, [13:0] its partner.
 constexpr unsigned kClaimBit = 1u << 25, kPostIsU = 1u << 16;
 __device__ __forceinline__ unsigned claim_word(unsigned tag, int t, int round) {
+  // (a cheaper two-multiplication hash was tried: same time, more rounds on the slowest frames)
   return tag | kClaimBit | ((hash32(t * 2654435761u + round * 0x9E3779B9u) & 0x7FFu) << 14) | static_cast<unsigned>(t);
 }
 #ifndef DT_MAXNREG
@@ -513,11 +514,14 @@ delaunay_kernel(const int32_t* __restrict__ pts_g, const int32_t* __restrict__ n
 #ifndef DT_DENSE
 #define DT_DENSE 32  // a word is dense when more than this many of its 32 triangles are dirty (32: no thinning)
 #endif
-      const bool dense = __popc(w) > DT_DENSE;
-      const unsigned h = hash32(DT_WORD(lane) * 0x9E3779B9u + round * 0x85EBCA6Bu);
-      const unsigned keep = DT_THIN == 2 ? h : (DT_THIN == 4 ? (h & hash32(h)) : (h & hash32(h) & hash32(h ^ 0x5bd1e995u)));
-      myword = dense ? (w & keep) : w;
-      if (dense && myword == 0u) myword = w & (0u - w);  // keep at least one (lowest) bit so progress is guaranteed
+      myword = w;
+      if (DT_DENSE < 32) {   // (compile-time: no thinning with the default)
+        const bool dense = __popc(w) > DT_DENSE;
+        const unsigned h = hash32(DT_WORD(lane) * 0x9E3779B9u + round * 0x85EBCA6Bu);
+        const unsigned keep = DT_THIN == 2 ? h : (DT_THIN == 4 ? (h & hash32(h)) : (h & hash32(h) & hash32(h ^ 0x5bd1e995u)));
+        if (dense) myword = w & keep;
+        if (dense && myword == 0u) myword = w & (0u - w);  // keep at least one (lowest) bit so progress is guaranteed
+      }
       A.dirty[DT_WORD(lane)] = w & ~myword;
       deferred = (w & ~myword) != 0u;  // unselected dirty triangles: the loop must not terminate this round
     }
