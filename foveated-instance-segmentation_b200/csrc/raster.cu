@@ -225,6 +225,9 @@ raster_span_kernel(const int32_t* __restrict__ pts, const uint4* __restrict__ me
 // instead of one per row); ~35 lane-instructions and one 2-byte store per (triangle, row), against ~8 per PIXEL tested by
 // the sweep.
 constexpr int kMarkCoopRows = 64;   // taller triangles are ALWAYS taken by the whole warp, rows strided by 32 (direct divisions)
+#ifndef FOVEA_TALL_CTAS
+#define FOVEA_TALL_CTAS 4   // CTAs per SM of raster_mark_tall_kernel's grid (2 / 4 / 8 measured: flat)
+#endif
 constexpr int kMarkThreads = 128;   // (<= 256: the sorted order is kept in bytes)
 
 __device__ __forceinline__ void mark_start(uint16_t* loc, unsigned lin, unsigned id) {   // lin: pixel index in the chunk (< 2^32)
@@ -564,7 +567,7 @@ static int locate_raster(const int32_t* pts, const uint16_t* mesh, const void* t
       raster_mark_kernel<<<dim3(ceil_div(tcap, kMarkThreads), nb), kMarkThreads, 0, s>>>(
           pts + static_cast<size_t>(b0) * cap, mesh4 + static_cast<size_t>(b0) * tcap, recs + static_cast<size_t>(b0) * tcap,
           ntri + b0, lc, queue, H, W, cap, tcap, tall_cost);
-      raster_mark_tall_kernel<<<kNumSMs * 4, 256, 0, s>>>(
+      raster_mark_tall_kernel<<<kNumSMs * FOVEA_TALL_CTAS, 256, 0, s>>>(
           pts + static_cast<size_t>(b0) * cap, mesh4 + static_cast<size_t>(b0) * tcap, recs + static_cast<size_t>(b0) * tcap,
           ntri + b0, lc, queue, H, W, cap, tcap);
       const long long rows = static_cast<long long>(nb) * H;
