@@ -7,7 +7,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "foveated-instance-segmentation_b200")]
 import bench
 from fovea import ops, _lib
 from fovea.pipeline import DevicePipeline
-cfg = dict(bench.WORKLOADS["b64_1024"]); dev = torch.device("cuda", 0)
+wl = sys.argv[1] if len(sys.argv) > 1 else "b64_1024"
+cfg = dict(bench.WORKLOADS[wl]); dev = torch.device("cuda", 0)
 B, C, H, W = (cfg[k] for k in "BCHW")
 x, xs, pred = bench.make_inputs(cfg, 0, device=dev)
 scores = torch.empty(B, C, H, W, device=dev)
@@ -21,7 +22,7 @@ def call(name, *a):
     if name in dup: real_call(name, *a)
     return r
 _lib.call = call; ops._lib.call = call
-def measure(n=20):
+def measure(n=20 if wl == "b64_1024" else 16):
     for _ in range(4): pipe.submit(x, xs, pred)
     pipe.fence(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
